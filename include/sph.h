@@ -1,0 +1,167 @@
+/*
+ * sph.h — C ABI of the B200-native SPH fluid-step engine (libsalva_b200.so).
+ *
+ * This is the drop-in boundary for salva3d's solver path: every entry point
+ * below is what a Rust `salva3d`-compatible shim binds over FFI in place of the
+ * reference's in-process Rust implementation.  The reference interface each
+ * entry point replaces is cited as  <file>:<line>  relative to the reference
+ * tree (dimforge/salva @ 7eecdfb).
+ *
+ * Conventions
+ *   - extern "C", no exceptions cross the boundary, no torch/CUDA types.
+ *   - All pointers are caller-owned HOST memory, copied during the call; the
+ *     library never retains them.  Vectors are tightly packed xyz f32 triples
+ *     (the memory layout of Vec<Point3<f32>> / Vec<Vector3<f32>>).
+ *   - A world has one logical owner (matches `&mut self`); calls on one world
+ *     must be externally serialised; different worlds are independent.
+ *   - Errors: every call returns an sph_status; sph_last_error() gives text.
+ *     Reference `assert!`/panic sites map to SPH_ERR_ZERO_DENSITY /
+ *     SPH_ERR_INVALID; the Rust shim turns them back into panics.
+ *   - There is NO CPU fallback: without a CUDA device sph_world_create fails
+ *     with SPH_ERR_CUDA.
+ */
+#ifndef SALVA_B200_SPH_H
+#define SALVA_B200_SPH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sph_world sph_world;
+
+typedef enum {
+    SPH_OK = 0,
+    SPH_ERR_INVALID = 1,      /* bad argument / bad handle / reference assert (contacts.rs:165) */
+    SPH_ERR_CUDA = 2,         /* CUDA runtime failure, or no device */
+    SPH_ERR_OOM = 3,          /* device allocation failed / grid too large */
+    SPH_ERR_NCCL = 4,         /* multi-GPU exchange failure */
+    SPH_ERR_ZERO_DENSITY = 5  /* reference asserts dfsph_solver.rs:92,145,662 */
+} sph_status;
+
+/* Pressure solver selection: LiquidWorld::new(solver, ..) liquid_world.rs:39-57 */
+enum { SPH_SOLVER_DFSPH = 0,  /* DFSPHSolver::new()  dfsph_solver.rs:54-70 */
+       SPH_SOLVER_IISPH = 1   /* IISPHSolver::new()  iisph_solver.rs:48-64 */ };
+
+/* Built-in NonPressureForce kinds (trait: solver/nonpressure_force.rs:10-30). */
+enum { SPH_FORCE_XSPH_VISCOSITY = 0,        /* p[0]=fluid coeff, p[1]=boundary coeff   xsph_viscosity.rs:19-26 */
+       SPH_FORCE_ARTIFICIAL_VISCOSITY = 1,  /* p[0]=fluid coeff, p[1]=boundary coeff, p[2]=alpha, p[3]=beta,
+                                               p[4]=speed_of_sound                      artificial_viscosity.rs:27-38 */
+       SPH_FORCE_AKINCI2013_TENSION = 2,    /* p[0]=tension coeff, p[1]=adhesion coeff akinci2013_surface_tension.rs:27-35 */
+       SPH_FORCE_BECKER2009_ELASTICITY = 3  /* p[0]=young, p[1]=poisson, p[2]=nonlinear becker2009_elasticity.rs:60-76 */ };
+
+typedef struct {
+    int32_t  solver;                 /* SPH_SOLVER_* */
+    float    particle_radius;        /* liquid_world.rs:41 */
+    float    smoothing_factor;       /* h = r * sf * 2   liquid_world.rs:44 */
+    uint32_t min_pressure_iter;      /* 1   dfsph_solver.rs:56 / iisph_solver.rs:50 */
+    uint32_t max_pressure_iter;      /* 50 */
+    float    max_density_error;      /* 0.05 */
+    uint32_t min_divergence_iter;    /* 1   dfsph_solver.rs:59 (DFSPH only) */
+    uint32_t max_divergence_iter;    /* 50 */
+    float    max_divergence_error;   /* 0.1 */
+    float    omega;                  /* 0.5  iisph_solver.rs:53 (IISPH only) */
+    int32_t  device;                 /* CUDA device ordinal for this world (this rank's GPU) */
+    int32_t  slab_rank;              /* multi-GPU slab decomposition along x: this world's slab index ... */
+    int32_t  slab_count;             /* ... of slab_count slabs (1 = single GPU) */
+    int32_t  deterministic;          /* 1: stable in-cell ordering => bit-reproducible run to run */
+} sph_world_desc;
+
+typedef struct {
+    int32_t kind;                    /* SPH_FORCE_* */
+    float   p[8];
+} sph_force_desc;
+
+/* Per-step statistics; supersedes the reference's wall-clock Counters
+ * (counters/mod.rs:17-30) with CUDA-event timings, and exposes the iteration
+ * counts the reference only has as commented println! (dfsph_solver.rs:449-452). */
+typedef struct {
+    float    step_ms;                /* counters.step_time */
+    float    grid_ms;                /* cd.grid_insertion_time: cell hash + counting sort + reorder */
+    float    neighbors_ms;           /* cd.neighborhood_search_time: neighbour-list build */
+    float    density_ms;             /* evaluate_kernels + compute_densities + compute_alphas */
+    float    divergence_ms;          /* divergence_solve */
+    float    nonpressure_ms;         /* solver.non_pressure_resolution_time */
+    float    pressure_ms;            /* pressure_solve (the roofline-capture region) */
+    float    integrate_ms;
+    uint32_t n_divergence_iter;      /* velocity-change updates executed in divergence_solve */
+    uint32_t n_pressure_iter;        /* velocity-change updates executed in pressure_solve */
+    uint32_t n_divergence_eval;      /* compute_divergences launches */
+    uint32_t n_pressure_eval;        /* compute_predicted_densities / compute_next_pressures launches */
+    float    last_divergence_error;
+    float    last_density_error;
+    uint64_t n_fluid_particles;
+    uint64_t n_boundary_particles;
+    uint64_t n_contacts;             /* cd.ncontacts: ff + fb + bb */
+    uint32_t max_neighbors;          /* widest fluid neighbour list this step */
+    uint32_t grid_dims[3];
+    uint64_t kernel_launches;        /* CUDA kernels launched by this step */
+} sph_step_stats;
+
+/* sph_debug_read() selectors: solver scratch in ORIGINAL particle order. */
+enum { SPH_DBG_DENSITY = 0,            /* densities            dfsph_solver.rs:41  */
+       SPH_DBG_ALPHA = 1,              /* alphas               dfsph_solver.rs:40  */
+       SPH_DBG_DIVERGENCE = 2,         /* divergences          dfsph_solver.rs:43  */
+       SPH_DBG_PREDICTED_DENSITY = 3,  /* predicted_densities  dfsph_solver.rs:42  */
+       SPH_DBG_VELOCITY_CHANGE = 4,    /* velocity_changes (3 floats/particle) dfsph_solver.rs:44 */
+       SPH_DBG_NUM_FLUID_CONTACTS = 5, /* len(ff list) as float, self included contacts.rs:83-87 */
+       SPH_DBG_NUM_BOUNDARY_CONTACTS = 6,
+       SPH_DBG_PRESSURE = 7,           /* IISPH pressures      iisph_solver.rs:37  */
+       SPH_DBG_ACCELERATION = 8        /* fluid.accelerations (3 floats/particle), after forces, before integrate */ };
+
+/* LiquidWorld::new  liquid_world.rs:39-57 */
+void       sph_world_desc_default(sph_world_desc* desc);
+sph_status sph_world_create(const sph_world_desc* desc, sph_world** out);
+void       sph_world_destroy(sph_world* w);
+
+/* LiquidWorld::add_fluid liquid_world.rs:161 + Fluid::new fluid.rs:40-68.
+ * volumes == NULL -> 0.8*(2r)^3 (fluid.rs:110-120); vel == NULL -> zeros. */
+sph_status sph_fluid_add(sph_world* w, const float* pos_xyz, const float* vel_xyz, const float* volumes,
+                         size_t n, float density0, uint32_t memberships, uint32_t filter, uint32_t* handle);
+/* fluid.nonpressure_forces.push(..)  fluid.rs:14; forces run in push order (dfsph_solver.rs:590). */
+sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid, const sph_force_desc* force);
+/* Fluid::add_particles fluid.rs:126-150 */
+sph_status sph_fluid_append(sph_world* w, uint32_t fluid, const float* pos_xyz, const float* vel_xyz, size_t n);
+/* Fluid::delete_particle_at_next_timestep fluid.rs:71-76; applied at the next step (fluid.rs:88-98). */
+sph_status sph_fluid_delete(sph_world* w, uint32_t fluid, const uint8_t* mask, size_t n);
+/* Host-side edits between steps through fluids_mut() (liquid_world.rs:186-188). NULL = leave unchanged. */
+sph_status sph_fluid_write(sph_world* w, uint32_t fluid, const float* pos_xyz, const float* vel_xyz, size_t n);
+/* Reads fluid.positions / fluid.velocities in ORIGINAL index order. NULL = skip. */
+sph_status sph_fluid_read(sph_world* w, uint32_t fluid, float* pos_xyz, float* vel_xyz, size_t cap, size_t* n);
+sph_status sph_fluid_count(sph_world* w, uint32_t fluid, size_t* n);
+
+/* LiquidWorld::add_boundary liquid_world.rs:166 + Boundary::new boundary.rs:28-46.
+ * want_forces != 0  <=>  boundary.forces = Some(..) (boundary.rs:21). */
+sph_status sph_boundary_add(sph_world* w, const float* pos_xyz, const float* vel_xyz, size_t n,
+                            uint32_t memberships, uint32_t filter, int want_forces, uint32_t* handle);
+/* CouplingManager::update_boundaries rewriting boundary particles (coupling_manager.rs:12-20). */
+sph_status sph_boundary_write(sph_world* w, uint32_t boundary, const float* pos_xyz, const float* vel_xyz, size_t n);
+/* boundary.forces read by CouplingManager::transmit_forces (coupling_manager.rs:22-27). */
+sph_status sph_boundary_read_forces(sph_world* w, uint32_t boundary, float* f_xyz, size_t cap);
+/* boundary.volumes after compute_boundary_volumes (dfsph_solver.rs:72-96). */
+sph_status sph_boundary_read_volumes(sph_world* w, uint32_t boundary, float* volumes, size_t cap);
+
+/* LiquidWorld::step  liquid_world.rs:62-158 */
+sph_status sph_world_step(sph_world* w, float dt, const float gravity[3]);
+/* Parity/bench aid: run exactly this many velocity-change updates in the next steps'
+ * divergence / pressure loops instead of the error-driven break (negative = free running). */
+sph_status sph_world_force_iterations(sph_world* w, int32_t n_divergence, int32_t n_pressure);
+sph_status sph_world_stats(sph_world* w, sph_step_stats* out);
+/* LiquidWorld::h / particle_radius  liquid_world.rs:201-208 */
+float      sph_world_h(const sph_world* w);
+float      sph_world_particle_radius(const sph_world* w);
+sph_status sph_debug_read(sph_world* w, uint32_t fluid, int what, float* out, size_t cap);
+const char* sph_last_error(const sph_world* w);
+const char* sph_version(void);
+
+/* Multi-GPU (one process per GPU).  The slab world of rank r exchanges its one-cell ghost
+ * columns with ranks r-1 / r+1 through NCCL; the host passes an already-initialised
+ * ncclComm_t (as void*) created by its own plumbing (torch.distributed / ncclCommInitRank). */
+sph_status sph_world_attach_nccl(sph_world* w, void* nccl_comm, int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALVA_B200_SPH_H */

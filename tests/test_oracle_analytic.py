@@ -1,0 +1,90 @@
+"""Pins the CPU oracle against analytic known answers derived from the reference's formulas
+(SURVEY.md Appendix B).  The reference ships no golden vectors for this path (PARITY UNPINNED
+upstream), so these closed-form values are the first anchor of the oracle."""
+import numpy as np
+import pytest
+
+from oracle.oracle import OracleWorld, lib
+from salva_b200 import scenes
+
+
+def test_kernel_w0_and_normalisation():
+    L = lib()
+    for h in (0.2, 0.1):
+        w0 = L.orc_kernel_w(0.0, h)
+        assert w0 == pytest.approx(8.0 / (np.pi * h ** 3), rel=1e-6)  # W(0) = sigma (Appendix B: 318.3099 / 2546.479)
+        # integral of W over the ball of radius h equals 1 (cubic_spline_kernel.rs normaliser 8/(pi h^3))
+        r = (np.arange(20000) + 0.5) * (h / 20000)
+        w = np.array([L.orc_kernel_w(float(x), h) for x in r[::20]])
+        integral = np.sum(4 * np.pi * r[::20] ** 2 * w) * (h / 1000)
+        assert integral == pytest.approx(1.0, rel=2e-3)
+    assert L.orc_kernel_w(0.0, 0.2) == pytest.approx(318.3099, rel=1e-6)
+    assert L.orc_kernel_w(0.0, 0.1) == pytest.approx(2546.479, rel=1e-6)
+
+
+def test_kernel_derivative_matches_finite_difference():
+    L = lib()
+    h = 0.2
+    for r in (0.01, 0.05, 0.099, 0.101, 0.15, 0.19):
+        fd = (L.orc_kernel_w(r + 1e-4, h) - L.orc_kernel_w(r - 1e-4, h)) / 2e-4
+        assert L.orc_kernel_dw(r, h) == pytest.approx(fd, rel=2e-2, abs=1e-1)
+    assert L.orc_kernel_dw(0.0, h) == 0.0          # q <= 1e-5  -> 0
+    assert L.orc_kernel_dw(0.2000001 * 1.01, h) == 0.0  # q > 1 -> 0
+
+
+@pytest.mark.parametrize("r,alpha_expected", [(0.05, 3.677856e-8), (0.025, 9.194639e-9)])
+def test_rest_lattice_interior_particle(r, alpha_expected):
+    """Interior particle of an unjittered cubic lattice: rho = 0.79998 rho0, 33 contacts incl. self
+    (27 strictly inside + 6 at exactly d == h, up to rounding), alpha as tabulated in Appendix B."""
+    n = 9
+    pts = scenes.block_lattice(n, n, n, r)
+    w = OracleWorld(r, 2.0)
+    f = w.add_fluid(pts, density0=1000.0)
+    w.force_iterations(0, 0)
+    w.step(1.0 / 200.0, gravity=(0.0, 0.0, 0.0))
+    centre = (n // 2) * n * n + (n // 2) * n + (n // 2)
+    dens = w.debug(f, "density")
+    alpha = w.debug(f, "alpha")
+    cnt = w.debug(f, "num_fluid_contacts")
+    assert dens[centre] == pytest.approx(799.978, rel=2e-5)
+    assert 27 <= cnt[centre] <= 33  # the six d == h pairs are accepted or not by f32 rounding
+    assert alpha[centre] == pytest.approx(alpha_expected, rel=2e-4)
+
+
+def test_momentum_conservation_of_pressure_solve():
+    """The fluid-fluid pair terms of compute_velocity_changes are antisymmetric (dfsph_solver.rs:237-255):
+    sum_i m_i * vc_i is unchanged by the pressure loop when there are no boundaries and no gravity."""
+    r = 0.05
+    rng = np.random.default_rng(3)
+    pts = scenes.jitter(scenes.block_lattice(8, 8, 8, r * 0.9), r, 7)  # compressed lattice => positive pressure
+    vel = rng.normal(0, 0.05, pts.shape).astype(np.float32)
+    w = OracleWorld(r, 2.0)
+    f = w.add_fluid(pts, density0=1000.0, velocities=vel)
+    w.force_iterations(2, 3)
+    w.step(1.0 / 200.0, gravity=(0.0, 0.0, 0.0))
+    p, v = w.read_fluid(f)
+    vc = w.debug(f, "velocity_change")
+    mom0 = vel.astype(np.float64).sum(axis=0)
+    mom1 = (v.astype(np.float64) + vc.astype(np.float64)).sum(axis=0)
+    assert np.abs(vc).max() > 1e-4  # the solve did something
+    assert np.allclose(mom0, mom1, atol=2e-3 * np.abs(v).sum())
+
+
+def test_first_step_has_zero_inv_dt():
+    """timestep_manager.rs:29-30 + dfsph_solver.rs:702: dt/inv_dt are 0 until advance() mid-step, so XSPH
+    contributes nothing on the very first step (xsph_viscosity.rs:92-93)."""
+    r = 0.05
+    pts = scenes.jitter(scenes.block_lattice(6, 6, 6, r), r, 11)
+    vel = np.random.default_rng(0).normal(0, 0.1, pts.shape).astype(np.float32)
+    a = OracleWorld(r, 2.0)
+    fa = a.add_fluid(pts, velocities=vel)
+    a.push_force(fa, *scenes.xsph_viscosity(0.5, 0.0))
+    b = OracleWorld(r, 2.0)
+    fb = b.add_fluid(pts, velocities=vel)
+    for w in (a, b):
+        w.force_iterations(1, 1)
+        w.step(0.005)
+    assert np.array_equal(a.debug(fa, "acceleration"), b.debug(fb, "acceleration"))
+    a.step(0.005)
+    b.step(0.005)
+    assert not np.array_equal(a.debug(fa, "acceleration"), b.debug(fb, "acceleration"))

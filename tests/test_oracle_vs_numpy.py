@@ -1,0 +1,73 @@
+"""Pins oracle/oracle.cpp (hash grid + contact lists) against the independent dense-matrix numpy
+restatement (oracle/numpy_ref.py) on small random scenes with boundaries, several fluids and forces."""
+import numpy as np
+import pytest
+
+from oracle.numpy_ref import NumpyDFSPH
+from oracle.oracle import OracleWorld
+from salva_b200 import scenes
+
+
+def _scene(seed, two_fluids=False, forces=()):
+    r = 0.05
+    rng = np.random.default_rng(seed)
+    pts = scenes.jitter(scenes.block_lattice(7, 6, 5, r * 0.93), r, seed, amplitude=0.3)
+    vel = rng.normal(0, 0.2, pts.shape).astype(np.float32)
+    floor = scenes.open_tank((-r, -r, -r), (7 * 2 * r + r, 0.5, 5 * 2 * r + r), r)
+    fluids = [dict(positions=pts, velocities=vel, density0=1000.0, forces=list(forces))]
+    if two_fluids:
+        up = scenes.jitter(scenes.block_lattice(7, 3, 5, r * 0.93, origin=(0.0, 6 * 2 * r * 0.93, 0.0)), r, seed + 1,
+                           amplitude=0.3)
+        fluids.append(dict(positions=up, velocities=rng.normal(0, 0.2, up.shape).astype(np.float32),
+                           density0=800.0, forces=list(forces)))
+    return dict(particle_radius=r, fluids=fluids, boundaries=[dict(positions=floor)])
+
+
+def _run(world, scene, nsteps, n_div, n_press, dt=0.005):
+    fh, bh = scenes.populate(world, scene)
+    world_force = getattr(world, "force_iterations", None)
+    if world_force:
+        world.force_iterations(n_div, n_press)
+    else:
+        world.force_div, world.force_press = n_div, n_press
+    for _ in range(nsteps):
+        world.step(dt)
+    return fh
+
+
+@pytest.mark.parametrize("forces", [(), (scenes.xsph_viscosity(0.5, 0.3),), (scenes.artificial_viscosity(1.0, 0.5),),
+                                    (scenes.akinci2013_surface_tension(1.0, 0.7),)])
+def test_single_fluid_steps_match(forces):
+    sc = _scene(5, forces=forces)
+    o = OracleWorld(sc["particle_radius"], 2.0)
+    n = NumpyDFSPH(sc["particle_radius"], 2.0)
+    fo = _run(o, sc, 3, 2, 3)
+    fn = _run(n, sc, 3, 2, 3)
+    po, vo = o.read_fluid(fo[0])
+    pn, vn = n.read_fluid(fn[0])
+    h = float(o.h)
+    assert np.array_equal(o.debug(fo[0], "num_fluid_contacts"), n.nff.astype(np.float32))
+    assert np.array_equal(o.debug(fo[0], "num_boundary_contacts"), n.nfb.astype(np.float32))
+    assert np.allclose(o.debug(fo[0], "density"), n.dens, rtol=2e-5)
+    assert np.allclose(o.debug(fo[0], "alpha"), n.alpha, rtol=1e-4, atol=1e-12)
+    assert np.allclose(o.debug(fo[0], "acceleration"), n.acc, rtol=1e-3, atol=2e-2)
+    assert np.abs(po - pn).max() < 1e-4 * h
+    assert np.abs(vo - vn).max() < 1e-4 * h / 0.005 * 10
+
+
+def test_two_fluids_free_running_match():
+    sc = _scene(9, two_fluids=True, forces=(scenes.xsph_viscosity(0.5, 0.0),))
+    o = OracleWorld(sc["particle_radius"], 2.0)
+    n = NumpyDFSPH(sc["particle_radius"], 2.0)
+    fo = _run(o, sc, 2, -1, -1)
+    fn = _run(n, sc, 2, -1, -1)
+    st = o.stats()
+    assert st["n_divergence_iter"] == n.n_div_iter
+    assert st["n_pressure_iter"] == n.n_press_iter
+    for a, b in zip(fo, fn):
+        po, vo = o.read_fluid(a)
+        pn, vn = n.read_fluid(b)
+        assert np.abs(po - pn).max() < 1e-4 * float(o.h)
+    # boundary volumes (dfsph_solver.rs:72-96)
+    vol, _ = o.read_boundary(0)
+    assert np.allclose(vol, n.bvol, rtol=1e-5)
