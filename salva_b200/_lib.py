@@ -1,0 +1,83 @@
+"""ctypes binding of libsalva_b200.so (the C ABI declared in include/sph.h).
+
+There is no fallback: if the CUDA library is missing or fails to load, importing a world fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsalva_b200.so")
+_LIB = None
+
+SPH_OK = 0
+STATUS_NAMES = {0: "SPH_OK", 1: "SPH_ERR_INVALID", 2: "SPH_ERR_CUDA", 3: "SPH_ERR_OOM", 4: "SPH_ERR_NCCL",
+                5: "SPH_ERR_ZERO_DENSITY"}
+
+
+class WorldDesc(C.Structure):
+    _fields_ = [("solver", C.c_int32), ("particle_radius", C.c_float), ("smoothing_factor", C.c_float),
+                ("min_pressure_iter", C.c_uint32), ("max_pressure_iter", C.c_uint32), ("max_density_error", C.c_float),
+                ("min_divergence_iter", C.c_uint32), ("max_divergence_iter", C.c_uint32),
+                ("max_divergence_error", C.c_float), ("omega", C.c_float), ("device", C.c_int32),
+                ("slab_rank", C.c_int32), ("slab_count", C.c_int32), ("deterministic", C.c_int32)]
+
+
+class ForceDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("p", C.c_float * 8)]
+
+
+class StepStats(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("step_ms", "grid_ms", "neighbors_ms", "density_ms", "divergence_ms",
+                                         "nonpressure_ms", "pressure_ms", "integrate_ms")] + \
+               [(n, C.c_uint32) for n in ("n_divergence_iter", "n_pressure_iter", "n_divergence_eval",
+                                          "n_pressure_eval")] + \
+               [("last_divergence_error", C.c_float), ("last_density_error", C.c_float),
+                ("n_fluid_particles", C.c_uint64), ("n_boundary_particles", C.c_uint64), ("n_contacts", C.c_uint64),
+                ("max_neighbors", C.c_uint32), ("grid_dims", C.c_uint32 * 3), ("kernel_launches", C.c_uint64)]
+
+
+# every symbol include/sph.h declares: name -> (restype, argtypes)
+_fp, _u8p, _vp = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.c_void_p
+SYMBOLS = {
+    "sph_world_desc_default": (None, [C.POINTER(WorldDesc)]),
+    "sph_world_create": (C.c_int, [C.POINTER(WorldDesc), C.POINTER(_vp)]),
+    "sph_world_destroy": (None, [_vp]),
+    "sph_fluid_add": (C.c_int, [_vp, _fp, _fp, _fp, C.c_size_t, C.c_float, C.c_uint32, C.c_uint32,
+                                C.POINTER(C.c_uint32)]),
+    "sph_fluid_push_force": (C.c_int, [_vp, C.c_uint32, C.POINTER(ForceDesc)]),
+    "sph_fluid_append": (C.c_int, [_vp, C.c_uint32, _fp, _fp, C.c_size_t]),
+    "sph_fluid_delete": (C.c_int, [_vp, C.c_uint32, _u8p, C.c_size_t]),
+    "sph_fluid_write": (C.c_int, [_vp, C.c_uint32, _fp, _fp, C.c_size_t]),
+    "sph_fluid_read": (C.c_int, [_vp, C.c_uint32, _fp, _fp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sph_fluid_count": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_size_t)]),
+    "sph_boundary_add": (C.c_int, [_vp, _fp, _fp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int,
+                                   C.POINTER(C.c_uint32)]),
+    "sph_boundary_write": (C.c_int, [_vp, C.c_uint32, _fp, _fp, C.c_size_t]),
+    "sph_boundary_read_forces": (C.c_int, [_vp, C.c_uint32, _fp, C.c_size_t]),
+    "sph_boundary_read_volumes": (C.c_int, [_vp, C.c_uint32, _fp, C.c_size_t]),
+    "sph_world_step": (C.c_int, [_vp, C.c_float, _fp]),
+    "sph_world_force_iterations": (C.c_int, [_vp, C.c_int32, C.c_int32]),
+    "sph_world_stats": (C.c_int, [_vp, C.POINTER(StepStats)]),
+    "sph_world_h": (C.c_float, [_vp]),
+    "sph_world_particle_radius": (C.c_float, [_vp]),
+    "sph_debug_read": (C.c_int, [_vp, C.c_uint32, C.c_int, _fp, C.c_size_t]),
+    "sph_last_error": (C.c_char_p, [_vp]),
+    "sph_version": (C.c_char_p, []),
+    "sph_world_attach_nccl": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+}
+
+
+def lib():
+    """Load libsalva_b200.so; raises (never falls back) when it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libsalva_b200.so is not built (run `python -c 'import __graft_entry__ as g; "
+                               "g.build()'`); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB

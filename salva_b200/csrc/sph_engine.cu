@@ -1,0 +1,1115 @@
+// sph_engine.cu — world state, step driver and the extern "C" boundary (include/sph.h) of the
+// B200-native SPH step path.  The step sequence restates LiquidWorld::step_with_coupling
+// (liquid_world.rs:67-158) + DFSPHSolver::step (dfsph_solver.rs:667-708) / IISPHSolver::step
+// (iisph_solver.rs:643-711) as a chain of CUDA kernels on one stream; see DESIGN.md.
+//
+// There is no CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sph.h"
+#include "sph_kernels.cuh"
+#include "sph_iisph.cuh"
+#include "sph_elasticity.cuh"
+
+using namespace sphk;
+
+namespace {
+
+// All worlds of a process share the module's __constant__ block; API calls are serialised per process
+// (GPU work of different worlds on one device would serialise anyway) and re-upload it on entry.
+std::mutex g_mutex;
+const void* g_const_owner = nullptr;
+
+inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = std::max(n, cap + cap / 4);
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+            cudaStreamSynchronize(st);
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct ForceRec;
+}  // namespace
+struct sph_world;
+namespace {
+struct ForceRec {
+    sph_force_desc d;
+    ElasticityState* elastic = nullptr;  // Becker2009 rest-pose state (sph_elasticity.cuh)
+};
+struct FluidRec {
+    size_t n = 0, offset = 0;
+    float density0 = 1000.f;
+    uint32_t memberships = 1, filter = 0xFFFFFFFFu;
+    std::vector<ForceRec> forces;
+    std::vector<uint8_t> pending_delete;
+    size_t n_pending = 0;
+};
+struct BoundaryRec {
+    size_t n = 0, offset = 0;
+    uint32_t memberships = 1, filter = 0xFFFFFFFFu;
+    bool want_forces = false;
+};
+
+sph_status iisph_step(sph_world* w, float dt_total, const float g[3]);
+void iisph_release(sph_world* w);
+const float* iisph_pred(sph_world* w);
+sph_status elasticity_solve(sph_world* w, uint32_t fluid, ForceRec& fr);
+void elasticity_release(ForceRec& fr);
+inline float __uint_as_float_host(uint32_t u) {
+    float f;
+    memcpy(&f, &u, sizeof f);
+    return f;
+}
+
+enum { EV_START = 0, EV_GRID, EV_NBR, EV_DENS, EV_DIV, EV_FOLD, EV_FORCES, EV_INTEG, EV_PRESS, EV_END, EV_COUNT };
+
+}  // namespace
+
+struct sph_world {
+    sph_world_desc desc;
+    float h = 0.f;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    std::string err;
+    Consts hc;
+
+    std::vector<FluidRec> fluids;
+    std::vector<BoundaryRec> bounds;
+    size_t N = 0, B = 0;
+
+    // timestep_manager.rs:21-31: dt/inv_dt are 0 until the first advance()
+    float dt = 0.f, inv_dt = 0.f;
+    int force_div = -1, force_press = -1;
+
+    // host truth in ORIGINAL order while `staged` (before the first step / after structural edits)
+    bool staged = true;
+    std::vector<float> h_pos, h_vel, h_vc, h_vol, h_press;
+    // boundaries: host copy is always kept (static data); b_dirty => re-upload
+    bool b_dirty = true;
+    std::vector<float> hb_pos, hb_vel;
+
+    // sorted device state (double buffered for the counting sort)
+    int cur = 0, bcur = 0;
+    DBuf<float4> pos[2], vel[2], vc[2], bpos[2], bvel[2];
+    DBuf<uint32_t> orig[2], borig[2];
+    DBuf<float> press[2];
+    DBuf<float4> vs, acc, normals, dbg_acc;
+    DBuf<float> dens, alpha, kappa, divv, pred, bvol, bforce;
+    DBuf<uint32_t> cid, rank, perm, cstart, bcid, brank, bperm, bstart, scan_aux[3];
+    DBuf<uint32_t> nbr_f, nbr_b, cnt_f, cnt_b;
+    DBuf<float> partial, errsum;
+    DBuf<int> d_scal;  // [0..6] bounds + bad flag, [7] error flag, [8..9] maxcnt
+    DBuf<unsigned long long> d_cnt;  // [0] bb contacts, [1] ff+fb contacts
+    DBuf<float> o_a, o_b, o_c, o_mass;  // staging, original order
+    DBuf<uint32_t> o_fid;
+    IisphState iisph;
+    float* h_pinned = nullptr;  // 64 floats of pinned host memory for small read-backs
+
+    uint32_t cap_f = 64, cap_b = 32, stride = 0;
+    bool lists_valid = false;
+    sph_step_stats stats;
+    uint64_t launches = 0;
+
+    sph_status fail(sph_status s, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return s;
+    }
+};
+
+namespace {
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return w->fail(e_ == cudaErrorMemoryAllocation ? SPH_ERR_OOM : SPH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                           cudaGetErrorString(e_), __FILE__, __LINE__);                            \
+    } while (0)
+#define TRY(call)                          \
+    do {                                   \
+        sph_status s_ = (call);            \
+        if (s_ != SPH_OK) return s_;       \
+    } while (0)
+#define LAUNCH(kern, n, threads, ...)                                                  \
+    do {                                                                               \
+        if ((n) > 0) {                                                                 \
+            kern<<<cdiv((n), (threads)), (threads), 0, w->st>>>(__VA_ARGS__);           \
+            w->launches++;                                                             \
+        }                                                                              \
+    } while (0)
+
+sph_status upload_consts(sph_world* w) {
+    CU(cudaMemcpyToSymbolAsync(C, &w->hc, sizeof(Consts), 0, cudaMemcpyHostToDevice, w->st));
+    g_const_owner = w;
+    return SPH_OK;
+}
+
+sph_status enter(sph_world* w) {
+    CU(cudaSetDevice(w->desc.device));
+    if (g_const_owner != w) TRY(upload_consts(w));
+    return SPH_OK;
+}
+
+void fill_static_consts(sph_world* w) {
+    Consts& c = w->hc;
+    c.h = w->h;
+    c.inv_h = 1.0f / w->h;
+    c.h2 = w->h * w->h;
+    c.sigma = 8.0f / (3.14159265358979323846f * w->h * w->h * w->h);
+    c.dsigma = c.sigma / w->h;
+    c.n_fluid = (uint32_t)w->N;
+    c.n_bound = (uint32_t)w->B;
+    c.n_fluids = (int)w->fluids.size();
+    c.n_bounds = (int)w->bounds.size();
+    for (size_t f = 0; f < w->fluids.size(); ++f)
+        c.fluids[f] = {w->fluids[f].density0, w->fluids[f].memberships, w->fluids[f].filter, (uint32_t)w->fluids[f].n};
+    for (size_t b = 0; b < w->bounds.size(); ++b) c.bounds[b] = {w->bounds[b].memberships, w->bounds[b].filter};
+    c.stride = w->stride;
+    c.cap_f = w->cap_f;
+    c.cap_b = w->cap_b;
+}
+
+// ---- exclusive scan over n u32 (in place) -------------------------------------------------------
+sph_status scan_exclusive(sph_world* w, uint32_t* data, size_t n, int level = 0) {
+    if (n == 0) return SPH_OK;
+    uint32_t nb = cdiv(n, SCAN_B);
+    if (nb == 1) {
+        k_scan_block<<<1, SCAN_T, 0, w->st>>>(data, data, (uint32_t)n, nullptr);
+        w->launches++;
+        return SPH_OK;
+    }
+    if (level >= 3) return w->fail(SPH_ERR_INVALID, "scan too deep");
+    CU(w->scan_aux[level].ensure(nb));
+    k_scan_block<<<nb, SCAN_T, 0, w->st>>>(data, data, (uint32_t)n, w->scan_aux[level].p);
+    w->launches++;
+    TRY(scan_exclusive(w, w->scan_aux[level].p, nb, level + 1));
+    k_scan_add<<<nb, SCAN_T, 0, w->st>>>(data, (uint32_t)n, w->scan_aux[level].p);
+    w->launches++;
+    return SPH_OK;
+}
+
+// ---- host <-> device staging --------------------------------------------------------------------
+// Device holds the truth -> pull everything back into the host vectors (original order).
+sph_status stage_down(sph_world* w) {
+    if (w->staged) return SPH_OK;
+    size_t N = w->N;
+    w->h_pos.resize(3 * N);
+    w->h_vel.resize(3 * N);
+    w->h_vc.resize(3 * N);
+    w->h_press.assign(N, 0.f);
+    if (N) {
+        int c = w->cur;
+        CU(w->o_a.ensure(3 * N));
+        const float4* srcs[3] = {w->pos[c].p, w->vel[c].p, w->vc[c].p};
+        float* dsts[3] = {w->h_pos.data(), w->h_vel.data(), w->h_vc.data()};
+        for (int a = 0; a < 3; ++a) {
+            LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, srcs[a], w->o_a.p);
+            CU(cudaMemcpyAsync(dsts[a], w->o_a.p, 3 * N * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+            CU(cudaStreamSynchronize(w->st));
+        }
+        if (w->desc.solver == SPH_SOLVER_IISPH && w->press[c].p) {
+            LAUNCH(k_export1, N, 256, (uint32_t)N, w->orig[c].p, w->press[c].p, w->o_a.p);
+            CU(cudaMemcpyAsync(w->h_press.data(), w->o_a.p, N * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+            CU(cudaStreamSynchronize(w->st));
+        }
+    }
+    w->staged = true;
+    w->lists_valid = false;
+    return SPH_OK;
+}
+
+void recompute_offsets(sph_world* w) {
+    size_t o = 0;
+    for (auto& f : w->fluids) {
+        f.offset = o;
+        o += f.n;
+    }
+    w->N = o;
+    o = 0;
+    for (auto& b : w->bounds) {
+        b.offset = o;
+        o += b.n;
+    }
+    w->B = o;
+}
+
+sph_status ensure_fluid_buffers(sph_world* w) {
+    size_t N = w->N;
+    for (int k = 0; k < 2; ++k) {
+        CU(w->pos[k].ensure(N));
+        CU(w->vel[k].ensure(N));
+        CU(w->vc[k].ensure(N));
+        CU(w->orig[k].ensure(N));
+        if (w->desc.solver == SPH_SOLVER_IISPH) CU(w->press[k].ensure(N));
+    }
+    CU(w->vs.ensure(N));
+    CU(w->acc.ensure(N));
+    CU(w->dbg_acc.ensure(N));
+    CU(w->dens.ensure(N));
+    CU(w->alpha.ensure(N));
+    CU(w->kappa.ensure(N));
+    CU(w->divv.ensure(N));
+    CU(w->pred.ensure(N));
+    CU(w->cid.ensure(N));
+    CU(w->rank.ensure(N));
+    CU(w->perm.ensure(N));
+    CU(w->cnt_f.ensure(N));
+    CU(w->cnt_b.ensure(N));
+    w->stride = (uint32_t)((N + 31) / 32 * 32);
+    CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
+    CU(w->nbr_b.ensure((size_t)w->cap_b * w->stride));
+    uint32_t nblk = cdiv(std::max<size_t>(N, 1), PASS_T);
+    CU(w->partial.ensure((size_t)nblk * std::max<size_t>(1, w->fluids.size())));
+    CU(w->errsum.ensure(MAX_FLUIDS));
+    return SPH_OK;
+}
+
+// Host vectors hold the truth -> build the device state (sorted order starts as the identity).
+sph_status stage_up(sph_world* w) {
+    if (!w->staged) return SPH_OK;
+    recompute_offsets(w);
+    size_t N = w->N;
+    TRY(ensure_fluid_buffers(w));
+    if (N) {
+        std::vector<float> mass(N);
+        std::vector<uint32_t> fid(N);
+        for (size_t f = 0; f < w->fluids.size(); ++f)
+            for (size_t i = 0; i < w->fluids[f].n; ++i) {
+                size_t g = w->fluids[f].offset + i;
+                mass[g] = w->h_vol[g] * w->fluids[f].density0;  // fluid.rs:183-185
+                fid[g] = (uint32_t)f;
+            }
+        CU(w->o_a.ensure(3 * N));
+        CU(w->o_b.ensure(3 * N));
+        CU(w->o_c.ensure(3 * N));
+        CU(w->o_mass.ensure(N));
+        CU(w->o_fid.ensure(N));
+        CU(cudaMemcpyAsync(w->o_a.p, w->h_pos.data(), 3 * N * sizeof(float), cudaMemcpyHostToDevice, w->st));
+        CU(cudaMemcpyAsync(w->o_b.p, w->h_vel.data(), 3 * N * sizeof(float), cudaMemcpyHostToDevice, w->st));
+        CU(cudaMemcpyAsync(w->o_c.p, w->h_vc.data(), 3 * N * sizeof(float), cudaMemcpyHostToDevice, w->st));
+        CU(cudaMemcpyAsync(w->o_mass.p, mass.data(), N * sizeof(float), cudaMemcpyHostToDevice, w->st));
+        CU(cudaMemcpyAsync(w->o_fid.p, fid.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice, w->st));
+        int c = w->cur;
+        LAUNCH(k_iota, N, 256, (uint32_t)N, w->orig[c].p);
+        CU(cudaMemsetAsync(w->pos[c].p, 0, N * sizeof(float4), w->st));
+        CU(cudaMemsetAsync(w->vel[c].p, 0, N * sizeof(float4), w->st));
+        LAUNCH(k_import, N, 256, (uint32_t)N, w->orig[c].p, w->o_a.p, w->o_b.p, w->o_c.p, w->o_mass.p, w->o_fid.p, w->pos[c].p, w->vel[c].p,
+               w->vc[c].p, 0u, (uint32_t)N);
+        if (w->desc.solver == SPH_SOLVER_IISPH) {
+            w->h_press.resize(N, 0.f);
+            CU(cudaMemcpyAsync(w->press[c].p, w->h_press.data(), N * sizeof(float), cudaMemcpyHostToDevice, w->st));
+        }
+        CU(cudaStreamSynchronize(w->st));  // host temporaries go out of scope
+    }
+    w->staged = false;
+    w->lists_valid = false;
+    return SPH_OK;
+}
+
+sph_status upload_boundaries(sph_world* w) {
+    if (!w->b_dirty) return SPH_OK;
+    recompute_offsets(w);
+    size_t B = w->B;
+    for (int k = 0; k < 2; ++k) {
+        CU(w->bpos[k].ensure(B));
+        CU(w->bvel[k].ensure(B));
+        CU(w->borig[k].ensure(B));
+    }
+    CU(w->bvol.ensure(B));
+    CU(w->bcid.ensure(B));
+    CU(w->brank.ensure(B));
+    CU(w->bperm.ensure(B));
+    CU(w->bforce.ensure(3 * B));
+    if (B) {
+        std::vector<float4> p(B), v(B);
+        for (size_t b = 0; b < w->bounds.size(); ++b)
+            for (size_t i = 0; i < w->bounds[b].n; ++i) {
+                size_t g = w->bounds[b].offset + i;
+                p[g] = make_float4(w->hb_pos[3 * g], w->hb_pos[3 * g + 1], w->hb_pos[3 * g + 2], 0.f);
+                v[g] = make_float4(w->hb_vel[3 * g], w->hb_vel[3 * g + 1], w->hb_vel[3 * g + 2], __uint_as_float_host((uint32_t)b));
+            }
+        int c = w->bcur;
+        CU(cudaMemcpyAsync(w->bpos[c].p, p.data(), B * sizeof(float4), cudaMemcpyHostToDevice, w->st));
+        CU(cudaMemcpyAsync(w->bvel[c].p, v.data(), B * sizeof(float4), cudaMemcpyHostToDevice, w->st));
+        LAUNCH(k_iota, B, 256, (uint32_t)B, w->borig[c].p);
+        CU(cudaStreamSynchronize(w->st));
+    }
+    w->b_dirty = false;
+    w->lists_valid = false;
+    return SPH_OK;
+}
+
+// fluid.rs:88-98 apply_particles_removal (+ solver scratch filtering dfsph_solver.rs:550-559)
+sph_status apply_pending_deletes(sph_world* w) {
+    bool any = false;
+    for (auto& f : w->fluids) any |= f.n_pending != 0;
+    if (!any) return SPH_OK;
+    TRY(stage_down(w));
+    std::vector<float> np, nv, nc, nvol, npr;
+    np.reserve(w->h_pos.size());
+    nv.reserve(w->h_pos.size());
+    nc.reserve(w->h_pos.size());
+    for (auto& f : w->fluids) {
+        size_t kept = 0;
+        for (size_t i = 0; i < f.n; ++i) {
+            if (f.n_pending && f.pending_delete[i]) continue;
+            size_t g = f.offset + i;
+            for (int a = 0; a < 3; ++a) {
+                np.push_back(w->h_pos[3 * g + a]);
+                nv.push_back(w->h_vel[3 * g + a]);
+                nc.push_back(w->h_vc[3 * g + a]);
+            }
+            nvol.push_back(w->h_vol[g]);
+            npr.push_back(g < w->h_press.size() ? w->h_press[g] : 0.f);
+            ++kept;
+        }
+        f.n = kept;
+        f.pending_delete.assign(kept, 0);
+        f.n_pending = 0;
+    }
+    w->h_pos.swap(np);
+    w->h_vel.swap(nv);
+    w->h_vc.swap(nc);
+    w->h_vol.swap(nvol);
+    w->h_press.swap(npr);
+    recompute_offsets(w);
+    return SPH_OK;
+}
+
+// ---- step phases ----------------------------------------------------------------------------------
+sph_status phase_grid(sph_world* w) {
+    size_t N = w->N, B = w->B;
+    int c = w->cur, bc = w->bcur;
+    int init[10] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(w->d_scal.p, init, sizeof init, cudaMemcpyHostToDevice, w->st));
+    CU(cudaMemsetAsync(w->d_cnt.p, 0, 2 * sizeof(unsigned long long), w->st));
+    if (N) {
+        k_bounds<<<std::min<uint32_t>(cdiv(N, 256), 1184), 256, 0, w->st>>>(w->pos[c].p, (uint32_t)N, w->d_scal.p);
+        w->launches++;
+    }
+    if (B) {
+        k_bounds<<<std::min<uint32_t>(cdiv(B, 256), 1184), 256, 0, w->st>>>(w->bpos[bc].p, (uint32_t)B, w->d_scal.p);
+        w->launches++;
+    }
+    int hb[7];
+    CU(cudaMemcpyAsync(hb, w->d_scal.p, sizeof hb, cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    if (hb[6]) return w->fail(SPH_ERR_INVALID, "non-finite or out-of-range particle coordinates");
+    long long dims[3];
+    for (int a = 0; a < 3; ++a) dims[a] = (long long)hb[3 + a] - hb[a] + 3;  // one padding cell each side
+    double ncell_d = (double)dims[0] * (double)dims[1] * (double)dims[2];
+    if (ncell_d > 1.0e9) return w->fail(SPH_ERR_OOM, "dense cell grid too large: %lld x %lld x %lld cells of width h", dims[0], dims[1], dims[2]);
+    size_t ncell = (size_t)dims[0] * dims[1] * dims[2];
+    w->hc.ox = hb[0] - 1;
+    w->hc.oy = hb[1] - 1;
+    w->hc.oz = hb[2] - 1;
+    w->hc.nx = (int)dims[0];
+    w->hc.ny = (int)dims[1];
+    w->hc.nz = (int)dims[2];
+    fill_static_consts(w);
+    TRY(upload_consts(w));
+    CU(w->cstart.ensure(ncell + 1));
+    CU(w->bstart.ensure(ncell + 1));
+    w->stats.grid_dims[0] = (uint32_t)dims[0];
+    w->stats.grid_dims[1] = (uint32_t)dims[1];
+    w->stats.grid_dims[2] = (uint32_t)dims[2];
+    // fluid: counting sort by cell, then reorder every persistent array
+    CU(cudaMemsetAsync(w->cstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));
+    LAUNCH(k_cell_hist, N, 256, w->pos[c].p, (uint32_t)N, w->cid.p, w->rank.p, w->cstart.p);
+    TRY(scan_exclusive(w, w->cstart.p, ncell + 1));
+    LAUNCH(k_cell_scatter, N, 256, (uint32_t)N, w->cid.p, w->rank.p, w->cstart.p, w->perm.p);
+    if (w->desc.deterministic) LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->cstart.p, w->perm.p);
+    if (N) {
+        GatherSet g;
+        memset(&g, 0, sizeof g);
+        g.in4[0] = w->pos[c].p; g.out4[0] = w->pos[c ^ 1].p;
+        g.in4[1] = w->vel[c].p; g.out4[1] = w->vel[c ^ 1].p;
+        g.in4[2] = w->vc[c].p;  g.out4[2] = w->vc[c ^ 1].p;
+        g.n4 = 3;
+        g.in1[0] = w->orig[c].p; g.out1[0] = w->orig[c ^ 1].p;
+        g.n1 = 1;
+        if (w->desc.solver == SPH_SOLVER_IISPH) {
+            g.in1[1] = reinterpret_cast<const uint32_t*>(w->press[c].p);
+            g.out1[1] = reinterpret_cast<uint32_t*>(w->press[c ^ 1].p);
+            g.n1 = 2;
+        }
+        LAUNCH(k_gather, N, 256, (uint32_t)N, w->perm.p, g);
+        w->cur = c ^ 1;
+    }
+    // boundaries: same sort
+    CU(cudaMemsetAsync(w->bstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));
+    if (B) {
+        LAUNCH(k_cell_hist, B, 256, w->bpos[bc].p, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p);
+        TRY(scan_exclusive(w, w->bstart.p, ncell + 1));
+        LAUNCH(k_cell_scatter, B, 256, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p, w->bperm.p);
+        if (w->desc.deterministic) LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->bstart.p, w->bperm.p);
+        GatherSet g;
+        memset(&g, 0, sizeof g);
+        g.in4[0] = w->bpos[bc].p; g.out4[0] = w->bpos[bc ^ 1].p;
+        g.in4[1] = w->bvel[bc].p; g.out4[1] = w->bvel[bc ^ 1].p;
+        g.n4 = 2;
+        g.in1[0] = w->borig[bc].p; g.out1[0] = w->borig[bc ^ 1].p;
+        g.n1 = 1;
+        LAUNCH(k_gather, B, 256, (uint32_t)B, w->bperm.p, g);
+        w->bcur = bc ^ 1;
+    }
+    CU(cudaGetLastError());
+    return SPH_OK;
+}
+
+sph_status phase_neighbors(sph_world* w) {
+    size_t N = w->N, B = w->B;
+    int c = w->cur, bc = w->bcur;
+    const bool multi = w->fluids.size() > 1;
+    if (B) {  // compute_boundary_volumes dfsph_solver.rs:72-96 (every substep, as the reference)
+        LAUNCH(k_boundary_volumes, B, 128, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->bvol.p, w->d_cnt.p, w->d_scal.p + 7);
+        LAUNCH(k_set_w, B, 256, (uint32_t)B, w->bpos[bc].p, w->bvol.p);
+        for (auto& b : w->bounds)
+            if (b.want_forces) {
+                CU(cudaMemsetAsync(w->bforce.p, 0, 3 * B * sizeof(float), w->st));
+                break;
+            }
+    }
+    for (int attempt = 0; attempt < 8 && N; ++attempt) {
+        CU(cudaMemsetAsync(w->d_scal.p + 8, 0, 2 * sizeof(int), w->st));
+        if (multi)
+            LAUNCH((k_neighbors<true>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
+                   w->cnt_f.p, w->cnt_b.p, reinterpret_cast<uint32_t*>(w->d_scal.p + 8));
+        else
+            LAUNCH((k_neighbors<false>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
+                   w->cnt_f.p, w->cnt_b.p, reinterpret_cast<uint32_t*>(w->d_scal.p + 8));
+        int hs[3];
+        CU(cudaMemcpyAsync(hs, w->d_scal.p + 7, sizeof hs, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaStreamSynchronize(w->st));
+        if (hs[0]) return w->fail(SPH_ERR_ZERO_DENSITY, "zero boundary-volume denominator (reference assert dfsph_solver.rs:92)");
+        w->stats.max_neighbors = (uint32_t)hs[1];
+        bool grow = false;
+        if ((uint32_t)hs[1] > w->cap_f) {
+            w->cap_f = ((uint32_t)hs[1] + 15) / 16 * 16;
+            grow = true;
+        }
+        if ((uint32_t)hs[2] > w->cap_b) {
+            w->cap_b = ((uint32_t)hs[2] + 15) / 16 * 16;
+            grow = true;
+        }
+        if (!grow) break;
+        CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
+        CU(w->nbr_b.ensure((size_t)w->cap_b * w->stride));
+        fill_static_consts(w);
+        TRY(upload_consts(w));
+    }
+    if (N) {
+        k_sum_u32<<<std::min<uint32_t>(cdiv(N, 256), 1184), 256, 0, w->st>>>((uint32_t)N, w->cnt_f.p, w->cnt_b.p, w->d_cnt.p + 1);
+        w->launches++;
+    }
+    CU(cudaGetLastError());
+    w->lists_valid = true;
+    return SPH_OK;
+}
+
+// mean-per-fluid -> max over fluids (dfsph_solver.rs:153-158, :347-352)
+sph_status read_error(sph_world* w, uint32_t nblk, float* out) {
+    int nf = (int)w->fluids.size();
+    k_reduce_partials<<<nf, 256, 0, w->st>>>(w->partial.p, nblk, nf, w->errsum.p);
+    w->launches++;
+    CU(cudaMemcpyAsync(w->h_pinned, w->errsum.p, nf * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    float mx = 0.f;
+    for (int f = 0; f < nf; ++f)
+        if (w->fluids[f].n) mx = std::max(mx, w->h_pinned[f] / (float)(double)w->fluids[f].n);
+    *out = mx;
+    return SPH_OK;
+}
+
+bool any_bforce(const sph_world* w) {
+    for (auto& b : w->bounds)
+        if (b.want_forces) return true;
+    return false;
+}
+
+#define DISPATCH2(kern, multi, bf, n, threads, ...)                                   \
+    do {                                                                              \
+        if (multi) {                                                                  \
+            if (bf) LAUNCH((kern<true, true>), n, threads, __VA_ARGS__);              \
+            else LAUNCH((kern<true, false>), n, threads, __VA_ARGS__);                \
+        } else {                                                                      \
+            if (bf) LAUNCH((kern<false, true>), n, threads, __VA_ARGS__);             \
+            else LAUNCH((kern<false, false>), n, threads, __VA_ARGS__);               \
+        }                                                                             \
+    } while (0)
+#define DISPATCH1(kern, multi, n, threads, ...)                         \
+    do {                                                                \
+        if (multi) LAUNCH((kern<true>), n, threads, __VA_ARGS__);       \
+        else LAUNCH((kern<false>), n, threads, __VA_ARGS__);            \
+    } while (0)
+
+// predict_advection dfsph_solver.rs:580-603: every fluid's forces in push order
+sph_status phase_forces(sph_world* w, const Lists& L) {
+    size_t N = w->N;
+    int c = w->cur, bc = w->bcur;
+    const bool multi = w->fluids.size() > 1, bf = any_bforce(w);
+    for (size_t f = 0; f < w->fluids.size(); ++f)
+        for (ForceRec& fr : w->fluids[f].forces) {
+            const float* p = fr.d.p;
+            switch (fr.d.kind) {
+                case SPH_FORCE_XSPH_VISCOSITY:
+                    DISPATCH2(k_force_xsph, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->acc.p,
+                              w->bforce.p, (uint32_t)f, p[0], p[1], w->inv_dt);
+                    break;
+                case SPH_FORCE_ARTIFICIAL_VISCOSITY:
+                    DISPATCH2(k_force_artificial, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->acc.p,
+                              w->bforce.p, (uint32_t)f, p[0], p[1], p[2], p[3], p[4]);
+                    break;
+                case SPH_FORCE_AKINCI2013_TENSION: {
+                    CU(w->normals.ensure(N));
+                    float h = w->h;
+                    float coh_norm = 32.0f / (3.14159265358979323846f * powf(h, 9.f));
+                    float h6_64 = powf(h, 6.f) / 64.0f;
+                    float adh_norm = 0.007f / powf(h, 3.25f);
+                    DISPATCH1(k_akinci_normals, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->dens.p, w->normals.p, (uint32_t)f);
+                    DISPATCH2(k_akinci_force, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->normals.p, w->acc.p,
+                              w->bforce.p, (uint32_t)f, p[0], p[1], coh_norm, h6_64, adh_norm);
+                    break;
+                }
+                case SPH_FORCE_BECKER2009_ELASTICITY:
+                    TRY(elasticity_solve(w, (uint32_t)f, fr));
+                    break;
+                default:
+                    return w->fail(SPH_ERR_INVALID, "unknown force kind %d", fr.d.kind);
+            }
+        }
+    CU(cudaGetLastError());
+    return SPH_OK;
+}
+
+// timestep_manager.rs:76-88
+void timestep_advance(sph_world* w, float total) {
+    w->dt = total;
+    w->inv_dt = total == 0.f ? 0.f : 1.0f / total;
+}
+
+// DFSPHSolver::step dfsph_solver.rs:667-708
+sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
+    size_t N = w->N;
+    int c = w->cur, bc = w->bcur;
+    const bool multi = w->fluids.size() > 1, bf = any_bforce(w);
+    Lists L{w->nbr_f.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+    uint32_t nblk = cdiv(N, PASS_T);
+    // divergence_solve :466-503 (uses the PREVIOUS step's inv_dt; 0 on the first step)
+    w->stats.n_divergence_iter = w->stats.n_divergence_eval = 0;
+    uint32_t maxit = w->force_div >= 0 ? (uint32_t)w->force_div + 1 : w->desc.max_divergence_iter;
+    for (uint32_t i = 0; i < maxit; ++i) {
+        DISPATCH1(k_divergence, multi, N, PASS_T, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, L, w->alpha.p, w->divv.p, w->kappa.p, w->partial.p);
+        w->stats.n_divergence_eval++;
+        if (w->force_div >= 0) {
+            if ((int)i >= w->force_div) break;
+        } else {
+            float avg;
+            TRY(read_error(w, nblk, &avg));
+            w->stats.last_divergence_error = avg;
+            float max_err = w->desc.max_divergence_error * w->inv_dt * 0.01f;
+            if (avg <= max_err && i >= w->desc.min_divergence_iter) break;
+        }
+        DISPATCH2(k_divergence_update, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->vc[c].p, w->vs.p, w->bforce.p,
+                  w->inv_dt);
+        w->stats.n_divergence_iter++;
+    }
+    CU(cudaEventRecord(w->ev[EV_DIV], w->st));
+    // update_velocities :422-430, zero vc :689-691, acc += gravity :574-578
+    LAUNCH(k_fold_velocities, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2]);
+    CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
+    TRY(phase_forces(w, L));
+    CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
+    timestep_advance(w, dt_total);  // :702
+    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p);
+    CU(cudaEventRecord(w->ev[EV_INTEG], w->st));
+    // pressure_solve :432-464
+    w->stats.n_pressure_iter = w->stats.n_pressure_eval = 0;
+    maxit = w->force_press >= 0 ? (uint32_t)w->force_press + 1 : w->desc.max_pressure_iter;
+    for (uint32_t i = 0; i < maxit; ++i) {
+        DISPATCH1(k_predict_density, multi, N, PASS_T, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->alpha.p,
+                  w->pred.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
+        w->stats.n_pressure_eval++;
+        if (w->force_press >= 0) {
+            if ((int)i >= w->force_press) break;
+        } else {
+            float avg;
+            TRY(read_error(w, nblk, &avg));
+            w->stats.last_density_error = avg;
+            if (avg <= w->desc.max_density_error && i >= w->desc.min_pressure_iter) break;
+        }
+        DISPATCH2(k_pressure_update, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->vc[c].p, w->vs.p, w->bforce.p,
+                  w->inv_dt);
+        w->stats.n_pressure_iter++;
+    }
+    CU(cudaEventRecord(w->ev[EV_PRESS], w->st));
+    LAUNCH(k_update_positions, N, 256, w->pos[c].p, w->vs.p, w->dt);  // :411-420
+    CU(cudaGetLastError());
+    return SPH_OK;
+}
+
+sph_status world_step(sph_world* w, float dt, const float g[3]) {
+    TRY(enter(w));
+    w->launches = 0;
+    memset(&w->stats, 0, sizeof w->stats);
+    TRY(apply_pending_deletes(w));  // liquid_world.rs:79-81
+    TRY(stage_up(w));
+    TRY(upload_boundaries(w));
+    size_t N = w->N;
+    w->stats.n_fluid_particles = N;
+    w->stats.n_boundary_particles = w->B;
+    if (w->fluids.size() > (size_t)MAX_FLUIDS || w->bounds.size() > (size_t)MAX_BOUNDARIES)
+        return w->fail(SPH_ERR_INVALID, "too many fluids (max %d) or boundaries (max %d)", MAX_FLUIDS, MAX_BOUNDARIES);
+    if (!(dt > F32_EPS)) return SPH_OK;  // timestep_manager.rs:56-58: is_done() before the first substep
+    CU(cudaEventRecord(w->ev[EV_START], w->st));
+    if (N + w->B == 0) return SPH_OK;
+    TRY(phase_grid(w));
+    CU(cudaEventRecord(w->ev[EV_GRID], w->st));
+    TRY(phase_neighbors(w));
+    CU(cudaEventRecord(w->ev[EV_NBR], w->st));
+    int c = w->cur, bc = w->bcur;
+    const bool multi = w->fluids.size() > 1;
+    Lists L{w->nbr_f.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+    // evaluate_kernels + compute_densities (liquid_world.rs:123-134) + compute_alphas (dfsph_solver.rs:679-684)
+    DISPATCH1(k_density_alpha, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->alpha.p, w->d_scal.p + 7);
+    CU(cudaEventRecord(w->ev[EV_DENS], w->st));
+    if (N) {
+        if (w->desc.solver == SPH_SOLVER_DFSPH) TRY(dfsph_step(w, dt, g));
+        else TRY(iisph_step(w, dt, g));
+    }
+    CU(cudaEventRecord(w->ev[EV_END], w->st));
+    int flag = 0;
+    unsigned long long cnts[2] = {0, 0};
+    CU(cudaMemcpyAsync(&flag, w->d_scal.p + 7, sizeof(int), cudaMemcpyDeviceToHost, w->st));
+    CU(cudaMemcpyAsync(cnts, w->d_cnt.p, sizeof cnts, cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    CU(cudaGetLastError());
+    w->stats.n_contacts = cnts[0] + cnts[1];
+    w->stats.kernel_launches = w->launches;
+    auto el = [&](int a, int b) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, w->ev[a], w->ev[b]);
+        return ms;
+    };
+    w->stats.step_ms = el(EV_START, EV_END);
+    w->stats.grid_ms = el(EV_START, EV_GRID);
+    w->stats.neighbors_ms = el(EV_GRID, EV_NBR);
+    w->stats.density_ms = el(EV_NBR, EV_DENS);
+    if (N && w->desc.solver == SPH_SOLVER_DFSPH) {
+        w->stats.divergence_ms = el(EV_DENS, EV_DIV);
+        w->stats.nonpressure_ms = el(EV_FOLD, EV_FORCES);
+        w->stats.pressure_ms = el(EV_INTEG, EV_PRESS);
+        w->stats.integrate_ms = el(EV_DIV, EV_FOLD) + el(EV_FORCES, EV_INTEG) + el(EV_PRESS, EV_END);
+    } else if (N) {
+        w->stats.nonpressure_ms = el(EV_DENS, EV_FORCES);
+        w->stats.pressure_ms = el(EV_INTEG, EV_PRESS);
+        w->stats.integrate_ms = el(EV_FORCES, EV_INTEG) + el(EV_PRESS, EV_END);
+    }
+    if (flag) return w->fail(SPH_ERR_ZERO_DENSITY, "zero density (reference asserts dfsph_solver.rs:92,145,662)");
+    return SPH_OK;
+}
+
+}  // namespace
+
+#include "sph_iisph_host.inl"
+#include "sph_elasticity_host.inl"
+
+// ===================================================================================================
+// extern "C" boundary
+// ===================================================================================================
+extern "C" {
+
+void sph_world_desc_default(sph_world_desc* d) {
+    memset(d, 0, sizeof *d);
+    d->solver = SPH_SOLVER_DFSPH;
+    d->particle_radius = 0.05f;
+    d->smoothing_factor = 2.0f;
+    d->min_pressure_iter = 1;
+    d->max_pressure_iter = 50;
+    d->max_density_error = 0.05f;
+    d->min_divergence_iter = 1;
+    d->max_divergence_iter = 50;
+    d->max_divergence_error = 0.1f;
+    d->omega = 0.5f;
+    d->device = 0;
+    d->slab_rank = 0;
+    d->slab_count = 1;
+    d->deterministic = 1;
+}
+
+sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
+    if (!desc || !out) return SPH_ERR_INVALID;
+    *out = nullptr;
+    if (!(desc->particle_radius > 0.f) || !(desc->smoothing_factor > 0.f)) return SPH_ERR_INVALID;
+    if (desc->solver != SPH_SOLVER_DFSPH && desc->solver != SPH_SOLVER_IISPH) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || desc->device < 0 || desc->device >= ndev) return SPH_ERR_CUDA;
+    if (cudaSetDevice(desc->device) != cudaSuccess) return SPH_ERR_CUDA;
+    sph_world* w = new sph_world();
+    w->desc = *desc;
+    w->h = desc->particle_radius * desc->smoothing_factor * 2.0f;  // liquid_world.rs:44
+    memset(&w->hc, 0, sizeof w->hc);
+    memset(&w->stats, 0, sizeof w->stats);
+    bool ok = cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < EV_COUNT; ++i) ok = cudaEventCreate(&w->ev[i]) == cudaSuccess;
+    ok = ok && cudaMallocHost(&w->h_pinned, 64 * sizeof(float)) == cudaSuccess;
+    ok = ok && w->d_scal.ensure(16) == cudaSuccess && w->d_cnt.ensure(2) == cudaSuccess;
+    if (!ok) {
+        delete w;
+        return SPH_ERR_CUDA;
+    }
+    fill_static_consts(w);
+    *out = w;
+    return SPH_OK;
+}
+
+void sph_world_destroy(sph_world* w) {
+    if (!w) return;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaSetDevice(w->desc.device);
+    if (w->st) cudaStreamSynchronize(w->st);
+    for (int k = 0; k < 2; ++k) {
+        w->pos[k].release(); w->vel[k].release(); w->vc[k].release(); w->bpos[k].release(); w->bvel[k].release();
+        w->orig[k].release(); w->borig[k].release(); w->press[k].release();
+    }
+    w->vs.release(); w->acc.release(); w->normals.release(); w->dbg_acc.release();
+    w->dens.release(); w->alpha.release(); w->kappa.release(); w->divv.release(); w->pred.release(); w->bvol.release(); w->bforce.release();
+    w->cid.release(); w->rank.release(); w->perm.release(); w->cstart.release(); w->bcid.release(); w->brank.release(); w->bperm.release();
+    w->bstart.release();
+    for (auto& a : w->scan_aux) a.release();
+    w->nbr_f.release(); w->nbr_b.release(); w->cnt_f.release(); w->cnt_b.release();
+    w->partial.release(); w->errsum.release(); w->d_scal.release(); w->d_cnt.release();
+    w->o_a.release(); w->o_b.release(); w->o_c.release(); w->o_mass.release(); w->o_fid.release();
+    iisph_release(w);
+    for (auto& f : w->fluids)
+        for (auto& fr : f.forces) elasticity_release(fr);
+    if (w->h_pinned) cudaFreeHost(w->h_pinned);
+    for (auto& e : w->ev)
+        if (e) cudaEventDestroy(e);
+    if (w->st) cudaStreamDestroy(w->st);
+    if (g_const_owner == w) g_const_owner = nullptr;
+    delete w;
+}
+
+sph_status sph_fluid_add(sph_world* w, const float* pos, const float* vel, const float* volumes, size_t n, float density0, uint32_t memberships,
+                         uint32_t filter, uint32_t* handle) {
+    if (!w) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (n && !pos) return w->fail(SPH_ERR_INVALID, "sph_fluid_add: null positions");
+    if (w->fluids.size() >= (size_t)MAX_FLUIDS) return w->fail(SPH_ERR_INVALID, "too many fluids (max %d)", MAX_FLUIDS);
+    TRY(enter(w));
+    TRY(stage_down(w));
+    FluidRec f;
+    f.n = n;
+    f.density0 = density0;
+    f.memberships = memberships;
+    f.filter = filter;
+    f.pending_delete.assign(n, 0);
+    float r = w->desc.particle_radius;
+    float pv = r * r * r * (float)(8.0 * 0.8);  // fluid.rs:110-120
+    w->h_pos.insert(w->h_pos.end(), pos, pos + 3 * n);
+    if (vel) w->h_vel.insert(w->h_vel.end(), vel, vel + 3 * n);
+    else w->h_vel.insert(w->h_vel.end(), 3 * n, 0.f);
+    w->h_vc.insert(w->h_vc.end(), 3 * n, 0.f);
+    if (volumes) w->h_vol.insert(w->h_vol.end(), volumes, volumes + n);
+    else w->h_vol.insert(w->h_vol.end(), n, pv);
+    w->h_press.insert(w->h_press.end(), n, 0.f);
+    w->fluids.push_back(f);
+    recompute_offsets(w);
+    if (handle) *handle = (uint32_t)w->fluids.size() - 1;
+    return SPH_OK;
+}
+
+sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid, const sph_force_desc* force) {
+    if (!w || !force) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    if (force->kind < 0 || force->kind > SPH_FORCE_BECKER2009_ELASTICITY) return w->fail(SPH_ERR_INVALID, "unknown force kind %d", force->kind);
+    ForceRec fr;
+    fr.d = *force;
+    w->fluids[fluid].forces.push_back(fr);
+    return SPH_OK;
+}
+
+// Fluid::add_particles fluid.rs:126-150 — appended at the end of the fluid's index range.
+sph_status sph_fluid_append(sph_world* w, uint32_t fluid, const float* pos, const float* vel, size_t n) {
+    if (!w) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    if (n == 0) return SPH_OK;
+    if (!pos) return w->fail(SPH_ERR_INVALID, "sph_fluid_append: null positions");
+    TRY(enter(w));
+    TRY(stage_down(w));
+    FluidRec& f = w->fluids[fluid];
+    size_t at = f.offset + f.n;
+    float r = w->desc.particle_radius;
+    float pv = r * r * r * (float)(8.0 * 0.8);
+    w->h_pos.insert(w->h_pos.begin() + 3 * at, pos, pos + 3 * n);
+    if (vel) w->h_vel.insert(w->h_vel.begin() + 3 * at, vel, vel + 3 * n);
+    else w->h_vel.insert(w->h_vel.begin() + 3 * at, 3 * n, 0.f);
+    w->h_vc.insert(w->h_vc.begin() + 3 * at, 3 * n, 0.f);
+    w->h_vol.insert(w->h_vol.begin() + at, n, pv);
+    w->h_press.resize(w->h_vol.size() - n, 0.f);
+    w->h_press.insert(w->h_press.begin() + at, n, 0.f);
+    f.n += n;
+    f.pending_delete.resize(f.n, 0);
+    recompute_offsets(w);
+    return SPH_OK;
+}
+
+sph_status sph_fluid_delete(sph_world* w, uint32_t fluid, const uint8_t* mask, size_t n) {
+    if (!w || !mask) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    FluidRec& f = w->fluids[fluid];
+    if (n != f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_delete: mask length %zu != particle count %zu", n, f.n);
+    for (size_t i = 0; i < n; ++i)
+        if (mask[i] && !f.pending_delete[i]) {
+            f.pending_delete[i] = 1;
+            f.n_pending++;
+        }
+    return SPH_OK;
+}
+
+sph_status sph_fluid_count(sph_world* w, uint32_t fluid, size_t* n) {
+    if (!w || !n) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    *n = w->fluids[fluid].n;
+    return SPH_OK;
+}
+
+sph_status sph_fluid_write(sph_world* w, uint32_t fluid, const float* pos, const float* vel, size_t n) {
+    if (!w) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    FluidRec& f = w->fluids[fluid];
+    if (n != f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_write: length %zu != particle count %zu", n, f.n);
+    if (n == 0 || (!pos && !vel)) return SPH_OK;
+    if (w->staged) {
+        if (pos) memcpy(w->h_pos.data() + 3 * f.offset, pos, 3 * n * sizeof(float));
+        if (vel) memcpy(w->h_vel.data() + 3 * f.offset, vel, 3 * n * sizeof(float));
+        return SPH_OK;
+    }
+    TRY(enter(w));
+    size_t N = w->N;
+    int c = w->cur;
+    CU(w->o_a.ensure(3 * N));
+    CU(w->o_b.ensure(3 * N));
+    if (pos) CU(cudaMemcpyAsync(w->o_a.p + 3 * f.offset, pos, 3 * n * sizeof(float), cudaMemcpyHostToDevice, w->st));
+    if (vel) CU(cudaMemcpyAsync(w->o_b.p + 3 * f.offset, vel, 3 * n * sizeof(float), cudaMemcpyHostToDevice, w->st));
+    LAUNCH(k_import, N, 256, (uint32_t)N, w->orig[c].p, pos ? w->o_a.p : nullptr, vel ? w->o_b.p : nullptr, (const float*)nullptr,
+           (const float*)nullptr, (const uint32_t*)nullptr, w->pos[c].p, w->vel[c].p, w->vc[c].p, (uint32_t)f.offset, (uint32_t)(f.offset + n));
+    CU(cudaStreamSynchronize(w->st));
+    w->lists_valid = false;
+    return SPH_OK;
+}
+
+sph_status sph_fluid_read(sph_world* w, uint32_t fluid, float* pos, float* vel, size_t cap, size_t* n_out) {
+    if (!w) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    FluidRec& f = w->fluids[fluid];
+    if (n_out) *n_out = f.n;
+    if (cap < f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_read: capacity %zu < particle count %zu", cap, f.n);
+    if (f.n == 0 || (!pos && !vel)) return SPH_OK;
+    if (w->staged) {
+        if (pos) memcpy(pos, w->h_pos.data() + 3 * f.offset, 3 * f.n * sizeof(float));
+        if (vel) memcpy(vel, w->h_vel.data() + 3 * f.offset, 3 * f.n * sizeof(float));
+        return SPH_OK;
+    }
+    TRY(enter(w));
+    size_t N = w->N;
+    int c = w->cur;
+    CU(w->o_a.ensure(3 * N));
+    CU(w->o_b.ensure(3 * N));
+    if (pos) {
+        LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, w->pos[c].p, w->o_a.p);
+        CU(cudaMemcpyAsync(pos, w->o_a.p + 3 * f.offset, 3 * f.n * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+    }
+    if (vel) {
+        LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, w->vel[c].p, w->o_b.p);
+        CU(cudaMemcpyAsync(vel, w->o_b.p + 3 * f.offset, 3 * f.n * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+    }
+    CU(cudaStreamSynchronize(w->st));
+    return SPH_OK;
+}
+
+sph_status sph_boundary_add(sph_world* w, const float* pos, const float* vel, size_t n, uint32_t memberships, uint32_t filter, int want_forces,
+                            uint32_t* handle) {
+    if (!w) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (n && !pos) return w->fail(SPH_ERR_INVALID, "sph_boundary_add: null positions");
+    if (w->bounds.size() >= (size_t)MAX_BOUNDARIES) return w->fail(SPH_ERR_INVALID, "too many boundaries (max %d)", MAX_BOUNDARIES);
+    BoundaryRec b;
+    b.n = n;
+    b.memberships = memberships;
+    b.filter = filter;
+    b.want_forces = want_forces != 0;
+    w->hb_pos.insert(w->hb_pos.end(), pos, pos + 3 * n);
+    if (vel) w->hb_vel.insert(w->hb_vel.end(), vel, vel + 3 * n);
+    else w->hb_vel.insert(w->hb_vel.end(), 3 * n, 0.f);
+    w->bounds.push_back(b);
+    recompute_offsets(w);
+    w->b_dirty = true;
+    if (handle) *handle = (uint32_t)w->bounds.size() - 1;
+    return SPH_OK;
+}
+
+sph_status sph_boundary_write(sph_world* w, uint32_t boundary, const float* pos, const float* vel, size_t n) {
+    if (!w) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (boundary >= w->bounds.size()) return w->fail(SPH_ERR_INVALID, "bad boundary handle %u", boundary);
+    BoundaryRec& b = w->bounds[boundary];
+    if (n != b.n) return w->fail(SPH_ERR_INVALID, "sph_boundary_write: length %zu != particle count %zu", n, b.n);
+    if (pos) memcpy(w->hb_pos.data() + 3 * b.offset, pos, 3 * n * sizeof(float));
+    if (vel) memcpy(w->hb_vel.data() + 3 * b.offset, vel, 3 * n * sizeof(float));
+    w->b_dirty = true;
+    return SPH_OK;
+}
+
+static sph_status boundary_export(sph_world* w, uint32_t boundary, float* out, size_t cap, bool forces) {
+    if (boundary >= w->bounds.size()) return w->fail(SPH_ERR_INVALID, "bad boundary handle %u", boundary);
+    BoundaryRec& b = w->bounds[boundary];
+    if (cap < b.n) return w->fail(SPH_ERR_INVALID, "capacity %zu < boundary particle count %zu", cap, b.n);
+    if (b.n == 0) return SPH_OK;
+    size_t width = forces ? 3 : 1;
+    if (w->b_dirty || (forces && !b.want_forces)) {
+        memset(out, 0, width * b.n * sizeof(float));
+        return SPH_OK;
+    }
+    TRY(enter(w));
+    size_t B = w->B;
+    int bc = w->bcur;
+    CU(w->o_c.ensure(3 * std::max(B, w->N)));
+    if (forces) {
+        // bforce is indexed by SORTED boundary index; reuse k_export3 through a float4 view is not possible -> small loop kernel
+        LAUNCH(k_export_rows3, B, 256, (uint32_t)B, w->borig[bc].p, w->bforce.p, w->o_c.p);
+    } else {
+        LAUNCH(k_export_w, B, 256, (uint32_t)B, w->borig[bc].p, w->bpos[bc].p, w->o_c.p);
+    }
+    CU(cudaMemcpyAsync(out, w->o_c.p + width * b.offset, width * b.n * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    return SPH_OK;
+}
+
+sph_status sph_boundary_read_forces(sph_world* w, uint32_t boundary, float* f_xyz, size_t cap) {
+    if (!w || !f_xyz) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    return boundary_export(w, boundary, f_xyz, cap, true);
+}
+sph_status sph_boundary_read_volumes(sph_world* w, uint32_t boundary, float* volumes, size_t cap) {
+    if (!w || !volumes) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    return boundary_export(w, boundary, volumes, cap, false);
+}
+
+sph_status sph_world_step(sph_world* w, float dt, const float gravity[3]) {
+    if (!w || !gravity) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    sph_status s = world_step(w, dt, gravity);
+    if (s != SPH_OK) cudaStreamSynchronize(w->st);
+    return s;
+}
+
+sph_status sph_world_force_iterations(sph_world* w, int32_t n_div, int32_t n_press) {
+    if (!w) return SPH_ERR_INVALID;
+    w->force_div = n_div;
+    w->force_press = n_press;
+    return SPH_OK;
+}
+
+sph_status sph_world_stats(sph_world* w, sph_step_stats* out) {
+    if (!w || !out) return SPH_ERR_INVALID;
+    *out = w->stats;
+    return SPH_OK;
+}
+
+float sph_world_h(const sph_world* w) { return w ? w->h : 0.f; }
+float sph_world_particle_radius(const sph_world* w) { return w ? w->desc.particle_radius : 0.f; }
+
+sph_status sph_debug_read(sph_world* w, uint32_t fluid, int what, float* out, size_t cap) {
+    if (!w || !out) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    FluidRec& f = w->fluids[fluid];
+    bool vec = what == SPH_DBG_VELOCITY_CHANGE || what == SPH_DBG_ACCELERATION;
+    size_t width = vec ? 3 : 1;
+    if (cap < f.n) return w->fail(SPH_ERR_INVALID, "sph_debug_read: capacity %zu < particle count %zu", cap, f.n);
+    if (f.n == 0) return SPH_OK;
+    if (w->staged) {
+        if (what == SPH_DBG_VELOCITY_CHANGE) memcpy(out, w->h_vc.data() + 3 * f.offset, 3 * f.n * sizeof(float));
+        else memset(out, 0, width * f.n * sizeof(float));
+        return SPH_OK;
+    }
+    TRY(enter(w));
+    size_t N = w->N;
+    int c = w->cur;
+    CU(w->o_c.ensure(3 * std::max(N, w->B)));
+    const float* s1 = nullptr;
+    switch (what) {
+        case SPH_DBG_DENSITY: s1 = w->dens.p; break;
+        case SPH_DBG_ALPHA: s1 = w->alpha.p; break;
+        case SPH_DBG_DIVERGENCE: s1 = w->divv.p; break;
+        case SPH_DBG_PREDICTED_DENSITY: s1 = w->desc.solver == SPH_SOLVER_IISPH ? iisph_pred(w) : w->pred.p; break;
+        case SPH_DBG_PRESSURE: s1 = w->press[c].p; break;
+        default: break;
+    }
+    if (s1) LAUNCH(k_export1, N, 256, (uint32_t)N, w->orig[c].p, s1, w->o_c.p);
+    else if (what == SPH_DBG_VELOCITY_CHANGE) LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, w->vc[c].p, w->o_c.p);
+    else if (what == SPH_DBG_ACCELERATION) LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, w->dbg_acc.p, w->o_c.p);
+    else if (what == SPH_DBG_NUM_FLUID_CONTACTS) LAUNCH(k_export1u, N, 256, (uint32_t)N, w->orig[c].p, w->cnt_f.p, w->o_c.p);
+    else if (what == SPH_DBG_NUM_BOUNDARY_CONTACTS) LAUNCH(k_export1u, N, 256, (uint32_t)N, w->orig[c].p, w->cnt_b.p, w->o_c.p);
+    else return w->fail(SPH_ERR_INVALID, "sph_debug_read: unknown selector %d", what);
+    CU(cudaMemcpyAsync(out, w->o_c.p + width * f.offset, width * f.n * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    return SPH_OK;
+}
+
+const char* sph_last_error(const sph_world* w) { return w ? w->err.c_str() : "null world"; }
+const char* sph_version(void) { return "salva_b200 0.1 (sm_100a)"; }
+
+sph_status sph_world_attach_nccl(sph_world* w, void* nccl_comm, int rank, int nranks) {
+    if (!w) return SPH_ERR_INVALID;
+    (void)nccl_comm; (void)rank; (void)nranks;
+    return w->fail(SPH_ERR_NCCL, "multi-GPU slab exchange is not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,280 @@
+"""Host-side mirror of salva3d's solver-path API on top of the C ABI (include/sph.h).
+
+The reference toolchain (Rust) is absent here, so the host side above the C ABI is this thin Python
+mirror with the reference's names and argument meaning (the Rust shim a maintainer would add is in
+INTEGRATION.md).  Mirrors:
+  LiquidWorld::{new, step, add_fluid, add_boundary, h, particle_radius}   liquid_world.rs:39-208
+  Fluid::{new, add_particles, delete_particle_at_next_timestep, num_particles}  fluid.rs:40-185
+  Boundary::new                                                           boundary.rs:28-46
+  DFSPHSolver::new / IISPHSolver::new (public tunables)                   dfsph_solver.rs:54-70, iisph_solver.rs:48-64
+  XSPHViscosity / ArtificialViscosity / Akinci2013SurfaceTension / Becker2009Elasticity ::new
+Every call goes to the CUDA library; there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ForceDesc, StepStats, WorldDesc
+
+DBG = dict(density=0, alpha=1, divergence=2, predicted_density=3, velocity_change=4, num_fluid_contacts=5,
+           num_boundary_contacts=6, pressure=7, acceleration=8)
+_VEC = {4, 8}
+
+
+class SphError(RuntimeError):
+    """A non-OK sph_status; reference assertion sites surface here (the Rust shim re-panics)."""
+
+    def __init__(self, status, message):
+        super().__init__("%s: %s" % (_lib.STATUS_NAMES.get(status, status), message))
+        self.status = status
+
+
+class InteractionGroups:
+    """interaction_groups.rs:20-79; default = (GROUP_1, ALL)."""
+
+    def __init__(self, memberships=1, filter=0xFFFFFFFF):
+        self.memberships, self.filter = memberships, filter
+
+    def test(self, rhs):
+        return (self.memberships & rhs.filter) != 0 and (rhs.memberships & self.filter) != 0
+
+
+class DFSPHSolver:
+    """dfsph_solver.rs:54-70 defaults."""
+    kind = 0
+
+    def __init__(self):
+        self.min_pressure_iter, self.max_pressure_iter, self.max_density_error = 1, 50, 0.05
+        self.min_divergence_iter, self.max_divergence_iter, self.max_divergence_error = 1, 50, 0.1
+        self.omega = 0.5
+
+
+class IISPHSolver(DFSPHSolver):
+    """iisph_solver.rs:48-64 defaults."""
+    kind = 1
+
+
+class XSPHViscosity:
+    kind = 0
+
+    def __init__(self, fluid_viscosity_coefficient, boundary_viscosity_coefficient):
+        self.params = [fluid_viscosity_coefficient, boundary_viscosity_coefficient]
+
+
+class ArtificialViscosity:
+    kind = 1
+
+    def __init__(self, fluid_viscosity_coefficient, boundary_viscosity_coefficient, alpha=1.0, beta=0.0,
+                 speed_of_sound=10.0):
+        self.params = [fluid_viscosity_coefficient, boundary_viscosity_coefficient, alpha, beta, speed_of_sound]
+
+
+class Akinci2013SurfaceTension:
+    kind = 2
+
+    def __init__(self, fluid_tension_coefficient, boundary_adhesion_coefficient):
+        self.params = [fluid_tension_coefficient, boundary_adhesion_coefficient]
+
+
+class Becker2009Elasticity:
+    kind = 3
+
+    def __init__(self, young_modulus, poisson_ratio, nonlinear_strain):
+        self.params = [young_modulus, poisson_ratio, 1.0 if nonlinear_strain else 0.0]
+
+
+class Fluid:
+    """fluid.rs:12-68: host description handed to LiquidWorld.add_fluid."""
+
+    def __init__(self, particle_positions, particle_radius, density0, interaction_groups=None):
+        self.positions = np.ascontiguousarray(particle_positions, np.float32).reshape(-1, 3)
+        self.velocities = None
+        self.volumes = None
+        self.particle_radius = particle_radius
+        self.density0 = density0
+        self.interaction_groups = interaction_groups or InteractionGroups()
+        self.nonpressure_forces = []
+
+    def num_particles(self):
+        return len(self.positions)
+
+
+class Boundary:
+    """boundary.rs:11-46"""
+
+    def __init__(self, particle_positions, interaction_groups=None, want_forces=False):
+        self.positions = np.ascontiguousarray(particle_positions, np.float32).reshape(-1, 3)
+        self.velocities = None
+        self.interaction_groups = interaction_groups or InteractionGroups()
+        self.want_forces = want_forces
+
+
+def _f32(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a.reshape(shape) if shape is not None else a
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class LiquidWorld:
+    """liquid_world.rs:17-158 on the GPU engine."""
+
+    def __init__(self, solver=None, particle_radius=0.05, smoothing_factor=2.0, device=0, deterministic=True,
+                 slab_rank=0, slab_count=1):
+        solver = solver or DFSPHSolver()
+        self._L = _lib.lib()
+        d = WorldDesc()
+        self._L.sph_world_desc_default(C.byref(d))
+        d.solver = solver.kind
+        d.particle_radius = particle_radius
+        d.smoothing_factor = smoothing_factor
+        d.min_pressure_iter, d.max_pressure_iter = solver.min_pressure_iter, solver.max_pressure_iter
+        d.max_density_error = solver.max_density_error
+        d.min_divergence_iter, d.max_divergence_iter = solver.min_divergence_iter, solver.max_divergence_iter
+        d.max_divergence_error = solver.max_divergence_error
+        d.omega = solver.omega
+        d.device = device
+        d.deterministic = int(deterministic)
+        d.slab_rank, d.slab_count = slab_rank, slab_count
+        self._w = C.c_void_p()
+        st = self._L.sph_world_create(C.byref(d), C.byref(self._w))
+        if st != 0:
+            self._w = None
+            raise SphError(st, "sph_world_create failed (no CUDA device?); there is no CPU fallback")
+        self._nb = {}
+
+    def close(self):
+        if getattr(self, "_w", None):
+            self._L.sph_world_destroy(self._w)
+            self._w = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, st):
+        if st != 0:
+            raise SphError(st, self._L.sph_last_error(self._w).decode())
+
+    # -- reference-shaped API ------------------------------------------------------------------
+    @property
+    def h(self):
+        return self._L.sph_world_h(self._w)
+
+    @property
+    def particle_radius(self):
+        return self._L.sph_world_particle_radius(self._w)
+
+    def add_fluid(self, fluid_or_positions, density0=1000.0, velocities=None, volumes=None, memberships=1,
+                  filter=0xFFFFFFFF):
+        forces = []
+        if isinstance(fluid_or_positions, Fluid):
+            f = fluid_or_positions
+            p, velocities, volumes, density0 = f.positions, f.velocities, f.volumes, f.density0
+            memberships, filter = f.interaction_groups.memberships, f.interaction_groups.filter
+            forces = f.nonpressure_forces
+        else:
+            p = fluid_or_positions
+        p = _f32(p, (-1, 3))
+        v = _f32(velocities, (-1, 3))
+        vol = _f32(volumes)
+        h = C.c_uint32()
+        self._ck(self._L.sph_fluid_add(self._w, _fp(p), _fp(v), _fp(vol), len(p), density0, memberships, filter,
+                                       C.byref(h)))
+        for fo in forces:
+            self.push_force(h.value, fo.kind, fo.params)
+        return h.value
+
+    def push_force(self, fluid, kind, params):
+        d = ForceDesc()
+        d.kind = kind
+        for i, x in enumerate(params):
+            d.p[i] = x
+        self._ck(self._L.sph_fluid_push_force(self._w, fluid, C.byref(d)))
+
+    def add_boundary(self, boundary_or_positions, velocities=None, memberships=1, filter=0xFFFFFFFF,
+                     want_forces=False):
+        if isinstance(boundary_or_positions, Boundary):
+            b = boundary_or_positions
+            p, velocities, want_forces = b.positions, b.velocities, b.want_forces
+            memberships, filter = b.interaction_groups.memberships, b.interaction_groups.filter
+        else:
+            p = boundary_or_positions
+        p = _f32(p, (-1, 3))
+        v = _f32(velocities, (-1, 3))
+        h = C.c_uint32()
+        self._ck(self._L.sph_boundary_add(self._w, _fp(p), _fp(v), len(p), memberships, filter, int(want_forces),
+                                          C.byref(h)))
+        self._nb[h.value] = len(p)
+        return h.value
+
+    def step(self, dt, gravity=(0.0, -9.81, 0.0)):
+        g = np.asarray(gravity, np.float32)
+        self._ck(self._L.sph_world_step(self._w, dt, _fp(g)))
+
+    # -- particle access (fluids_mut() edits, fluid.rs / liquid_world.rs:181-198) -------------------
+    def num_particles(self, fluid):
+        n = C.c_size_t()
+        self._ck(self._L.sph_fluid_count(self._w, fluid, C.byref(n)))
+        return n.value
+
+    def read_fluid(self, fluid, positions=None, velocities=None):
+        """Returns (positions, velocities) in ORIGINAL index order; optional preallocated outputs."""
+        n = self.num_particles(fluid)
+        p = np.empty((n, 3), np.float32) if positions is None else positions
+        v = np.empty((n, 3), np.float32) if velocities is None else velocities
+        m = C.c_size_t()
+        self._ck(self._L.sph_fluid_read(self._w, fluid, _fp(p), _fp(v), n, C.byref(m)))
+        return p, v
+
+    def write_fluid(self, fluid, positions=None, velocities=None):
+        p = _f32(positions, (-1, 3))
+        v = _f32(velocities, (-1, 3))
+        n = len(p) if p is not None else len(v)
+        self._ck(self._L.sph_fluid_write(self._w, fluid, _fp(p), _fp(v), n))
+
+    def append_particles(self, fluid, positions, velocities=None):
+        p = _f32(positions, (-1, 3))
+        v = _f32(velocities, (-1, 3))
+        self._ck(self._L.sph_fluid_append(self._w, fluid, _fp(p), _fp(v), len(p)))
+
+    def delete_particles(self, fluid, mask):
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        self._ck(self._L.sph_fluid_delete(self._w, fluid, m.ctypes.data_as(C.POINTER(C.c_uint8)), len(m)))
+
+    def write_boundary(self, b, positions=None, velocities=None):
+        p = _f32(positions, (-1, 3))
+        v = _f32(velocities, (-1, 3))
+        self._ck(self._L.sph_boundary_write(self._w, b, _fp(p), _fp(v), self._nb[b]))
+
+    def read_boundary(self, b):
+        n = self._nb[b]
+        vol = np.empty(n, np.float32)
+        f = np.zeros((n, 3), np.float32)
+        self._ck(self._L.sph_boundary_read_volumes(self._w, b, _fp(vol), n))
+        self._ck(self._L.sph_boundary_read_forces(self._w, b, _fp(f), n))
+        return vol, f
+
+    # -- parity / bench aids -----------------------------------------------------------------------
+    def force_iterations(self, n_div=-1, n_press=-1):
+        self._ck(self._L.sph_world_force_iterations(self._w, n_div, n_press))
+
+    def stats(self):
+        s = StepStats()
+        self._ck(self._L.sph_world_stats(self._w, C.byref(s)))
+        out = {}
+        for name, _ in StepStats._fields_:
+            v = getattr(s, name)
+            out[name] = list(v) if name == "grid_dims" else v
+        return out
+
+    def debug(self, fluid, what):
+        code = DBG[what] if isinstance(what, str) else what
+        n = self.num_particles(fluid)
+        out = np.zeros((n, 3) if code in _VEC else (n,), np.float32)
+        self._ck(self._L.sph_debug_read(self._w, fluid, code, _fp(out), n))
+        return out

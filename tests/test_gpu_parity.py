@@ -1,0 +1,199 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs (SURVEY.md §8c tolerances, written next to each assert).
+
+  - neighbour counts: exact (integer)
+  - rho, alpha, div, rho*: rel <= 1e-5 (+ abs 1e-6 * rho0 scale)
+  - N-step trajectories with forced iteration counts: max|dx| <= 1e-3 h, max|dv| <= 1e-3 h/dt
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle import OracleWorld
+from salva_b200 import DFSPHSolver, LiquidWorld, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(scene, solver=0, **kw):
+    r = scene["particle_radius"]
+    gpu = LiquidWorld(DFSPHSolver(), particle_radius=r, smoothing_factor=2.0, **kw)
+    cpu = OracleWorld(r, 2.0, solver=solver)
+    fg, bg = scenes.populate(gpu, scene)
+    fc, bc = scenes.populate(cpu, scene)
+    return gpu, cpu, fg, fc, bg, bc
+
+
+def _small_scene(seed=3, forces=(), two_fluids=False, nx=12, ny=10, nz=9, compress=0.93, vel_sigma=0.2, want_forces=False):
+    r = 0.05
+    rng = np.random.default_rng(seed)
+    pts = scenes.jitter(scenes.block_lattice(nx, ny, nz, r * compress), r, seed, amplitude=0.3)
+    vel = rng.normal(0, vel_sigma, pts.shape).astype(np.float32)
+    tank = scenes.open_tank((-r, -r, -r), (nx * 2 * r + r, 1.0, nz * 2 * r + r), r)
+    fluids = [dict(positions=pts, velocities=vel, density0=1000.0, forces=list(forces))]
+    if two_fluids:
+        up = scenes.jitter(scenes.block_lattice(nx, 4, nz, r * compress, origin=(0.0, ny * 2 * r * compress, 0.0)), r,
+                           seed + 1, amplitude=0.3)
+        fluids.append(dict(positions=up, velocities=rng.normal(0, vel_sigma, up.shape).astype(np.float32),
+                           density0=800.0, forces=list(forces)))
+    return dict(particle_radius=r, fluids=fluids, boundaries=[dict(positions=tank, want_forces=want_forces)])
+
+
+def _rel(a, b, scale=None):
+    scale = np.abs(b).max() if scale is None else scale
+    return float(np.abs(a - b).max() / max(scale, 1e-30))
+
+
+def test_single_pass_quantities_match_oracle():
+    sc = _small_scene()
+    gpu, cpu, fg, fc, bg, bc = _pair(sc)
+    for w in (gpu, cpu):
+        w.force_iterations(1, 1)
+        w.step(0.005)
+    f, o = fg[0], fc[0]
+    assert np.array_equal(gpu.debug(f, "num_fluid_contacts"), cpu.debug(o, "num_fluid_contacts"))      # exact
+    assert np.array_equal(gpu.debug(f, "num_boundary_contacts"), cpu.debug(o, "num_boundary_contacts"))  # exact
+    assert _rel(gpu.debug(f, "density"), cpu.debug(o, "density")) <= 1e-5
+    assert _rel(gpu.debug(f, "alpha"), cpu.debug(o, "alpha")) <= 1e-5
+    assert _rel(gpu.debug(f, "divergence"), cpu.debug(o, "divergence")) <= 1e-4
+    assert _rel(gpu.debug(f, "predicted_density"), cpu.debug(o, "predicted_density")) <= 1e-5
+    volg, _ = gpu.read_boundary(bg[0])
+    volc, _ = cpu.read_boundary(bc[0])
+    assert _rel(volg, volc) <= 1e-5
+    sg, so = gpu.stats(), cpu.stats()
+    assert sg["n_contacts"] == so["n_contacts"]
+
+
+@pytest.mark.parametrize("forces", [(), (scenes.xsph_viscosity(0.5, 0.3),), (scenes.artificial_viscosity(1.0, 0.5),),
+                                    (scenes.akinci2013_surface_tension(1.0, 0.7),)],
+                         ids=["none", "xsph", "artificial", "akinci2013"])
+def test_trajectory_forced_iterations(forces):
+    sc = _small_scene(seed=5, forces=forces)
+    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    dt = 0.005
+    for w in (gpu, cpu):
+        w.force_iterations(2, 3)
+    for _ in range(10):
+        gpu.step(dt)
+        cpu.step(dt)
+    pg, vg = gpu.read_fluid(fg[0])
+    pc, vc = cpu.read_fluid(fc[0])
+    h = float(gpu.h)
+    assert _rel(gpu.debug(fg[0], "acceleration"), cpu.debug(fc[0], "acceleration")) <= 1e-3
+    assert np.abs(pg - pc).max() <= 1e-3 * h
+    assert np.abs(vg - vc).max() <= 1e-3 * h / dt
+
+
+def test_two_fluids_with_groups_and_free_running_iterations():
+    sc = _small_scene(seed=9, forces=(scenes.xsph_viscosity(0.5, 0.0),), two_fluids=True)
+    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    for _ in range(4):
+        gpu.step(0.005)
+        cpu.step(0.005)
+        sg, so = gpu.stats(), cpu.stats()
+        assert sg["n_divergence_iter"] == so["n_divergence_iter"]
+        assert sg["n_pressure_iter"] == so["n_pressure_iter"]
+        assert sg["last_density_error"] == pytest.approx(so["last_density_error"], rel=1e-3, abs=1e-7)
+    h = float(gpu.h)
+    for a, b in zip(fg, fc):
+        pg, vg = gpu.read_fluid(a)
+        pc, vc = cpu.read_fluid(b)
+        assert np.array_equal(gpu.debug(a, "num_fluid_contacts"), cpu.debug(b, "num_fluid_contacts"))
+        assert np.abs(pg - pc).max() <= 1e-3 * h
+
+
+def test_interaction_groups_filter_pairs():
+    """Two fluids whose groups do not match never see each other (contacts.rs:355-362)."""
+    sc = _small_scene(seed=11, two_fluids=True)
+    sc["fluids"][0].update(memberships=1, filter=1)
+    sc["fluids"][1].update(memberships=2, filter=2)
+    sc["boundaries"][0].update(memberships=3, filter=3)
+    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    for w in (gpu, cpu):
+        w.force_iterations(1, 2)
+        w.step(0.005)
+    for a, b in zip(fg, fc):
+        assert np.array_equal(gpu.debug(a, "num_fluid_contacts"), cpu.debug(b, "num_fluid_contacts"))
+        assert _rel(gpu.debug(a, "density"), cpu.debug(b, "density")) <= 1e-5
+
+
+def test_config_c1_basic3_ten_steps():
+    """BASELINE.json configs[0]: examples3d/basic3.rs scene, reference CPU (f32)."""
+    sc = scenes.scene_c1()
+    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    for w in (gpu, cpu):
+        w.force_iterations(1, 2)
+    for _ in range(10):
+        gpu.step(sc["dt"])
+        cpu.step(sc["dt"])
+    pg, vg = gpu.read_fluid(fg[0])
+    pc, vc = cpu.read_fluid(fc[0])
+    h = float(gpu.h)
+    assert np.array_equal(gpu.debug(fg[0], "num_fluid_contacts"), cpu.debug(fc[0], "num_fluid_contacts"))
+    assert np.abs(pg - pc).max() <= 1e-3 * h
+    assert np.abs(vg - vc).max() <= 1e-3 * h / sc["dt"]
+
+
+def test_host_edits_append_delete_roundtrip():
+    """fluids_mut() edits, Fluid::add_particles (fluid.rs:126-150) and deletion (fluid.rs:71-98) keep ORIGINAL
+    index order and match the oracle's host-side semantics."""
+    sc = _small_scene(seed=13, nx=8, ny=6, nz=6)
+    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    f, o = fg[0], fc[0]
+    rng = np.random.default_rng(1)
+    for w in (gpu, cpu):
+        w.force_iterations(1, 2)
+        w.step(0.005)
+    p0, v0 = gpu.read_fluid(f)
+    newv = (v0 * 0.5).astype(np.float32)
+    extra = (p0[:20] + np.array([0.0, 0.8, 0.0], np.float32)).astype(np.float32)
+    mask = np.zeros(len(p0), np.uint8)
+    mask[rng.choice(len(p0), 30, replace=False)] = 1
+    for w, h in ((gpu, f), (cpu, o)):
+        w.write_fluid(h, velocities=newv)
+        w.delete_particles(h, mask)
+        w.append_particles(h, extra)
+        w.step(0.005)
+        w.step(0.005)
+    assert gpu.num_particles(f) == cpu.num_particles(o) == len(p0) - 30 + 20
+    pg, vg = gpu.read_fluid(f)
+    pc, vc = cpu.read_fluid(o)
+    assert np.abs(pg - pc).max() <= 1e-3 * float(gpu.h)
+
+
+def test_boundary_forces_accumulate_like_reference():
+    """Boundary::apply_force (boundary.rs:62-67) writers: dfsph_solver.rs:269-272,403-405 and the force plugins."""
+    sc = _small_scene(seed=17, forces=(scenes.xsph_viscosity(0.5, 0.3),), want_forces=True)
+    gpu, cpu, fg, fc, bg, bc = _pair(sc)
+    for w in (gpu, cpu):
+        w.force_iterations(2, 3)
+    for _ in range(3):
+        gpu.step(0.005)
+        cpu.step(0.005)
+    _, fgp = gpu.read_boundary(bg[0])
+    _, fcp = cpu.read_boundary(bc[0])
+    assert np.abs(fcp).max() > 0
+    assert _rel(fgp, fcp) <= 1e-3
+
+
+def test_deterministic_mode_is_bit_reproducible():
+    sc = _small_scene(seed=21)
+    outs = []
+    for _ in range(2):
+        gpu = LiquidWorld(particle_radius=sc["particle_radius"], deterministic=True)
+        fg, _ = scenes.populate(gpu, sc)
+        for _ in range(5):
+            gpu.step(0.005)
+        outs.append(gpu.read_fluid(fg[0]))
+        gpu.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_error_paths():
+    from salva_b200 import SphError
+    gpu = LiquidWorld(particle_radius=0.05)
+    f = gpu.add_fluid(np.array([[0, 0, 0], [np.nan, 0, 0]], np.float32))
+    with pytest.raises(SphError) as e:
+        gpu.step(0.005)
+    assert e.value.status == 1
+    with pytest.raises(SphError):
+        gpu.read_fluid(f + 7)
