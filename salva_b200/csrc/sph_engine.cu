@@ -471,6 +471,7 @@ sph_status phase_grid(sph_world* w) {
         }
         LAUNCH(k_gather, N, 256, (uint32_t)N, w->perm.p, g);
         w->cur = c ^ 1;
+        LAUNCH(k_make_vstar, N, 256, w->vel[w->cur].p, w->vc[w->cur].p, w->vs.p);
     }
     // boundaries: same sort
     CU(cudaMemsetAsync(w->bstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));

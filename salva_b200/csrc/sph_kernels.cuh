@@ -540,6 +540,14 @@ k_divergence_update(const float4* __restrict__ pos, const float4* __restrict__ v
     vs[i] = make_float4(v.x + c4.x, v.y + c4.y, v.z + c4.z, 0.f);
 }
 
+// v* = vel + vc after the reorder (the divergence solve works on vel + vc carried over from the previous step, Appendix A.3.2)
+__global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __restrict__ vc, float4* __restrict__ vs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_fluid) return;
+    float4 v = vel[i], c = vc[i];
+    vs[i] = make_float4(v.x + c.x, v.y + c.y, v.z + c.z, 0.f);
+}
+
 // a10: update_velocities dfsph_solver.rs:422-430 + zero vc :689-691 + acc = gravity (predict_advection :574-578)
 __global__ void k_fold_velocities(float4* __restrict__ vel, float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ acc, float gx, float gy,
                                   float gz) {
