@@ -86,6 +86,10 @@ typedef struct {
     float    nonpressure_ms;         /* solver.non_pressure_resolution_time */
     float    pressure_ms;            /* pressure_solve (the roofline-capture region) */
     float    integrate_ms;
+    float    divergence_eval_ms;     /* sum over compute_divergences launches              (kernel K4a) */
+    float    divergence_update_ms;   /* sum over compute_velocity_changes_for_divergence   (kernel K4b) */
+    float    predict_density_ms;     /* sum over compute_predicted_densities launches      (kernel K8a) */
+    float    pressure_update_ms;     /* sum over compute_velocity_changes launches         (kernel K8b) */
     uint32_t n_divergence_iter;      /* velocity-change updates executed in divergence_solve */
     uint32_t n_pressure_iter;        /* velocity-change updates executed in pressure_solve */
     uint32_t n_divergence_eval;      /* compute_divergences launches */

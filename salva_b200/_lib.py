@@ -28,7 +28,8 @@ class ForceDesc(C.Structure):
 
 class StepStats(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("step_ms", "grid_ms", "neighbors_ms", "density_ms", "divergence_ms",
-                                         "nonpressure_ms", "pressure_ms", "integrate_ms")] + \
+                                         "nonpressure_ms", "pressure_ms", "integrate_ms", "divergence_eval_ms",
+                                         "divergence_update_ms", "predict_density_ms", "pressure_update_ms")] + \
                [(n, C.c_uint32) for n in ("n_divergence_iter", "n_pressure_iter", "n_divergence_eval",
                                           "n_pressure_eval")] + \
                [("last_divergence_error", C.c_float), ("last_density_error", C.c_float),

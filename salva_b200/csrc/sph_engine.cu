@@ -136,6 +136,11 @@ struct sph_world {
     IisphState iisph;
     float* h_pinned = nullptr;  // 64 floats of pinned host memory for small read-backs
 
+    // fine-grained kernel timers: (slot, begin, end) event pairs accumulated into stats at step end
+    struct Span { int slot; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    size_t n_spans = 0;
+
     uint32_t cap_f = 64, cap_b = 32, stride = 0;
     bool lists_valid = false;
     sph_step_stats stats;
@@ -173,6 +178,24 @@ namespace {
             w->launches++;                                                             \
         }                                                                              \
     } while (0)
+
+enum { SP_DIV_EVAL = 0, SP_DIV_UPD, SP_PRED, SP_PUPD, SP_COUNT };
+sph_status span_begin(sph_world* w, int slot) {
+    if (w->n_spans == w->spans.size()) {
+        sph_world::Span s{slot, nullptr, nullptr};
+        CU(cudaEventCreate(&s.a));
+        CU(cudaEventCreate(&s.b));
+        w->spans.push_back(s);
+    }
+    w->spans[w->n_spans].slot = slot;
+    CU(cudaEventRecord(w->spans[w->n_spans].a, w->st));
+    return SPH_OK;
+}
+sph_status span_end(sph_world* w) {
+    CU(cudaEventRecord(w->spans[w->n_spans].b, w->st));
+    w->n_spans++;
+    return SPH_OK;
+}
 
 sph_status upload_consts(sph_world* w) {
     CU(cudaMemcpyToSymbolAsync(C, &w->hc, sizeof(Consts), 0, cudaMemcpyHostToDevice, w->st));
@@ -636,7 +659,9 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     w->stats.n_divergence_iter = w->stats.n_divergence_eval = 0;
     uint32_t maxit = w->force_div >= 0 ? (uint32_t)w->force_div + 1 : w->desc.max_divergence_iter;
     for (uint32_t i = 0; i < maxit; ++i) {
+        TRY(span_begin(w, SP_DIV_EVAL));
         DISPATCH1(k_divergence, multi, N, PASS_T, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, L, w->alpha.p, w->divv.p, w->kappa.p, w->partial.p);
+        TRY(span_end(w));
         w->stats.n_divergence_eval++;
         if (w->force_div >= 0) {
             if ((int)i >= w->force_div) break;
@@ -647,8 +672,10 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
             float max_err = w->desc.max_divergence_error * w->inv_dt * 0.01f;
             if (avg <= max_err && i >= w->desc.min_divergence_iter) break;
         }
+        TRY(span_begin(w, SP_DIV_UPD));
         DISPATCH2(k_divergence_update, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->vc[c].p, w->vs.p, w->bforce.p,
                   w->inv_dt);
+        TRY(span_end(w));
         w->stats.n_divergence_iter++;
     }
     CU(cudaEventRecord(w->ev[EV_DIV], w->st));
@@ -664,8 +691,10 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     w->stats.n_pressure_iter = w->stats.n_pressure_eval = 0;
     maxit = w->force_press >= 0 ? (uint32_t)w->force_press + 1 : w->desc.max_pressure_iter;
     for (uint32_t i = 0; i < maxit; ++i) {
+        TRY(span_begin(w, SP_PRED));
         DISPATCH1(k_predict_density, multi, N, PASS_T, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->alpha.p,
                   w->pred.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
+        TRY(span_end(w));
         w->stats.n_pressure_eval++;
         if (w->force_press >= 0) {
             if ((int)i >= w->force_press) break;
@@ -675,8 +704,10 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
             w->stats.last_density_error = avg;
             if (avg <= w->desc.max_density_error && i >= w->desc.min_pressure_iter) break;
         }
+        TRY(span_begin(w, SP_PUPD));
         DISPATCH2(k_pressure_update, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->vc[c].p, w->vs.p, w->bforce.p,
                   w->inv_dt);
+        TRY(span_end(w));
         w->stats.n_pressure_iter++;
     }
     CU(cudaEventRecord(w->ev[EV_PRESS], w->st));
@@ -688,6 +719,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
 sph_status world_step(sph_world* w, float dt, const float g[3]) {
     TRY(enter(w));
     w->launches = 0;
+    w->n_spans = 0;
     memset(&w->stats, 0, sizeof w->stats);
     TRY(apply_pending_deletes(w));  // liquid_world.rs:79-81
     TRY(stage_up(w));
@@ -741,6 +773,18 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
         w->stats.nonpressure_ms = el(EV_DENS, EV_FORCES);
         w->stats.pressure_ms = el(EV_INTEG, EV_PRESS);
         w->stats.integrate_ms = el(EV_FORCES, EV_INTEG) + el(EV_PRESS, EV_END);
+    }
+    {
+        float acc[SP_COUNT] = {0.f, 0.f, 0.f, 0.f};
+        for (size_t k = 0; k < w->n_spans; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, w->spans[k].a, w->spans[k].b);
+            acc[w->spans[k].slot] += ms;
+        }
+        w->stats.divergence_eval_ms = acc[SP_DIV_EVAL];
+        w->stats.divergence_update_ms = acc[SP_DIV_UPD];
+        w->stats.predict_density_ms = acc[SP_PRED];
+        w->stats.pressure_update_ms = acc[SP_PUPD];
     }
     if (flag) return w->fail(SPH_ERR_ZERO_DENSITY, "zero density (reference asserts dfsph_solver.rs:92,145,662)");
     return SPH_OK;
@@ -821,6 +865,10 @@ void sph_world_destroy(sph_world* w) {
     iisph_release(w);
     for (auto& f : w->fluids)
         for (auto& fr : f.forces) elasticity_release(fr);
+    for (auto& s : w->spans) {
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
     if (w->h_pinned) cudaFreeHost(w->h_pinned);
     for (auto& e : w->ev)
         if (e) cudaEventDestroy(e);
