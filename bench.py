@@ -207,7 +207,7 @@ def native_arm(args, rank, world_size):
     nf, nb = scene_particles(sc)
     solver = DFSPHSolver() if sc["solver"] == 0 else IISPHSolver()
     world = LiquidWorld(solver, particle_radius=sc["particle_radius"], smoothing_factor=sc["smoothing_factor"],
-                        device=local_rank, deterministic=not args.fast_sort)
+                        device=local_rank, deterministic=not args.fast_sort, gather_backend=args.backend)
     fh, _ = scenes.populate(world, sc)
     if args.force_iters:
         world.force_iterations(*args.force_iters)
@@ -327,6 +327,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fast-sort", action="store_true", help="skip the deterministic in-cell ordering")
     ap.add_argument("--force-iters", type=int, nargs=2, default=None)
+    ap.add_argument("--backend", type=int, default=0, help="0 = L1/texture gathers (default), 1 = tile/TMA shared-memory gathers")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world_size = int(os.environ.get("WORLD_SIZE", 1))

@@ -19,7 +19,8 @@ class WorldDesc(C.Structure):
                 ("min_pressure_iter", C.c_uint32), ("max_pressure_iter", C.c_uint32), ("max_density_error", C.c_float),
                 ("min_divergence_iter", C.c_uint32), ("max_divergence_iter", C.c_uint32),
                 ("max_divergence_error", C.c_float), ("omega", C.c_float), ("device", C.c_int32),
-                ("slab_rank", C.c_int32), ("slab_count", C.c_int32), ("deterministic", C.c_int32)]
+                ("slab_rank", C.c_int32), ("slab_count", C.c_int32), ("deterministic", C.c_int32),
+                ("gather_backend", C.c_int32)]
 
 
 class ForceDesc(C.Structure):

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -18,10 +19,16 @@
 
 #include "../../include/sph.h"
 #include "sph_kernels.cuh"
+#include "sph_passes.cuh"
+#include "sph_tile.cuh"
 #include "sph_iisph.cuh"
 #include "sph_elasticity.cuh"
 
 using namespace sphk;
+
+#ifndef SALVA_B200_TEX_DEFAULT
+#define SALVA_B200_TEX_DEFAULT true
+#endif
 
 namespace {
 
@@ -128,6 +135,16 @@ struct sph_world {
     DBuf<float> dens, alpha, kappa, divv, pred, bvol, bforce;
     DBuf<uint32_t> cid, rank, perm, cstart, bcid, brank, bperm, bstart, scan_aux[3];
     DBuf<uint32_t> nbr_f, nbr_b, cnt_f, cnt_b;
+    // gather_backend 1 (sph_tile.cuh): 16-bit tile-local fluid contact indices
+    DBuf<uint16_t> nbr16;
+    uint32_t tile_slots = 2048;  // widest tile halo seen by the last neighbour build (local index space size)
+    uint32_t n_tiles = 0;
+    bool tile = false;
+    // gather_backend 0: the second per-contact gather (v* / kappa) can go through the texture pipe
+    bool use_tex = false;
+    cudaTextureObject_t tex_vs = 0, tex_kappa = 0;
+    const void* tex_vs_ptr = nullptr;
+    const void* tex_kappa_ptr = nullptr;
     DBuf<float> partial, errsum;
     DBuf<int> d_scal;  // [0..6] bounds + bad flag, [7] error flag, [8..9] maxcnt
     DBuf<unsigned long long> d_cnt;  // [0] bb contacts, [1] ff+fb contacts
@@ -304,18 +321,19 @@ sph_status ensure_fluid_buffers(sph_world* w) {
     CU(w->vs.ensure(N));
     CU(w->acc.ensure(N));
     CU(w->dbg_acc.ensure(N));
-    CU(w->dens.ensure(N));
-    CU(w->alpha.ensure(N));
-    CU(w->kappa.ensure(N));
-    CU(w->divv.ensure(N));
-    CU(w->pred.ensure(N));
+    CU(w->dens.ensure(N + 8));
+    CU(w->alpha.ensure(N + 8));
+    CU(w->kappa.ensure(N + 8));
+    CU(w->divv.ensure(N + 8));
+    CU(w->pred.ensure(N + 8));
     CU(w->cid.ensure(N));
     CU(w->rank.ensure(N));
     CU(w->perm.ensure(N));
     CU(w->cnt_f.ensure(N));
     CU(w->cnt_b.ensure(N));
     w->stride = (uint32_t)((N + 31) / 32 * 32);
-    CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
+    if (w->tile) CU(w->nbr16.ensure((size_t)w->cap_f * w->stride));
+    else CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
     CU(w->nbr_b.ensure((size_t)w->cap_b * w->stride));
     uint32_t nblk = cdiv(std::max<size_t>(N, 1), PASS_T);
     CU(w->partial.ensure((size_t)nblk * std::max<size_t>(1, w->fluids.size())));
@@ -439,7 +457,7 @@ sph_status apply_pending_deletes(sph_world* w) {
 sph_status phase_grid(sph_world* w) {
     size_t N = w->N, B = w->B;
     int c = w->cur, bc = w->bcur;
-    int init[10] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0, 0, 0};
+    int init[11] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(w->d_scal.p, init, sizeof init, cudaMemcpyHostToDevice, w->st));
     CU(cudaMemsetAsync(w->d_cnt.p, 0, 2 * sizeof(unsigned long long), w->st));
     if (N) {
@@ -465,10 +483,15 @@ sph_status phase_grid(sph_world* w) {
     w->hc.nx = (int)dims[0];
     w->hc.ny = (int)dims[1];
     w->hc.nz = (int)dims[2];
+    w->hc.ntx = (int)((dims[0] - 2 + TILE_X - 1) / TILE_X);
+    w->hc.nty = (int)((dims[1] - 2 + TILE_Y - 1) / TILE_Y);
+    w->hc.ntz = (int)((dims[2] - 2 + TILE_Z - 1) / TILE_Z);
+    w->n_tiles = (uint32_t)w->hc.ntx * w->hc.nty * w->hc.ntz;
     fill_static_consts(w);
     TRY(upload_consts(w));
     CU(w->cstart.ensure(ncell + 1));
     CU(w->bstart.ensure(ncell + 1));
+    if (w->tile) CU(w->partial.ensure((size_t)std::max<uint32_t>(w->n_tiles, 1) * std::max<size_t>(1, w->fluids.size())));
     w->stats.grid_dims[0] = (uint32_t)dims[0];
     w->stats.grid_dims[1] = (uint32_t)dims[1];
     w->stats.grid_dims[2] = (uint32_t)dims[2];
@@ -517,6 +540,60 @@ sph_status phase_grid(sph_world* w) {
     return SPH_OK;
 }
 
+// ---- tile kernel launches (gather_backend 1, sph_tile.cuh) -------------------------------------------
+constexpr size_t TILE_DYN_SMEM_LIMIT = 200 * 1024;
+// Number of halo slots staged in shared memory for a kernel that needs `slot_bytes` per slot.
+uint32_t tile_cap(const sph_world* w, uint32_t slot_bytes) {
+    uint32_t want = (w->tile_slots + 63u) / 64u * 64u;
+    uint32_t fit = (uint32_t)(TILE_DYN_SMEM_LIMIT / slot_bytes) / 64u * 64u;
+    return std::min(want, fit);
+}
+template <class K>
+cudaError_t tile_prepare(K kern) {
+    static std::mutex m;
+    static std::vector<const void*> done;
+    std::lock_guard<std::mutex> lock(m);
+    const void* key = reinterpret_cast<const void*>(kern);
+    for (const void* d : done)
+        if (d == key) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_DYN_SMEM_LIMIT);
+    if (e == cudaSuccess) done.push_back(key);
+    return e;
+}
+#define LAUNCH_TILE(kern, slot_bytes, cap, ...)                                                      \
+    do {                                                                                             \
+        if (w->n_tiles > 0) {                                                                        \
+            CU(tile_prepare(kern));                                                                  \
+            kern<<<w->n_tiles, TILE_T, (size_t)(cap) * (slot_bytes), w->st>>>(__VA_ARGS__);          \
+            w->launches++;                                                                           \
+        }                                                                                            \
+    } while (0)
+#define TDISPATCH1(kern, multi, slot_bytes, cap, ...)                               \
+    do {                                                                            \
+        if (multi) LAUNCH_TILE((kern<true>), slot_bytes, cap, __VA_ARGS__);         \
+        else LAUNCH_TILE((kern<false>), slot_bytes, cap, __VA_ARGS__);              \
+    } while (0)
+#define TDISPATCH2(kern, multi, bf, slot_bytes, cap, ...)                                  \
+    do {                                                                                   \
+        if (multi) {                                                                       \
+            if (bf) LAUNCH_TILE((kern<true, true>), slot_bytes, cap, __VA_ARGS__);         \
+            else LAUNCH_TILE((kern<true, false>), slot_bytes, cap, __VA_ARGS__);           \
+        } else {                                                                           \
+            if (bf) LAUNCH_TILE((kern<false, true>), slot_bytes, cap, __VA_ARGS__);        \
+            else LAUNCH_TILE((kern<false, false>), slot_bytes, cap, __VA_ARGS__);          \
+        }                                                                                  \
+    } while (0)
+#define TDISPATCH3(kern, multi, bf, third, slot_bytes, cap, ...)                                          \
+    do {                                                                                                  \
+        if (multi) {                                                                                      \
+            if (bf) LAUNCH_TILE((kern<true, true, third>), slot_bytes, cap, __VA_ARGS__);                 \
+            else LAUNCH_TILE((kern<true, false, third>), slot_bytes, cap, __VA_ARGS__);                   \
+        } else {                                                                                          \
+            if (bf) LAUNCH_TILE((kern<false, true, third>), slot_bytes, cap, __VA_ARGS__);                \
+            else LAUNCH_TILE((kern<false, false, third>), slot_bytes, cap, __VA_ARGS__);                  \
+        }                                                                                                 \
+    } while (0)
+
 sph_status phase_neighbors(sph_world* w) {
     size_t N = w->N, B = w->B;
     int c = w->cur, bc = w->bcur;
@@ -531,17 +608,29 @@ sph_status phase_neighbors(sph_world* w) {
             }
     }
     for (int attempt = 0; attempt < 8 && N; ++attempt) {
-        CU(cudaMemsetAsync(w->d_scal.p + 8, 0, 2 * sizeof(int), w->st));
-        if (multi)
+        CU(cudaMemsetAsync(w->d_scal.p + 8, 0, 3 * sizeof(int), w->st));
+        uint32_t* maxcnt = reinterpret_cast<uint32_t*>(w->d_scal.p + 8);
+        if (w->tile) {
+            LAUNCH(k_neighbors_boundary, N, 128, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_b.p, w->cnt_b.p, maxcnt);
+            uint32_t sb = multi ? 32u : 16u;
+            uint32_t cap = tile_cap(w, sb);
+            TDISPATCH1(k_tile_neighbors, multi, sb, cap, w->pos[c].p, w->vel[c].p, w->cstart.p, cap, w->nbr16.p, w->cnt_f.p, maxcnt);
+        } else if (multi) {
             LAUNCH((k_neighbors<true>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
-                   w->cnt_f.p, w->cnt_b.p, reinterpret_cast<uint32_t*>(w->d_scal.p + 8));
-        else
+                   w->cnt_f.p, w->cnt_b.p, maxcnt);
+        } else {
             LAUNCH((k_neighbors<false>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
-                   w->cnt_f.p, w->cnt_b.p, reinterpret_cast<uint32_t*>(w->d_scal.p + 8));
-        int hs[3];
+                   w->cnt_f.p, w->cnt_b.p, maxcnt);
+        }
+        int hs[4];
         CU(cudaMemcpyAsync(hs, w->d_scal.p + 7, sizeof hs, cudaMemcpyDeviceToHost, w->st));
         CU(cudaStreamSynchronize(w->st));
         if (hs[0]) return w->fail(SPH_ERR_ZERO_DENSITY, "zero boundary-volume denominator (reference assert dfsph_solver.rs:92)");
+        if (w->tile) {
+            if ((uint32_t)hs[3] > 65535u)
+                return w->fail(SPH_ERR_INVALID, "tile halo of %d particles exceeds the 16-bit contact index space", hs[3]);
+            w->tile_slots = std::max<uint32_t>((uint32_t)hs[3], 64u);
+        }
         w->stats.max_neighbors = (uint32_t)hs[1];
         bool grow = false;
         if ((uint32_t)hs[1] > w->cap_f) {
@@ -553,7 +642,8 @@ sph_status phase_neighbors(sph_world* w) {
             grow = true;
         }
         if (!grow) break;
-        CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
+        if (w->tile) CU(w->nbr16.ensure((size_t)w->cap_f * w->stride));
+        else CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
         CU(w->nbr_b.ensure((size_t)w->cap_b * w->stride));
         fill_static_consts(w);
         TRY(upload_consts(w));
@@ -603,20 +693,140 @@ bool any_bforce(const sph_world* w) {
         else LAUNCH((kern<false>), n, threads, __VA_ARGS__);            \
     } while (0)
 
-// predict_advection dfsph_solver.rs:580-603: every fluid's forces in push order
-sph_status phase_forces(sph_world* w, const Lists& L) {
+// ---- gather passes: one wrapper per reference function, two backends ------------------------------------
+template <class T>
+sph_status ensure_tex(sph_world* w, cudaTextureObject_t* tex, const void** cur, const T* ptr, size_t n) {
+    if (*cur == ptr && *tex) return SPH_OK;
+    if (*tex) cudaDestroyTextureObject(*tex);
+    *tex = 0;
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = const_cast<T*>(ptr);
+    rd.res.linear.desc = cudaCreateChannelDesc<T>();
+    rd.res.linear.sizeInBytes = n * sizeof(T);
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.readMode = cudaReadModeElementType;
+    CU(cudaCreateTextureObject(tex, &rd, &td, nullptr));
+    *cur = ptr;
+    return SPH_OK;
+}
+
+sph_status launch_density_alpha(sph_world* w) {
+    size_t N = w->N;
+    int c = w->cur, bc = w->bcur;
+    const bool multi = w->fluids.size() > 1;
+    if (w->tile) {
+        TileLists L{w->nbr16.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+        uint32_t cap = tile_cap(w, 16);
+        TDISPATCH1(k_tile_density_alpha, multi, 16, cap, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->cstart.p, cap, L, w->dens.p, w->alpha.p,
+                   w->d_scal.p + 7);
+    } else {
+        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+        DISPATCH1(k_density_alpha, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->alpha.p, w->d_scal.p + 7);
+    }
+    return SPH_OK;
+}
+#define BOOL3(kern, b0, b1, b2, n, threads, ...)                                                   \
+    do {                                                                                           \
+        if (b0) {                                                                                  \
+            if (b1) { if (b2) LAUNCH((kern<true, true, true>), n, threads, __VA_ARGS__); else LAUNCH((kern<true, true, false>), n, threads, __VA_ARGS__); } \
+            else    { if (b2) LAUNCH((kern<true, false, true>), n, threads, __VA_ARGS__); else LAUNCH((kern<true, false, false>), n, threads, __VA_ARGS__); } \
+        } else {                                                                                   \
+            if (b1) { if (b2) LAUNCH((kern<false, true, true>), n, threads, __VA_ARGS__); else LAUNCH((kern<false, true, false>), n, threads, __VA_ARGS__); } \
+            else    { if (b2) LAUNCH((kern<false, false, true>), n, threads, __VA_ARGS__); else LAUNCH((kern<false, false, false>), n, threads, __VA_ARGS__); } \
+        }                                                                                          \
+    } while (0)
+#define BOOL4(kern, b0, b1, b2, b3, n, threads, ...)                                               \
+    do {                                                                                           \
+        if (b3) BOOL3_T(kern, b0, b1, b2, true, n, threads, __VA_ARGS__);                          \
+        else BOOL3_T(kern, b0, b1, b2, false, n, threads, __VA_ARGS__);                            \
+    } while (0)
+#define BOOL3_T(kern, b0, b1, b2, B3, n, threads, ...)                                             \
+    do {                                                                                           \
+        if (b0) {                                                                                  \
+            if (b1) { if (b2) LAUNCH((kern<true, true, true, B3>), n, threads, __VA_ARGS__); else LAUNCH((kern<true, true, false, B3>), n, threads, __VA_ARGS__); } \
+            else    { if (b2) LAUNCH((kern<true, false, true, B3>), n, threads, __VA_ARGS__); else LAUNCH((kern<true, false, false, B3>), n, threads, __VA_ARGS__); } \
+        } else {                                                                                   \
+            if (b1) { if (b2) LAUNCH((kern<false, true, true, B3>), n, threads, __VA_ARGS__); else LAUNCH((kern<false, true, false, B3>), n, threads, __VA_ARGS__); } \
+            else    { if (b2) LAUNCH((kern<false, false, true, B3>), n, threads, __VA_ARGS__); else LAUNCH((kern<false, false, false, B3>), n, threads, __VA_ARGS__); } \
+        }                                                                                          \
+    } while (0)
+
+// compute_divergences (predict = false) / compute_predicted_densities (predict = true); returns #partials
+sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk) {
+    size_t N = w->N;
+    int c = w->cur, bc = w->bcur;
+    const bool multi = w->fluids.size() > 1;
+    if (w->tile) {
+        TileLists L{w->nbr16.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+        uint32_t cap = tile_cap(w, 32);
+        TDISPATCH2(k_tile_vel_divergence, multi, predict, 32, cap, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, w->cstart.p, cap, L,
+                   w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
+        *nblk = w->n_tiles;
+    } else {
+        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+        if (w->use_tex) TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
+        BOOL3(k_vel_divergence, multi, predict, w->use_tex, N, PASS_T, w->pos[c].p, w->vs.p, w->tex_vs, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L,
+              w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
+        *nblk = cdiv(N, PASS_T);
+    }
+    return SPH_OK;
+}
+// compute_velocity_changes_for_divergence (pressure = false) / compute_velocity_changes (pressure = true)
+sph_status launch_vel_update(sph_world* w, bool pressure) {
     size_t N = w->N;
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1, bf = any_bforce(w);
+    if (w->tile) {
+        TileLists L{w->nbr16.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+        uint32_t cap = tile_cap(w, 20);
+        if (pressure)
+            TDISPATCH3(k_tile_vel_update, multi, bf, true, 20, cap, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->cstart.p, cap, L, w->kappa.p, w->vc[c].p,
+                       w->vs.p, w->bforce.p, w->inv_dt);
+        else
+            TDISPATCH3(k_tile_vel_update, multi, bf, false, 20, cap, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->cstart.p, cap, L, w->kappa.p, w->vc[c].p,
+                       w->vs.p, w->bforce.p, w->inv_dt);
+    } else {
+        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+        // measured (profiles/r1_v1_*): the texture pipe helps the float4 v* gather (-12 %) but not the 4-byte kappa gather
+        const bool tex = false;
+        if (tex) TRY(ensure_tex(w, &w->tex_kappa, &w->tex_kappa_ptr, w->kappa.p, w->kappa.cap));
+        BOOL4(k_vel_update, multi, bf, pressure, tex, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->tex_kappa,
+              w->vc[c].p, w->vs.p, w->bforce.p, w->inv_dt);
+    }
+    return SPH_OK;
+}
+
+// predict_advection dfsph_solver.rs:580-603: every fluid's forces in push order
+sph_status phase_forces(sph_world* w) {
+    size_t N = w->N;
+    int c = w->cur, bc = w->bcur;
+    const bool multi = w->fluids.size() > 1, bf = any_bforce(w);
+    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+    TileLists TL{w->nbr16.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
     for (size_t f = 0; f < w->fluids.size(); ++f)
         for (ForceRec& fr : w->fluids[f].forces) {
             const float* p = fr.d.p;
             switch (fr.d.kind) {
                 case SPH_FORCE_XSPH_VISCOSITY:
+                    if (w->tile) {
+                        uint32_t cap = tile_cap(w, 36);
+                        TDISPATCH2(k_tile_xsph, multi, bf, 36, cap, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, w->cstart.p, cap, TL,
+                                   w->dens.p, w->acc.p, w->bforce.p, (uint32_t)f, p[0], p[1], w->inv_dt);
+                        break;
+                    }
                     DISPATCH2(k_force_xsph, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->acc.p,
                               w->bforce.p, (uint32_t)f, p[0], p[1], w->inv_dt);
                     break;
                 case SPH_FORCE_ARTIFICIAL_VISCOSITY:
+                    if (w->tile) {
+                        uint32_t cap = tile_cap(w, 36);
+                        TDISPATCH2(k_tile_artificial, multi, bf, 36, cap, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, w->cstart.p, cap, TL,
+                                   w->dens.p, w->acc.p, w->bforce.p, (uint32_t)f, p[0], p[1], p[2], p[3], p[4]);
+                        break;
+                    }
                     DISPATCH2(k_force_artificial, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->acc.p,
                               w->bforce.p, (uint32_t)f, p[0], p[1], p[2], p[3], p[4]);
                     break;
@@ -626,6 +836,15 @@ sph_status phase_forces(sph_world* w, const Lists& L) {
                     float coh_norm = 32.0f / (3.14159265358979323846f * powf(h, 9.f));
                     float h6_64 = powf(h, 6.f) / 64.0f;
                     float adh_norm = 0.007f / powf(h, 3.25f);
+                    if (w->tile) {
+                        uint32_t sb1 = multi ? 36u : 20u, sb2 = multi ? 52u : 36u;
+                        uint32_t cap1 = tile_cap(w, sb1), cap2 = tile_cap(w, sb2);
+                        TDISPATCH1(k_tile_akinci_normals, multi, sb1, cap1, w->pos[c].p, w->vel[c].p, w->cstart.p, cap1, TL, w->dens.p, w->normals.p,
+                                   (uint32_t)f);
+                        TDISPATCH2(k_tile_akinci_force, multi, bf, sb2, cap2, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->cstart.p, cap2, TL, w->dens.p,
+                                   w->normals.p, w->acc.p, w->bforce.p, (uint32_t)f, p[0], p[1], coh_norm, h6_64, adh_norm);
+                        break;
+                    }
                     DISPATCH1(k_akinci_normals, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->dens.p, w->normals.p, (uint32_t)f);
                     DISPATCH2(k_akinci_force, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->normals.p, w->acc.p,
                               w->bforce.p, (uint32_t)f, p[0], p[1], coh_norm, h6_64, adh_norm);
@@ -653,14 +872,14 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     size_t N = w->N;
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1, bf = any_bforce(w);
-    Lists L{w->nbr_f.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
-    uint32_t nblk = cdiv(N, PASS_T);
+    uint32_t nblk = 0;
+    (void)bc; (void)multi; (void)bf;
     // divergence_solve :466-503 (uses the PREVIOUS step's inv_dt; 0 on the first step)
     w->stats.n_divergence_iter = w->stats.n_divergence_eval = 0;
     uint32_t maxit = w->force_div >= 0 ? (uint32_t)w->force_div + 1 : w->desc.max_divergence_iter;
     for (uint32_t i = 0; i < maxit; ++i) {
         TRY(span_begin(w, SP_DIV_EVAL));
-        DISPATCH1(k_divergence, multi, N, PASS_T, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, L, w->alpha.p, w->divv.p, w->kappa.p, w->partial.p);
+        TRY(launch_vel_divergence(w, false, &nblk));
         TRY(span_end(w));
         w->stats.n_divergence_eval++;
         if (w->force_div >= 0) {
@@ -673,8 +892,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
             if (avg <= max_err && i >= w->desc.min_divergence_iter) break;
         }
         TRY(span_begin(w, SP_DIV_UPD));
-        DISPATCH2(k_divergence_update, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->vc[c].p, w->vs.p, w->bforce.p,
-                  w->inv_dt);
+        TRY(launch_vel_update(w, false));
         TRY(span_end(w));
         w->stats.n_divergence_iter++;
     }
@@ -682,7 +900,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     // update_velocities :422-430, zero vc :689-691, acc += gravity :574-578
     LAUNCH(k_fold_velocities, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2]);
     CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
-    TRY(phase_forces(w, L));
+    TRY(phase_forces(w));
     CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
     timestep_advance(w, dt_total);  // :702
     LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p);
@@ -692,8 +910,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     maxit = w->force_press >= 0 ? (uint32_t)w->force_press + 1 : w->desc.max_pressure_iter;
     for (uint32_t i = 0; i < maxit; ++i) {
         TRY(span_begin(w, SP_PRED));
-        DISPATCH1(k_predict_density, multi, N, PASS_T, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->alpha.p,
-                  w->pred.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
+        TRY(launch_vel_divergence(w, true, &nblk));
         TRY(span_end(w));
         w->stats.n_pressure_eval++;
         if (w->force_press >= 0) {
@@ -705,8 +922,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
             if (avg <= w->desc.max_density_error && i >= w->desc.min_pressure_iter) break;
         }
         TRY(span_begin(w, SP_PUPD));
-        DISPATCH2(k_pressure_update, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->vc[c].p, w->vs.p, w->bforce.p,
-                  w->inv_dt);
+        TRY(launch_vel_update(w, true));
         TRY(span_end(w));
         w->stats.n_pressure_iter++;
     }
@@ -738,9 +954,9 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
     CU(cudaEventRecord(w->ev[EV_NBR], w->st));
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1;
-    Lists L{w->nbr_f.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+    (void)c; (void)bc; (void)multi;
     // evaluate_kernels + compute_densities (liquid_world.rs:123-134) + compute_alphas (dfsph_solver.rs:679-684)
-    DISPATCH1(k_density_alpha, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->alpha.p, w->d_scal.p + 7);
+    if (N) TRY(launch_density_alpha(w));
     CU(cudaEventRecord(w->ev[EV_DENS], w->st));
     if (N) {
         if (w->desc.solver == SPH_SOLVER_DFSPH) TRY(dfsph_step(w, dt, g));
@@ -816,6 +1032,7 @@ void sph_world_desc_default(sph_world_desc* d) {
     d->slab_rank = 0;
     d->slab_count = 1;
     d->deterministic = 1;
+    d->gather_backend = 0;
 }
 
 sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
@@ -830,6 +1047,11 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     sph_world* w = new sph_world();
     w->desc = *desc;
     w->h = desc->particle_radius * desc->smoothing_factor * 2.0f;  // liquid_world.rs:44
+    w->tile = desc->gather_backend == 1;
+    {
+        const char* t = getenv("SALVA_B200_TEX");
+        w->use_tex = t ? atoi(t) != 0 : SALVA_B200_TEX_DEFAULT;
+    }
     memset(&w->hc, 0, sizeof w->hc);
     memset(&w->stats, 0, sizeof w->stats);
     bool ok = cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking) == cudaSuccess;
@@ -859,12 +1081,14 @@ void sph_world_destroy(sph_world* w) {
     w->cid.release(); w->rank.release(); w->perm.release(); w->cstart.release(); w->bcid.release(); w->brank.release(); w->bperm.release();
     w->bstart.release();
     for (auto& a : w->scan_aux) a.release();
-    w->nbr_f.release(); w->nbr_b.release(); w->cnt_f.release(); w->cnt_b.release();
+    w->nbr_f.release(); w->nbr16.release(); w->nbr_b.release(); w->cnt_f.release(); w->cnt_b.release();
     w->partial.release(); w->errsum.release(); w->d_scal.release(); w->d_cnt.release();
     w->o_a.release(); w->o_b.release(); w->o_c.release(); w->o_mass.release(); w->o_fid.release();
     iisph_release(w);
     for (auto& f : w->fluids)
         for (auto& fr : f.forces) elasticity_release(fr);
+    if (w->tex_vs) cudaDestroyTextureObject(w->tex_vs);
+    if (w->tex_kappa) cudaDestroyTextureObject(w->tex_kappa);
     for (auto& s : w->spans) {
         cudaEventDestroy(s.a);
         cudaEventDestroy(s.b);

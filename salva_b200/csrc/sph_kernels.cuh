@@ -8,8 +8,9 @@
 //   vs4   : v* = vel + vc          (materialised so gather passes read ONE vector per neighbour)
 //   bpos4 : boundary x, y, z, volume (dfsph_solver.rs:72-96);  bvel4: boundary velocity, boundary id
 // Neighbour lists ("contacts", contacts.rs:83-87) are index-only and column-major:
-//   nbr_f[k * stride + i] = sorted index of the k-th fluid neighbour of i (self included, ascending j),
-//   nbr_b[k * stride + i] likewise for boundary particles; W and grad W are recomputed from pos4 in
+//   nbr_f[((k / 4) * stride + i) * 4 + k % 4] = sorted index of the k-th fluid neighbour of i (self included,
+//   ascending j): groups of 4 contacts are interleaved so a thread fetches 4 indices with one coalesced LDG.128;
+//   nbr_b[k * stride + i] likewise (scalar) for boundary particles; W and grad W are recomputed from pos4 in
 //   every pass (cheaper than streaming cached 16-byte contacts from HBM: see DESIGN.md).
 #pragma once
 #include <cuda_runtime.h>
@@ -35,6 +36,7 @@ struct Consts {
     float dsigma;                // sigma / h               cubic_spline_kernel.rs:79
     int ox, oy, oz;              // grid origin in cell coordinates (one padding cell each side)
     int nx, ny, nz;
+    int ntx, nty, ntz;           // tile grid (sph_tile.cuh): 2 x 2 cell columns x TILE_Z cells per tile
     uint32_t n_fluid, n_bound;   // particle totals
     uint32_t stride;             // neighbour-list column stride (>= n_fluid, multiple of 32)
     uint32_t cap_f, cap_b;       // list capacities (rows)
@@ -300,7 +302,7 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
                                                      C.fluids[fj].filter);
                     }
                     if (ok) {
-                        if (nf < C.cap_f) nbr_f[(size_t)nf * C.stride + i] = j;
+                        if (nf < C.cap_f) nbr_f[((size_t)(nf >> 2) * C.stride + i) * 4 + (nf & 3)] = j;
                         ++nf;
                     }
                 }
@@ -376,53 +378,9 @@ __global__ void k_set_w(uint32_t n, float4* __restrict__ a, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Neighbour-gather pass skeleton: calls ff(j, pair, pj) for every fluid contact and fb(j, pair, pj) for
-// every boundary contact of particle i.
+// Error reduction + elementwise (streaming) kernels.  The neighbour-gather passes live in sph_passes.cuh
+// (default backend) and sph_tile.cuh (tile/TMA backend).
 // ------------------------------------------------------------------------------------------------
-struct Lists {
-    const uint32_t* nbr_f;
-    const uint32_t* nbr_b;
-    const uint32_t* cnt_f;
-    const uint32_t* cnt_b;
-};
-
-template <bool W, bool G, class FF>
-__device__ __forceinline__ void for_fluid_contacts(uint32_t i, const float4& pi, const Lists& L, const float4* __restrict__ pos, FF ff) {
-    uint32_t n = min(L.cnt_f[i], C.cap_f);
-    const uint32_t* col = L.nbr_f + i;
-#pragma unroll 4
-    for (uint32_t k = 0; k < n; ++k) {
-        uint32_t j = col[(size_t)k * C.stride];
-        float4 pj = __ldg(&pos[j]);
-        Pair p = make_pair<W, G>(pi, pj);
-        ff(j, p, pj);
-    }
-}
-template <bool W, bool G, class FB>
-__device__ __forceinline__ void for_boundary_contacts(uint32_t i, const float4& pi, const Lists& L, const float4* __restrict__ bpos, FB fb) {
-    uint32_t n = min(L.cnt_b[i], C.cap_b);
-    const uint32_t* col = L.nbr_b + i;
-    for (uint32_t k = 0; k < n; ++k) {
-        uint32_t j = col[(size_t)k * C.stride];
-        float4 pj = __ldg(&bpos[j]);
-        Pair p = make_pair<W, G>(pi, pj);
-        fb(j, p, pj);
-    }
-}
-
-// Per-fluid deterministic error reduction: partial[block * n_fluids + f].
-template <bool MULTI>
-__device__ __forceinline__ void reduce_error(float e, uint32_t fi, bool valid, float* __restrict__ partial, float* sm) {
-    if (!MULTI) {
-        float s = block_sum(valid ? e : 0.f, sm);
-        if (threadIdx.x == 0) partial[blockIdx.x] = s;
-    } else {
-        for (int f = 0; f < C.n_fluids; ++f) {
-            float s = block_sum((valid && fi == (uint32_t)f) ? e : 0.f, sm);
-            if (threadIdx.x == 0) partial[(size_t)blockIdx.x * C.n_fluids + f] = s;
-        }
-    }
-}
 // One block per fluid: fixed-order sum of the per-block partials.
 __global__ void k_reduce_partials(const float* __restrict__ partial, uint32_t nblocks, int n_fluids, float* __restrict__ out) {
     __shared__ float sm[32];
@@ -434,111 +392,6 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, uint32_t nb
 }
 
 constexpr int PASS_T = 128;  // threads per block of the gather passes
-
-// ------------------------------------------------------------------------------------------------
-// K3: densities (dfsph_solver.rs:628-665) fused with alphas (dfsph_solver.rs:165-216) and the per-contact
-// kernel evaluation of helper.rs:9-65.
-// ------------------------------------------------------------------------------------------------
-template <bool MULTI>
-__global__ void __launch_bounds__(PASS_T)
-k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
-                float* __restrict__ dens, float* __restrict__ alpha, int* __restrict__ err) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
-    float4 pi = pos[i];
-    float rho0 = C.fluids[MULTI ? fid_of(vel[i]) : 0].density0;
-    float rho = 0.f, sq = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-    for_fluid_contacts<true, true>(i, pi, L, pos, [&](uint32_t, const Pair& p, const float4& pj) {
-        rho = fmaf(pj.w, p.w, rho);
-        float s = p.g * pj.w;  // m_j * gradient
-        float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
-        sq += ax * ax + ay * ay + az * az;
-        gx += ax; gy += ay; gz += az;
-    });
-    for_boundary_contacts<true, true>(i, pi, L, bpos, [&](uint32_t, const Pair& p, const float4& pj) {
-        float mb = pj.w * rho0;  // boundary pseudo mass: vol_b * rho0_i
-        rho = fmaf(mb, p.w, rho);
-        float s = p.g * mb;
-        float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
-        sq += ax * ax + ay * ay + az * az;
-        gx += ax; gy += ay; gz += az;
-    });
-    if (rho == 0.f) atomicOr(err, 1);  // assert!(!density.is_zero()) dfsph_solver.rs:662
-    float den = sq + (gx * gx + gy * gy + gz * gz);
-    dens[i] = rho;
-    alpha[i] = den <= 1.0e-5f ? 0.f : 1.0f / den;  // dfsph_solver.rs:209-213
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4a: compute_divergences dfsph_solver.rs:279-356.  Writes div_i and kdiv_i = div_i * alpha_i.
-// ------------------------------------------------------------------------------------------------
-template <bool MULTI>
-__global__ void __launch_bounds__(PASS_T)
-k_divergence(const float4* __restrict__ pos, const float4* __restrict__ vs, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
-             const float* __restrict__ alpha, float* __restrict__ divv, float* __restrict__ kappa, float* __restrict__ partial) {
-    __shared__ float sm[32];
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < C.n_fluid;
-    float e = 0.f;
-    uint32_t fi = 0;
-    if (valid) {
-        float4 pi = pos[i];
-        float4 vi = vs[i];
-        fi = MULTI ? fid_of(vel[i]) : 0u;
-        float rho0 = C.fluids[fi].density0;
-        float d = 0.f;
-        if (L.cnt_f[i] + L.cnt_b[i] >= 20u) {  // min_neighbors_for_divergence_solve dfsph_solver.rs:62,301-314
-            for_fluid_contacts<false, true>(i, pi, L, pos, [&](uint32_t j, const Pair& p, const float4& pj) {
-                float4 vj = __ldg(&vs[j]);
-                float dv = (vi.x - vj.x) * p.dx + (vi.y - vj.y) * p.dy + (vi.z - vj.z) * p.dz;
-                d = fmaf(dv * p.g, pj.w, d);
-            });
-            for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t, const Pair& p, const float4& pj) {
-                float dv = vi.x * p.dx + vi.y * p.dy + vi.z * p.dz;  // boundary velocity ignored (:336-338)
-                d = fmaf(dv * p.g, pj.w * rho0, d);
-            });
-            d = fmaxf(d, 0.f);
-        }
-        divv[i] = d;
-        kappa[i] = d * alpha[i];
-        e = d / rho0;
-    }
-    reduce_error<MULTI>(e, fi, valid, partial, sm);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4b: compute_velocity_changes_for_divergence dfsph_solver.rs:358-409 (+ v* = vel + vc).
-// ------------------------------------------------------------------------------------------------
-template <bool MULTI, bool BFORCE>
-__global__ void __launch_bounds__(PASS_T)
-k_divergence_update(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
-                    const float* __restrict__ kappa, float4* __restrict__ vc, float4* __restrict__ vs, float* __restrict__ bforce, float inv_dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
-    float4 pi = pos[i];
-    float4 v = vel[i];
-    float rho0 = C.fluids[MULTI ? fid_of(v) : 0].density0;
-    float ki = kappa[i];
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    for_fluid_contacts<false, true>(i, pi, L, pos, [&](uint32_t j, const Pair& p, const float4& pj) {
-        float c = -(ki + __ldg(&kappa[j])) * pj.w * p.g;
-        ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
-    });
-    for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
-        float c = -ki * pj.w * rho0 * p.g;
-        ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
-        if (BFORCE) {  // boundary2.apply_force(c.j, delta * (-inv_dt * m_i)) :405
-            float s = c * (-inv_dt * pi.w);
-            atomicAdd(&bforce[3 * (size_t)j + 0], s * p.dx);
-            atomicAdd(&bforce[3 * (size_t)j + 1], s * p.dy);
-            atomicAdd(&bforce[3 * (size_t)j + 2], s * p.dz);
-        }
-    });
-    float4 c4 = vc[i];
-    c4.x += ax; c4.y += ay; c4.z += az;
-    vc[i] = c4;
-    vs[i] = make_float4(v.x + c4.x, v.y + c4.y, v.z + c4.z, 0.f);
-}
 
 // v* = vel + vc after the reorder (the divergence solve works on vel + vc carried over from the previous step, Appendix A.3.2)
 __global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __restrict__ vc, float4* __restrict__ vs) {
@@ -560,6 +413,7 @@ __global__ void k_fold_velocities(float4* __restrict__ vel, float4* __restrict__
     vs[i] = make_float4(v.x, v.y, v.z, 0.f);
     acc[i] = make_float4(gx, gy, gz, 0.f);
 }
+
 // IISPH variant: accelerations += gravity only (vc is already zero, velocities untouched).
 __global__ void k_set_gravity(const float4* __restrict__ vel, float4* __restrict__ vs, float4* __restrict__ acc, float gx, float gy, float gz) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -582,81 +436,6 @@ __global__ void k_integrate_acc(const float4* __restrict__ vel, float4* __restri
     acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// ------------------------------------------------------------------------------------------------
-// K8a: compute_predicted_densities dfsph_solver.rs:98-162.  Writes rho*_i and kappa+_i = max((rho*-rho0) alpha, 0).
-// ------------------------------------------------------------------------------------------------
-template <bool MULTI>
-__global__ void __launch_bounds__(PASS_T)
-k_predict_density(const float4* __restrict__ pos, const float4* __restrict__ vs, const float4* __restrict__ vel, const float4* __restrict__ bpos,
-                  const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens, const float* __restrict__ alpha, float* __restrict__ pred,
-                  float* __restrict__ kappa, float* __restrict__ partial, float dt, int* __restrict__ err) {
-    __shared__ float sm[32];
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < C.n_fluid;
-    float e = 0.f;
-    uint32_t fi = 0;
-    if (valid) {
-        float4 pi = pos[i];
-        float4 vi = vs[i];
-        fi = MULTI ? fid_of(vel[i]) : 0u;
-        float rho0 = C.fluids[fi].density0;
-        float delta = 0.f;
-        for_fluid_contacts<false, true>(i, pi, L, pos, [&](uint32_t j, const Pair& p, const float4& pj) {
-            float4 vj = __ldg(&vs[j]);
-            float dv = (vi.x - vj.x) * p.dx + (vi.y - vj.y) * p.dy + (vi.z - vj.z) * p.dz;
-            delta = fmaf(dv * p.g, pj.w, delta);
-        });
-        for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
-            float4 vj = __ldg(&bvel[j]);
-            float dv = (vi.x - vj.x) * p.dx + (vi.y - vj.y) * p.dy + (vi.z - vj.z) * p.dz;
-            delta = fmaf(dv * p.g, pj.w * rho0, delta);
-        });
-        float pd = fmaf(delta, dt, dens[i]);
-        if (pd == 0.f) atomicOr(err, 1);  // assert dfsph_solver.rs:145
-        pred[i] = pd;
-        kappa[i] = fmaxf((pd - rho0) * alpha[i], 0.f);
-        e = pd < rho0 ? 0.f : pd / rho0 - 1.0f;
-    }
-    reduce_error<MULTI>(e, fi, valid, partial, sm);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K8b: compute_velocity_changes dfsph_solver.rs:218-277 (+ v* = vel + vc).
-// ------------------------------------------------------------------------------------------------
-template <bool MULTI, bool BFORCE>
-__global__ void __launch_bounds__(PASS_T)
-k_pressure_update(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
-                  const float* __restrict__ kappa, float4* __restrict__ vc, float4* __restrict__ vs, float* __restrict__ bforce, float inv_dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
-    float4 pi = pos[i];
-    float4 v = vel[i];
-    float rho0 = C.fluids[MULTI ? fid_of(v) : 0].density0;
-    float ki = kappa[i];  // already clamped to >= 0
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    for_fluid_contacts<false, true>(i, pi, L, pos, [&](uint32_t j, const Pair& p, const float4& pj) {
-        float kij = ki + __ldg(&kappa[j]);  // max(ki,0) + max(kj,0); contributes only if > 0 (:248-254)
-        float c = kij * pj.w * inv_dt * p.g;
-        ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
-    });
-    if (ki > 0.f) {  // :257
-        for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
-            float c = ki * pj.w * rho0 * inv_dt * p.g;
-            ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
-            if (BFORCE) {  // apply_force(c.j, delta * (inv_dt * m_i)) :269-272
-                float s = c * inv_dt * pi.w;
-                atomicAdd(&bforce[3 * (size_t)j + 0], s * p.dx);
-                atomicAdd(&bforce[3 * (size_t)j + 1], s * p.dy);
-                atomicAdd(&bforce[3 * (size_t)j + 2], s * p.dz);
-            }
-        });
-    }
-    float4 c4 = vc[i];
-    c4.x -= ax; c4.y -= ay; c4.z -= az;
-    vc[i] = c4;
-    vs[i] = make_float4(v.x + c4.x, v.y + c4.y, v.z + c4.z, 0.f);
-}
-
 // a22: update_positions dfsph_solver.rs:411-420: pos += (vel + vc) * dt
 __global__ void k_update_positions(float4* __restrict__ pos, const float4* __restrict__ vs, float dt) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -666,114 +445,6 @@ __global__ void k_update_positions(float4* __restrict__ pos, const float4* __res
     pos[i] = p;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Nonpressure forces (predict_advection dfsph_solver.rs:565-604).  Only contacts of the SAME fluid
-// count (c.i_model == c.j_model); `which` selects the fluid a force instance belongs to.
-// ------------------------------------------------------------------------------------------------
-// a12: XSPHViscosity::solve xsph_viscosity.rs:30-95
-template <bool MULTI, bool BFORCE>
-__global__ void __launch_bounds__(PASS_T)
-k_force_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L,
-             const float* __restrict__ dens, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float cf, float cb, float inv_dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
-    float4 vi = vel[i];
-    if (MULTI && fid_of(vi) != which) return;
-    float4 pi = pos[i];
-    float rho0 = C.fluids[which].density0;
-    float fx = 0.f, fy = 0.f, fz = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
-    if (cf != 0.f)
-        for_fluid_contacts<true, false>(i, pi, L, pos, [&](uint32_t j, const Pair& p, const float4& pj) {
-            float4 vj = __ldg(&vel[j]);
-            if (MULTI && fid_of(vj) != which) return;
-            float c = cf * p.w * pj.w / __ldg(&dens[j]);  // coeff * W * (vol_j * rho0) / rho_j
-            fx = fmaf(c, vj.x - vi.x, fx); fy = fmaf(c, vj.y - vi.y, fy); fz = fmaf(c, vj.z - vi.z, fz);
-        });
-    if (cb != 0.f) {
-        float rho_i = dens[i];
-        for_boundary_contacts<true, false>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
-            float4 vj = __ldg(&bvel[j]);
-            float c = cb * p.w * pj.w * rho0 / rho_i;
-            float dx = c * (vj.x - vi.x), dy = c * (vj.y - vi.y), dz = c * (vj.z - vi.z);
-            bx += dx; by += dy; bz += dz;
-            if (BFORCE) {  // apply_force(c.j, delta * (-m_i * inv_dt)) :87-88
-                float s = -pi.w * inv_dt;
-                atomicAdd(&bforce[3 * (size_t)j + 0], s * dx);
-                atomicAdd(&bforce[3 * (size_t)j + 1], s * dy);
-                atomicAdd(&bforce[3 * (size_t)j + 2], s * dz);
-            }
-        });
-    }
-    float4 a = acc[i];
-    a.x += fx * inv_dt + bx * inv_dt; a.y += fy * inv_dt + by * inv_dt; a.z += fz * inv_dt + bz * inv_dt;
-    acc[i] = a;
-}
-
-// a13: ArtificialViscosity::solve artificial_viscosity.rs:40-124
-template <bool MULTI, bool BFORCE>
-__global__ void __launch_bounds__(PASS_T)
-k_force_artificial(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L,
-                   const float* __restrict__ dens, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float cf, float cb, float alpha,
-                   float beta, float cs) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
-    float4 vi = vel[i];
-    if (MULTI && fid_of(vi) != which) return;
-    float4 pi = pos[i];
-    float rho0 = C.fluids[which].density0;
-    float rho_i = dens[i];
-    float eta2 = C.h * C.h * 0.01f;
-    float fx = 0.f, fy = 0.f, fz = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
-    if (cf != 0.f)
-        for_fluid_contacts<false, true>(i, pi, L, pos, [&](uint32_t j, const Pair& p, const float4& pj) {
-            float4 vj = __ldg(&vel[j]);
-            if (MULTI && fid_of(vj) != which) return;
-            float vr = p.dx * (vi.x - vj.x) + p.dy * (vi.y - vj.y) + p.dz * (vi.z - vj.z);
-            if (vr < 0.f) {
-                float davg = (rho_i + __ldg(&dens[j])) * 0.5f;
-                float mu = C.h * vr / (p.d2 + eta2);
-                float c = cf * (cs * alpha * mu - beta * mu * mu) * (pj.w / davg) * p.g;
-                fx = fmaf(c, p.dx, fx); fy = fmaf(c, p.dy, fy); fz = fmaf(c, p.dz, fz);
-            }
-        });
-    if (cb != 0.f)
-        for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
-            float4 vj = __ldg(&bvel[j]);
-            float vr = p.dx * (vi.x - vj.x) + p.dy * (vi.y - vj.y) + p.dz * (vi.z - vj.z);
-            if (vr < 0.f) {
-                float mu = C.h * vr / (p.d2 + eta2);
-                float c = cb * (cs * alpha * mu - beta * mu * mu) * (pj.w * rho0 / rho_i) * p.g;
-                bx = fmaf(c, p.dx, bx); by = fmaf(c, p.dy, by); bz = fmaf(c, p.dz, bz);
-                if (BFORCE) {  // apply_force(c.j, boundary_acc * -m_i): the RUNNING sum, as the reference (:117)
-                    atomicAdd(&bforce[3 * (size_t)j + 0], -pi.w * bx);
-                    atomicAdd(&bforce[3 * (size_t)j + 1], -pi.w * by);
-                    atomicAdd(&bforce[3 * (size_t)j + 2], -pi.w * bz);
-                }
-            }
-        });
-    float4 a = acc[i];
-    a.x += fx + bx; a.y += fy + by; a.z += fz + bz;
-    acc[i] = a;
-}
-
-// a14 pass 1: Akinci2013 compute_normals akinci2013_surface_tension.rs:43-68
-template <bool MULTI>
-__global__ void __launch_bounds__(PASS_T)
-k_akinci_normals(const float4* __restrict__ pos, const float4* __restrict__ vel, Lists L, const float* __restrict__ dens, float4* __restrict__ normals,
-                 uint32_t which) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
-    if (MULTI && fid_of(vel[i]) != which) return;
-    float4 pi = pos[i];
-    float nx = 0.f, ny = 0.f, nz = 0.f;
-    for_fluid_contacts<false, true>(i, pi, L, pos, [&](uint32_t j, const Pair& p, const float4& pj) {
-        if (MULTI && fid_of(__ldg(&vel[j])) != which) return;
-        float c = p.g * (pj.w / __ldg(&dens[j]));
-        nx = fmaf(c, p.dx, nx); ny = fmaf(c, p.dy, ny); nz = fmaf(c, p.dz, nz);
-    });
-    normals[i] = make_float4(nx * C.h, ny * C.h, nz * C.h, 0.f);
-}
-
 __device__ __forceinline__ float powi3(float x) { return x * x * x; }
 // akinci2013_surface_tension.rs:71-88
 __device__ __forceinline__ float cohesion_kernel(float r, float coh_norm, float h6_64) {
@@ -781,6 +452,7 @@ __device__ __forceinline__ float cohesion_kernel(float r, float coh_norm, float 
     float c = r <= C.h * 0.5f ? 2.0f * hr - h6_64 : (r <= C.h ? hr : 0.f);
     return coh_norm * c;
 }
+
 // akinci2013_surface_tension.rs:90-111
 __device__ __forceinline__ float adhesion_kernel(float r, float adh_norm) {
     if (r > C.h * 0.5f && r <= C.h) {
@@ -788,47 +460,6 @@ __device__ __forceinline__ float adhesion_kernel(float r, float adh_norm) {
         return adh_norm * sqrtf(sqrtf(x));  // powf(0.25)
     }
     return 0.f;
-}
-// a14 pass 2: Akinci2013SurfaceTension::solve akinci2013_surface_tension.rs:113-192
-template <bool MULTI, bool BFORCE>
-__global__ void __launch_bounds__(PASS_T)
-k_akinci_force(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens,
-               const float4* __restrict__ normals, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float gamma, float adh,
-               float coh_norm, float h6_64, float adh_norm) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
-    if (MULTI && fid_of(vel[i]) != which) return;
-    float4 pi = pos[i];
-    float rho0 = C.fluids[which].density0;
-    float rho_i = dens[i];
-    float4 ni = normals[i];
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    if (gamma != 0.f)
-        for_fluid_contacts<false, false>(i, pi, L, pos, [&](uint32_t j, const Pair& p, const float4& pj) {
-            if (MULTI && fid_of(__ldg(&vel[j])) != which) return;
-            float4 nj = __ldg(&normals[j]);
-            // cohesion_vec = dir * C(dist) if |dpos|^2 > eps^2 (Unit::try_new_and_get)
-            float coh = p.d2 > F32_EPS * F32_EPS ? cohesion_kernel(p.r, coh_norm, h6_64) / p.r : 0.f;
-            float cm = coh * (-gamma * pj.w);
-            float kij = 2.0f * rho0 / (rho_i + __ldg(&dens[j]));
-            ax += (-gamma * (ni.x - nj.x) + cm * p.dx) * kij;
-            ay += (-gamma * (ni.y - nj.y) + cm * p.dy) * kij;
-            az += (-gamma * (ni.z - nj.z) + cm * p.dz) * kij;
-        });
-    if (adh != 0.f)
-        for_boundary_contacts<false, false>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
-            float ad = p.d2 > F32_EPS * F32_EPS ? adhesion_kernel(p.r, adh_norm) / p.r : 0.f;
-            float c = ad * adh * (pj.w * rho0);
-            ax -= c * p.dx; ay -= c * p.dy; az -= c * p.dz;
-            if (BFORCE) {  // apply_force(c.j, adhesion_acc * m_i) :188
-                atomicAdd(&bforce[3 * (size_t)j + 0], c * p.dx * pi.w);
-                atomicAdd(&bforce[3 * (size_t)j + 1], c * p.dy * pi.w);
-                atomicAdd(&bforce[3 * (size_t)j + 2], c * p.dz * pi.w);
-            }
-        });
-    float4 a = acc[i];
-    a.x += ax; a.y += ay; a.z += az;
-    acc[i] = a;
 }
 
 // ------------------------------------------------------------------------------------------------

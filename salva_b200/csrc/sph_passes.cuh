@@ -1,0 +1,397 @@
+// sph_passes.cuh — neighbour-gather passes, default backend: one thread per particle walks its index-only
+// contact list and gathers neighbour data from global memory through L1 (and, for the second per-contact vector,
+// optionally through the TEXTURE pipe, whose data path is separate from the LSU one: profiles/r1_v0_* show the
+// LSU data pipe — two float4 gathers per contact — is what bounds these kernels, not DRAM).
+//
+// Contacts are consumed in groups of four: one coalesced LDG.128 brings 4 list indices per thread (the next group is
+// prefetched before the current one is used), then 4 position gathers + 4 auxiliary gathers are issued back to back
+// and only then the 4 pair evaluations run, so 8+ independent loads are in flight per thread.
+#pragma once
+#include "sph_kernels.cuh"
+
+namespace sphk {
+
+struct Lists {
+    const uint4* nbr_f;     // nbr_f[(k / 4) * stride + i] = contacts 4*(k/4) .. 4*(k/4)+3 of particle i (sorted indices)
+    const uint32_t* nbr_b;  // nbr_b[k * stride + i]
+    const uint32_t* cnt_f;
+    const uint32_t* cnt_b;
+};
+
+struct NoAux {};
+
+// ld(j) -> Aux loads whatever else the pass needs from neighbour j; ff(j, pair, pos_j, aux) consumes one contact.
+template <bool W, bool G, class LD, class FF>
+__device__ __forceinline__ void for_fluid_contacts(uint32_t i, const float4& pi, const Lists& L, const float4* __restrict__ pos, LD ld, FF ff) {
+    const uint32_t n = min(L.cnt_f[i], C.cap_f);
+    const uint32_t nq = (n + 3u) >> 2;
+    const uint4* col = L.nbr_f + i;
+    uint4 J = nq ? __ldg(col) : make_uint4(i, i, i, i);
+    for (uint32_t q = 0; q < nq; ++q) {
+        uint4 Jn = J;
+        if (q + 1 < nq) Jn = __ldg(col + (size_t)(q + 1) * C.stride);  // prefetch the next group of indices
+        uint32_t j[4] = {J.x, J.y, J.z, J.w};
+        const uint32_t k0 = q * 4u;
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ok[u] = k0 + u < n;
+            if (!ok[u]) j[u] = i;  // unwritten tail slots of the last group: point at self, masked below
+        }
+        float4 pj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pj[u] = __ldg(&pos[j[u]]);
+        decltype(ld(0u)) aux[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) aux[u] = ld(j[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ok[u]) {
+                Pair p = make_pair<W, G>(pi, pj[u]);
+                ff(j[u], p, pj[u], aux[u]);
+            }
+        }
+        J = Jn;
+    }
+}
+template <bool W, bool G, class FB>
+__device__ __forceinline__ void for_boundary_contacts(uint32_t i, const float4& pi, const Lists& L, const float4* __restrict__ bpos, FB fb) {
+    uint32_t n = min(L.cnt_b[i], C.cap_b);
+    const uint32_t* col = L.nbr_b + i;
+    for (uint32_t k = 0; k < n; ++k) {
+        uint32_t j = col[(size_t)k * C.stride];
+        float4 pj = __ldg(&bpos[j]);
+        Pair p = make_pair<W, G>(pi, pj);
+        fb(j, p, pj);
+    }
+}
+
+template <bool TEX>
+__device__ __forceinline__ float4 fetch4(const float4* __restrict__ a, cudaTextureObject_t t, uint32_t j) {
+    if (TEX) return tex1Dfetch<float4>(t, (int)j);
+    return __ldg(&a[j]);
+}
+template <bool TEX>
+__device__ __forceinline__ float fetch1(const float* __restrict__ a, cudaTextureObject_t t, uint32_t j) {
+    if (TEX) return tex1Dfetch<float>(t, (int)j);
+    return __ldg(&a[j]);
+}
+
+// Per-fluid deterministic error reduction: partial[block * n_fluids + f].
+template <bool MULTI>
+__device__ __forceinline__ void reduce_error(float e, uint32_t fi, bool valid, float* __restrict__ partial, float* sm) {
+    if (!MULTI) {
+        float s = block_sum(valid ? e : 0.f, sm);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    } else {
+        for (int f = 0; f < C.n_fluids; ++f) {
+            float s = block_sum((valid && fi == (uint32_t)f) ? e : 0.f, sm);
+            if (threadIdx.x == 0) partial[(size_t)blockIdx.x * C.n_fluids + f] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: densities (dfsph_solver.rs:628-665) fused with alphas (dfsph_solver.rs:165-216) and the per-contact
+// kernel evaluation of helper.rs:9-65.
+// ------------------------------------------------------------------------------------------------
+template <bool MULTI>
+__global__ void __launch_bounds__(PASS_T)
+k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
+                float* __restrict__ dens, float* __restrict__ alpha, int* __restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_fluid) return;
+    float4 pi = pos[i];
+    float rho0 = C.fluids[MULTI ? fid_of(vel[i]) : 0].density0;
+    float rho = 0.f, sq = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+    for_fluid_contacts<true, true>(
+        i, pi, L, pos, [](uint32_t) { return NoAux{}; },
+        [&](uint32_t, const Pair& p, const float4& pj, NoAux) {
+            rho = fmaf(pj.w, p.w, rho);
+            float s = p.g * pj.w;  // m_j * gradient
+            float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
+            sq += ax * ax + ay * ay + az * az;
+            gx += ax; gy += ay; gz += az;
+        });
+    for_boundary_contacts<true, true>(i, pi, L, bpos, [&](uint32_t, const Pair& p, const float4& pj) {
+        float mb = pj.w * rho0;  // boundary pseudo mass: vol_b * rho0_i
+        rho = fmaf(mb, p.w, rho);
+        float s = p.g * mb;
+        float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
+        sq += ax * ax + ay * ay + az * az;
+        gx += ax; gy += ay; gz += az;
+    });
+    if (rho == 0.f) atomicOr(err, 1);  // assert!(!density.is_zero()) dfsph_solver.rs:662
+    float den = sq + (gx * gx + gy * gy + gz * gz);
+    dens[i] = rho;
+    alpha[i] = den <= 1.0e-5f ? 0.f : 1.0f / den;  // dfsph_solver.rs:209-213
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4a / K8a: compute_divergences dfsph_solver.rs:279-356 (PREDICT = false) and compute_predicted_densities
+// dfsph_solver.rs:98-162 (PREDICT = true) share one kernel: sum_j m_j (v*_i - v*_j) . gradW_ij.
+//   PREDICT: out = rho*_i, kappa = max((rho* - rho0) alpha, 0), boundary term uses the boundary velocity (:136-141);
+//   else   : out = div_i (0 below 20 contacts, :62,301-314), kappa = div * alpha, boundary velocity ignored (:336-338).
+// ------------------------------------------------------------------------------------------------
+template <bool MULTI, bool PREDICT, bool TEX>
+__global__ void __launch_bounds__(PASS_T)
+k_vel_divergence(const float4* __restrict__ pos, const float4* __restrict__ vs, cudaTextureObject_t tvs, const float4* __restrict__ vel,
+                 const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
+                 const float* __restrict__ alpha, float* __restrict__ out, float* __restrict__ kappa, float* __restrict__ partial, float dt,
+                 int* __restrict__ err) {
+    __shared__ float sm[32];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < C.n_fluid;
+    float e = 0.f;
+    uint32_t fi = 0;
+    if (valid) {
+        float4 pi = pos[i];
+        float4 vi = vs[i];
+        fi = MULTI ? fid_of(vel[i]) : 0u;
+        float rho0 = C.fluids[fi].density0;
+        float d = 0.f;
+        if (PREDICT || L.cnt_f[i] + L.cnt_b[i] >= 20u) {
+            for_fluid_contacts<false, true>(
+                i, pi, L, pos, [&](uint32_t j) { return fetch4<TEX>(vs, tvs, j); },
+                [&](uint32_t, const Pair& p, const float4& pj, const float4& vj) {
+                    float dv = (vi.x - vj.x) * p.dx + (vi.y - vj.y) * p.dy + (vi.z - vj.z) * p.dz;
+                    d = fmaf(dv * p.g, pj.w, d);
+                });
+            for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+                float dv;
+                if (PREDICT) {
+                    float4 vj = __ldg(&bvel[j]);
+                    dv = (vi.x - vj.x) * p.dx + (vi.y - vj.y) * p.dy + (vi.z - vj.z) * p.dz;
+                } else {
+                    dv = vi.x * p.dx + vi.y * p.dy + vi.z * p.dz;
+                }
+                d = fmaf(dv * p.g, pj.w * rho0, d);
+            });
+        }
+        if (PREDICT) {
+            float pd = fmaf(d, dt, dens[i]);
+            if (pd == 0.f) atomicOr(err, 1);  // assert dfsph_solver.rs:145
+            out[i] = pd;
+            kappa[i] = fmaxf((pd - rho0) * alpha[i], 0.f);
+            e = pd < rho0 ? 0.f : pd / rho0 - 1.0f;
+        } else {
+            d = fmaxf(d, 0.f);
+            out[i] = d;
+            kappa[i] = d * alpha[i];
+            e = d / rho0;
+        }
+    }
+    reduce_error<MULTI>(e, fi, valid, partial, sm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b / K8b: compute_velocity_changes_for_divergence dfsph_solver.rs:358-409 (PRESSURE = false) and
+// compute_velocity_changes dfsph_solver.rs:218-277 (PRESSURE = true):
+//   vc_i -= scale * [ sum_j (k_i + k_j) m_j gradW_ij + sum_b k_i vol_b rho0 gradW_ib ],  v* = vel + vc.
+// PRESSURE: k = kappa+ (>= 0), scale = inv_dt, boundary term only if k_i > 0 (:257); else k = div*alpha, scale = 1.
+// ------------------------------------------------------------------------------------------------
+template <bool MULTI, bool BFORCE, bool PRESSURE, bool TEX>
+__global__ void __launch_bounds__(PASS_T)
+k_vel_update(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ kappa,
+             cudaTextureObject_t tkappa, float4* __restrict__ vc, float4* __restrict__ vs, float* __restrict__ bforce, float inv_dt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_fluid) return;
+    float4 pi = pos[i];
+    float4 v = vel[i];
+    float rho0 = C.fluids[MULTI ? fid_of(v) : 0].density0;
+    float ki = kappa[i];
+    const float scale = PRESSURE ? inv_dt : 1.0f;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for_fluid_contacts<false, true>(
+        i, pi, L, pos, [&](uint32_t j) { return fetch1<TEX>(kappa, tkappa, j); },
+        [&](uint32_t, const Pair& p, const float4& pj, float kj) {
+            float c = (ki + kj) * pj.w * scale * p.g;
+            ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
+        });
+    if (!PRESSURE || ki > 0.f) {
+        for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+            float c = ki * pj.w * rho0 * scale * p.g;
+            ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
+            if (BFORCE) {  // :269-272 / :403-405 both reduce to +c * inv_dt * m_i * x_ij on the boundary particle
+                float s = c * inv_dt * pi.w;
+                atomicAdd(&bforce[3 * (size_t)j + 0], s * p.dx);
+                atomicAdd(&bforce[3 * (size_t)j + 1], s * p.dy);
+                atomicAdd(&bforce[3 * (size_t)j + 2], s * p.dz);
+            }
+        });
+    }
+    float4 c4 = vc[i];
+    c4.x -= ax; c4.y -= ay; c4.z -= az;
+    vc[i] = c4;
+    vs[i] = make_float4(v.x + c4.x, v.y + c4.y, v.z + c4.z, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Nonpressure forces (predict_advection dfsph_solver.rs:565-604).  Only contacts of the SAME fluid
+// count (c.i_model == c.j_model); `which` selects the fluid a force instance belongs to.
+// ------------------------------------------------------------------------------------------------
+struct VelRho {
+    float4 v;
+    float rho;
+};
+// a12: XSPHViscosity::solve xsph_viscosity.rs:30-95
+template <bool MULTI, bool BFORCE>
+__global__ void __launch_bounds__(PASS_T)
+k_force_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L,
+             const float* __restrict__ dens, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float cf, float cb, float inv_dt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_fluid) return;
+    float4 vi = vel[i];
+    if (MULTI && fid_of(vi) != which) return;
+    float4 pi = pos[i];
+    float rho0 = C.fluids[which].density0;
+    float fx = 0.f, fy = 0.f, fz = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+    if (cf != 0.f)
+        for_fluid_contacts<true, false>(
+            i, pi, L, pos, [&](uint32_t j) { return VelRho{__ldg(&vel[j]), __ldg(&dens[j])}; },
+            [&](uint32_t, const Pair& p, const float4& pj, const VelRho& a) {
+                if (MULTI && fid_of(a.v) != which) return;
+                float c = cf * p.w * pj.w / a.rho;  // coeff * W * (vol_j * rho0) / rho_j
+                fx = fmaf(c, a.v.x - vi.x, fx); fy = fmaf(c, a.v.y - vi.y, fy); fz = fmaf(c, a.v.z - vi.z, fz);
+            });
+    if (cb != 0.f) {
+        float rho_i = dens[i];
+        for_boundary_contacts<true, false>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+            float4 vj = __ldg(&bvel[j]);
+            float c = cb * p.w * pj.w * rho0 / rho_i;
+            float dx = c * (vj.x - vi.x), dy = c * (vj.y - vi.y), dz = c * (vj.z - vi.z);
+            bx += dx; by += dy; bz += dz;
+            if (BFORCE) {  // apply_force(c.j, delta * (-m_i * inv_dt)) :87-88
+                float s = -pi.w * inv_dt;
+                atomicAdd(&bforce[3 * (size_t)j + 0], s * dx);
+                atomicAdd(&bforce[3 * (size_t)j + 1], s * dy);
+                atomicAdd(&bforce[3 * (size_t)j + 2], s * dz);
+            }
+        });
+    }
+    float4 a = acc[i];
+    a.x += fx * inv_dt + bx * inv_dt; a.y += fy * inv_dt + by * inv_dt; a.z += fz * inv_dt + bz * inv_dt;
+    acc[i] = a;
+}
+
+// a13: ArtificialViscosity::solve artificial_viscosity.rs:40-124
+template <bool MULTI, bool BFORCE>
+__global__ void __launch_bounds__(PASS_T)
+k_force_artificial(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L,
+                   const float* __restrict__ dens, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float cf, float cb, float alpha,
+                   float beta, float cs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_fluid) return;
+    float4 vi = vel[i];
+    if (MULTI && fid_of(vi) != which) return;
+    float4 pi = pos[i];
+    float rho0 = C.fluids[which].density0;
+    float rho_i = dens[i];
+    float eta2 = C.h * C.h * 0.01f;
+    float fx = 0.f, fy = 0.f, fz = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+    if (cf != 0.f)
+        for_fluid_contacts<false, true>(
+            i, pi, L, pos, [&](uint32_t j) { return VelRho{__ldg(&vel[j]), __ldg(&dens[j])}; },
+            [&](uint32_t, const Pair& p, const float4& pj, const VelRho& a) {
+                if (MULTI && fid_of(a.v) != which) return;
+                float vr = p.dx * (vi.x - a.v.x) + p.dy * (vi.y - a.v.y) + p.dz * (vi.z - a.v.z);
+                if (vr < 0.f) {
+                    float davg = (rho_i + a.rho) * 0.5f;
+                    float mu = C.h * vr / (p.d2 + eta2);
+                    float c = cf * (cs * alpha * mu - beta * mu * mu) * (pj.w / davg) * p.g;
+                    fx = fmaf(c, p.dx, fx); fy = fmaf(c, p.dy, fy); fz = fmaf(c, p.dz, fz);
+                }
+            });
+    if (cb != 0.f)
+        for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+            float4 vj = __ldg(&bvel[j]);
+            float vr = p.dx * (vi.x - vj.x) + p.dy * (vi.y - vj.y) + p.dz * (vi.z - vj.z);
+            if (vr < 0.f) {
+                float mu = C.h * vr / (p.d2 + eta2);
+                float c = cb * (cs * alpha * mu - beta * mu * mu) * (pj.w * rho0 / rho_i) * p.g;
+                bx = fmaf(c, p.dx, bx); by = fmaf(c, p.dy, by); bz = fmaf(c, p.dz, bz);
+                if (BFORCE) {  // apply_force(c.j, boundary_acc * -m_i): the RUNNING sum, as the reference (:117)
+                    atomicAdd(&bforce[3 * (size_t)j + 0], -pi.w * bx);
+                    atomicAdd(&bforce[3 * (size_t)j + 1], -pi.w * by);
+                    atomicAdd(&bforce[3 * (size_t)j + 2], -pi.w * bz);
+                }
+            }
+        });
+    float4 a = acc[i];
+    a.x += fx + bx; a.y += fy + by; a.z += fz + bz;
+    acc[i] = a;
+}
+
+struct FidRho {
+    uint32_t fid;
+    float rho;
+};
+// a14 pass 1: Akinci2013 compute_normals akinci2013_surface_tension.rs:43-68
+template <bool MULTI>
+__global__ void __launch_bounds__(PASS_T)
+k_akinci_normals(const float4* __restrict__ pos, const float4* __restrict__ vel, Lists L, const float* __restrict__ dens, float4* __restrict__ normals,
+                 uint32_t which) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_fluid) return;
+    if (MULTI && fid_of(vel[i]) != which) return;
+    float4 pi = pos[i];
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    for_fluid_contacts<false, true>(
+        i, pi, L, pos, [&](uint32_t j) { return FidRho{MULTI ? fid_of(__ldg(&vel[j])) : 0u, __ldg(&dens[j])}; },
+        [&](uint32_t, const Pair& p, const float4& pj, const FidRho& a) {
+            if (MULTI && a.fid != which) return;
+            float c = p.g * (pj.w / a.rho);
+            nx = fmaf(c, p.dx, nx); ny = fmaf(c, p.dy, ny); nz = fmaf(c, p.dz, nz);
+        });
+    normals[i] = make_float4(nx * C.h, ny * C.h, nz * C.h, 0.f);
+}
+
+struct NrmRho {
+    float4 n;
+    float rho;
+    uint32_t fid;
+};
+// a14 pass 2: Akinci2013SurfaceTension::solve akinci2013_surface_tension.rs:113-192
+template <bool MULTI, bool BFORCE>
+__global__ void __launch_bounds__(PASS_T)
+k_akinci_force(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens,
+               const float4* __restrict__ normals, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float gamma, float adh,
+               float coh_norm, float h6_64, float adh_norm) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_fluid) return;
+    if (MULTI && fid_of(vel[i]) != which) return;
+    float4 pi = pos[i];
+    float rho0 = C.fluids[which].density0;
+    float rho_i = dens[i];
+    float4 ni = normals[i];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (gamma != 0.f)
+        for_fluid_contacts<false, false>(
+            i, pi, L, pos, [&](uint32_t j) { return NrmRho{__ldg(&normals[j]), __ldg(&dens[j]), MULTI ? fid_of(__ldg(&vel[j])) : 0u}; },
+            [&](uint32_t, const Pair& p, const float4& pj, const NrmRho& a) {
+                if (MULTI && a.fid != which) return;
+                // cohesion_vec = dir * C(dist) if |dpos|^2 > eps^2 (Unit::try_new_and_get)
+                float coh = p.d2 > F32_EPS * F32_EPS ? cohesion_kernel(p.r, coh_norm, h6_64) / p.r : 0.f;
+                float cm = coh * (-gamma * pj.w);
+                float kij = 2.0f * rho0 / (rho_i + a.rho);
+                ax += (-gamma * (ni.x - a.n.x) + cm * p.dx) * kij;
+                ay += (-gamma * (ni.y - a.n.y) + cm * p.dy) * kij;
+                az += (-gamma * (ni.z - a.n.z) + cm * p.dz) * kij;
+            });
+    if (adh != 0.f)
+        for_boundary_contacts<false, false>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+            float ad = p.d2 > F32_EPS * F32_EPS ? adhesion_kernel(p.r, adh_norm) / p.r : 0.f;
+            float c = ad * adh * (pj.w * rho0);
+            ax -= c * p.dx; ay -= c * p.dy; az -= c * p.dz;
+            if (BFORCE) {  // apply_force(c.j, adhesion_acc * m_i) :188
+                atomicAdd(&bforce[3 * (size_t)j + 0], c * p.dx * pi.w);
+                atomicAdd(&bforce[3 * (size_t)j + 1], c * p.dy * pi.w);
+                atomicAdd(&bforce[3 * (size_t)j + 2], c * p.dz * pi.w);
+            }
+        });
+    float4 a = acc[i];
+    a.x += ax; a.y += ay; a.z += az;
+    acc[i] = a;
+}
+
+}  // namespace sphk

@@ -125,7 +125,7 @@ class LiquidWorld:
     """liquid_world.rs:17-158 on the GPU engine."""
 
     def __init__(self, solver=None, particle_radius=0.05, smoothing_factor=2.0, device=0, deterministic=True,
-                 slab_rank=0, slab_count=1):
+                 slab_rank=0, slab_count=1, gather_backend=0):
         solver = solver or DFSPHSolver()
         self._L = _lib.lib()
         d = WorldDesc()
@@ -141,6 +141,7 @@ class LiquidWorld:
         d.device = device
         d.deterministic = int(deterministic)
         d.slab_rank, d.slab_count = slab_rank, slab_count
+        d.gather_backend = gather_backend
         self._w = C.c_void_p()
         st = self._L.sph_world_create(C.byref(d), C.byref(self._w))
         if st != 0:

@@ -66,9 +66,10 @@ def test_single_pass_quantities_match_oracle():
 @pytest.mark.parametrize("forces", [(), (scenes.xsph_viscosity(0.5, 0.3),), (scenes.artificial_viscosity(1.0, 0.5),),
                                     (scenes.akinci2013_surface_tension(1.0, 0.7),)],
                          ids=["none", "xsph", "artificial", "akinci2013"])
-def test_trajectory_forced_iterations(forces):
+@pytest.mark.parametrize("backend", [0, 1], ids=["l1-gather", "tile-tma"])
+def test_trajectory_forced_iterations(forces, backend):
     sc = _small_scene(seed=5, forces=forces)
-    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    gpu, cpu, fg, fc, _, _ = _pair(sc, gather_backend=backend)
     dt = 0.005
     for w in (gpu, cpu):
         w.force_iterations(2, 3)
@@ -83,9 +84,10 @@ def test_trajectory_forced_iterations(forces):
     assert np.abs(vg - vc).max() <= 1e-3 * h / dt
 
 
-def test_two_fluids_with_groups_and_free_running_iterations():
+@pytest.mark.parametrize("backend", [0, 1], ids=["l1-gather", "tile-tma"])
+def test_two_fluids_with_groups_and_free_running_iterations(backend):
     sc = _small_scene(seed=9, forces=(scenes.xsph_viscosity(0.5, 0.0),), two_fluids=True)
-    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    gpu, cpu, fg, fc, _, _ = _pair(sc, gather_backend=backend)
     for _ in range(4):
         gpu.step(0.005)
         cpu.step(0.005)
@@ -160,10 +162,11 @@ def test_host_edits_append_delete_roundtrip():
     assert np.abs(pg - pc).max() <= 1e-3 * float(gpu.h)
 
 
-def test_boundary_forces_accumulate_like_reference():
+@pytest.mark.parametrize("backend", [0, 1], ids=["l1-gather", "tile-tma"])
+def test_boundary_forces_accumulate_like_reference(backend):
     """Boundary::apply_force (boundary.rs:62-67) writers: dfsph_solver.rs:269-272,403-405 and the force plugins."""
     sc = _small_scene(seed=17, forces=(scenes.xsph_viscosity(0.5, 0.3),), want_forces=True)
-    gpu, cpu, fg, fc, bg, bc = _pair(sc)
+    gpu, cpu, fg, fc, bg, bc = _pair(sc, gather_backend=backend)
     for w in (gpu, cpu):
         w.force_iterations(2, 3)
     for _ in range(3):
