@@ -1047,7 +1047,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     sph_world* w = new sph_world();
     w->desc = *desc;
     w->h = desc->particle_radius * desc->smoothing_factor * 2.0f;  // liquid_world.rs:44
-    w->tile = desc->gather_backend == 1;
+    w->tile = desc->gather_backend == 1 && desc->solver == SPH_SOLVER_DFSPH;  // the tile backend covers the DFSPH passes only
     {
         const char* t = getenv("SALVA_B200_TEX");
         w->use_tex = t ? atoi(t) != 0 : SALVA_B200_TEX_DEFAULT;

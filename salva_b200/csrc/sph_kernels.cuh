@@ -507,6 +507,10 @@ __global__ void k_export_w(uint32_t n, const uint32_t* __restrict__ orig, const 
     if (s >= n) return;
     dst[orig[s]] = src[s].w;
 }
+__global__ void k_export_w_plain(uint32_t n, const float4* __restrict__ src, float* __restrict__ dst) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) dst[s] = src[s].w;
+}
 __global__ void k_export1(uint32_t n, const uint32_t* __restrict__ orig, const float* __restrict__ src, float* __restrict__ dst) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
