@@ -104,6 +104,10 @@ typedef struct {
     uint32_t max_neighbors;          /* widest fluid neighbour list this step */
     uint32_t grid_dims[3];
     uint64_t kernel_launches;        /* CUDA kernels launched by this step */
+    uint32_t n_ghost_particles;      /* multi-GPU: ghost particles received from the neighbour slabs this step */
+    uint32_t n_migrated;             /* multi-GPU: particles handed over to / received from neighbour slabs */
+    uint32_t n_exchanges;            /* multi-GPU: ghost-refresh exchanges (ncclSend/Recv groups) this step */
+    uint32_t reserved_;
 } sph_step_stats;
 
 /* sph_debug_read() selectors: solver scratch in ORIGINAL particle order. */
@@ -162,10 +166,21 @@ sph_status sph_debug_read(sph_world* w, uint32_t fluid, int what, float* out, si
 const char* sph_last_error(const sph_world* w);
 const char* sph_version(void);
 
-/* Multi-GPU (one process per GPU).  The slab world of rank r exchanges its one-cell ghost
- * columns with ranks r-1 / r+1 through NCCL; the host passes an already-initialised
- * ncclComm_t (as void*) created by its own plumbing (torch.distributed / ncclCommInitRank). */
+/* Caller-visible particle ids (default: the index a particle had when it was added).  They follow particles when the
+ * sort reorders them and when a particle migrates to another rank's slab. */
+sph_status sph_fluid_set_ids(sph_world* w, uint32_t fluid, const uint32_t* ids, size_t n);
+sph_status sph_fluid_read_ids(sph_world* w, uint32_t fluid, uint32_t* ids, size_t cap);
+
+/* Multi-GPU (one process per GPU; the reference has no counterpart: SURVEY.md §8e).  1-D slab decomposition along x:
+ * the world of rank r owns the particles whose cell column floor(x / h) lies in [cell_lo, cell_hi) (INT32_MIN / INT32_MAX
+ * = open end), the host adds only those to it (plus ALL boundary particles), and every step the library exchanges
+ * one-cell ghost columns with ranks r-1 / r+1 (ncclSend/ncclRecv over NVLink) and migrates particles that crossed a
+ * plane.  Either hand over an initialised ncclComm_t (attach) or let the library create one from a unique id that
+ * rank 0 obtained with sph_nccl_unique_id() and the host's own plumbing (torch.distributed) broadcast. */
+sph_status sph_nccl_unique_id(char out_id[128]);
+sph_status sph_world_create_nccl(sph_world* w, const char unique_id[128], int rank, int nranks);
 sph_status sph_world_attach_nccl(sph_world* w, void* nccl_comm, int rank, int nranks);
+sph_status sph_world_set_slab(sph_world* w, int32_t cell_lo, int32_t cell_hi);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,9 @@ class StepStats(C.Structure):
                                           "n_pressure_eval")] + \
                [("last_divergence_error", C.c_float), ("last_density_error", C.c_float),
                 ("n_fluid_particles", C.c_uint64), ("n_boundary_particles", C.c_uint64), ("n_contacts", C.c_uint64),
-                ("max_neighbors", C.c_uint32), ("grid_dims", C.c_uint32 * 3), ("kernel_launches", C.c_uint64)]
+                ("max_neighbors", C.c_uint32), ("grid_dims", C.c_uint32 * 3), ("kernel_launches", C.c_uint64),
+                ("n_ghost_particles", C.c_uint32), ("n_migrated", C.c_uint32), ("n_exchanges", C.c_uint32),
+                ("reserved_", C.c_uint32)]
 
 
 # every symbol include/sph.h declares: name -> (restype, argtypes)
@@ -66,6 +68,11 @@ SYMBOLS = {
     "sph_last_error": (C.c_char_p, [_vp]),
     "sph_version": (C.c_char_p, []),
     "sph_world_attach_nccl": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "sph_world_create_nccl": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
+    "sph_world_set_slab": (C.c_int, [_vp, C.c_int32, C.c_int32]),
+    "sph_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "sph_fluid_set_ids": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t]),
+    "sph_fluid_read_ids": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t]),
 }
 
 

@@ -55,8 +55,7 @@ __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a
 // scatter the fluid's particles to original order: cur[t] = (pos.xyz, mass), slot_of[t] = s
 __global__ void k_el_to_orig(const float4* __restrict__ pos, const uint32_t* __restrict__ orig, uint32_t lo, uint32_t hi, float4* __restrict__ cur,
                              uint32_t* __restrict__ slot_of) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= C.n_fluid) return;
+    SPH_OWNED_INDEX(s)
     uint32_t g = orig[s];
     if (g < lo || g >= hi) return;
     cur[g - lo] = pos[s];

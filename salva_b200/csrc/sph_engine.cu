@@ -89,7 +89,12 @@ struct BoundaryRec {
 };
 
 sph_status iisph_step(sph_world* w, float dt_total, const float g[3]);
+sph_status slab_begin_step(sph_world* w);
+sph_status slab_after_sort(sph_world* w);
+sph_status slab_refresh(sph_world* w, void* array, size_t elem);
+sph_status slab_allreduce(sph_world* w, float* buf, size_t n);
 void iisph_release(sph_world* w);
+void slab_release(sph_world* w);
 const float* iisph_pred(sph_world* w);
 sph_status elasticity_solve(sph_world* w, uint32_t fluid, ForceRec& fr);
 void elasticity_release(ForceRec& fr);
@@ -98,6 +103,22 @@ inline float __uint_as_float_host(uint32_t u) {
     memcpy(&f, &u, sizeof f);
     return f;
 }
+
+struct SlabState {
+    bool active = false, own_comm = false;
+    int rank = 0, nranks = 1;
+    int lo = INT_MIN, hi = INT_MAX;  // owned cell columns [lo, hi) in absolute cell coordinates floor(x / h)
+    int has_left = 0, has_right = 0;
+    void* comm = nullptr;
+    DBuf<uint32_t> d_cnt, flag, flag2, flag_o, gid_l, gid_r;
+    DBuf<unsigned long long> d_cnt64;
+    DBuf<float4> out_l[3], out_r[3];
+    // slot ranges of the current step (after the sort)
+    uint32_t gl_count = 0, sl_begin = 0, sl_count = 0, sr_begin = 0, sr_count = 0, gr_begin = 0, gr_count = 0;
+    uint32_t exp_ghost_l = 0, exp_ghost_r = 0, exp_send_l = 0, exp_send_r = 0;
+    uint32_t migrated_in = 0, migrated_out = 0;
+    unsigned long long global_n = 0;
+};
 
 enum { EV_START = 0, EV_GRID, EV_NBR, EV_DENS, EV_DIV, EV_FOLD, EV_FORCES, EV_INTEG, EV_PRESS, EV_END, EV_COUNT };
 
@@ -113,7 +134,11 @@ struct sph_world {
 
     std::vector<FluidRec> fluids;
     std::vector<BoundaryRec> bounds;
-    size_t N = 0, B = 0;
+    size_t N = 0, B = 0;   // N = fluid particles OWNED by this world
+    size_t Ntot = 0;       // slots of the sorted arrays during a step: owned + ghost (== N on one GPU)
+    uint32_t own_begin = 0;  // first owned slot (ghost columns of a slab world sit at both ends of the sorted arrays)
+    SlabState slab;
+    uint64_t stats_exchanges = 0;
 
     // timestep_manager.rs:21-31: dt/inv_dt are 0 until the first advance()
     float dt = 0.f, inv_dt = 0.f;
@@ -130,6 +155,8 @@ struct sph_world {
     int cur = 0, bcur = 0;
     DBuf<float4> pos[2], vel[2], vc[2], bpos[2], bvel[2];
     DBuf<uint32_t> orig[2], borig[2];
+    DBuf<uint32_t> gid[2];  // caller-visible particle ids (default: original index); follow particles across ranks
+    std::vector<uint32_t> h_gid;
     DBuf<float> press[2];
     DBuf<float4> vs, acc, normals, dbg_acc;
     DBuf<float> dens, alpha, kappa, divv, pred, bvol, bforce;
@@ -233,7 +260,9 @@ void fill_static_consts(sph_world* w) {
     c.h2 = w->h * w->h;
     c.sigma = 8.0f / (3.14159265358979323846f * w->h * w->h * w->h);
     c.dsigma = c.sigma / w->h;
-    c.n_fluid = (uint32_t)w->N;
+    c.n_fluid = (uint32_t)w->Ntot;
+    c.i_begin = w->own_begin;
+    c.n_owned = (uint32_t)w->N;
     c.n_bound = (uint32_t)w->B;
     c.n_fluids = (int)w->fluids.size();
     c.n_bounds = (int)w->bounds.size();
@@ -273,18 +302,23 @@ sph_status stage_down(sph_world* w) {
     w->h_vel.resize(3 * N);
     w->h_vc.resize(3 * N);
     w->h_press.assign(N, 0.f);
+    w->h_gid.resize(N);
     if (N) {
         int c = w->cur;
+        uint32_t ob = w->own_begin;
         CU(w->o_a.ensure(3 * N));
         const float4* srcs[3] = {w->pos[c].p, w->vel[c].p, w->vc[c].p};
         float* dsts[3] = {w->h_pos.data(), w->h_vel.data(), w->h_vc.data()};
         for (int a = 0; a < 3; ++a) {
-            LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, srcs[a], w->o_a.p);
+            LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p + ob, srcs[a] + ob, w->o_a.p);
             CU(cudaMemcpyAsync(dsts[a], w->o_a.p, 3 * N * sizeof(float), cudaMemcpyDeviceToHost, w->st));
             CU(cudaStreamSynchronize(w->st));
         }
+        LAUNCH(k_export_u32, N, 256, (uint32_t)N, w->orig[c].p + ob, w->gid[c].p + ob, reinterpret_cast<uint32_t*>(w->o_a.p));
+        CU(cudaMemcpyAsync(w->h_gid.data(), w->o_a.p, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+        CU(cudaStreamSynchronize(w->st));
         if (w->desc.solver == SPH_SOLVER_IISPH && w->press[c].p) {
-            LAUNCH(k_export1, N, 256, (uint32_t)N, w->orig[c].p, w->press[c].p, w->o_a.p);
+            LAUNCH(k_export1, N, 256, (uint32_t)N, w->orig[c].p + ob, w->press[c].p + ob, w->o_a.p);
             CU(cudaMemcpyAsync(w->h_press.data(), w->o_a.p, N * sizeof(float), cudaMemcpyDeviceToHost, w->st));
             CU(cudaStreamSynchronize(w->st));
         }
@@ -310,13 +344,15 @@ void recompute_offsets(sph_world* w) {
 }
 
 sph_status ensure_fluid_buffers(sph_world* w) {
-    size_t N = w->N;
+    size_t N = std::max(w->Ntot, w->N);
     for (int k = 0; k < 2; ++k) {
-        CU(w->pos[k].ensure(N));
-        CU(w->vel[k].ensure(N));
-        CU(w->vc[k].ensure(N));
-        CU(w->orig[k].ensure(N));
-        if (w->desc.solver == SPH_SOLVER_IISPH) CU(w->press[k].ensure(N));
+        bool keep = k == w->cur;  // the live buffers may be grown while they hold particles (ghost append)
+        CU(w->pos[k].ensure(N, keep, w->st));
+        CU(w->vel[k].ensure(N, keep, w->st));
+        CU(w->vc[k].ensure(N, keep, w->st));
+        CU(w->orig[k].ensure(N, keep, w->st));
+        CU(w->gid[k].ensure(N, keep, w->st));
+        if (w->desc.solver == SPH_SOLVER_IISPH) CU(w->press[k].ensure(N, keep, w->st));
     }
     CU(w->vs.ensure(N));
     CU(w->acc.ensure(N));
@@ -346,7 +382,10 @@ sph_status stage_up(sph_world* w) {
     if (!w->staged) return SPH_OK;
     recompute_offsets(w);
     size_t N = w->N;
+    w->Ntot = N;
+    w->own_begin = 0;
     TRY(ensure_fluid_buffers(w));
+    w->h_gid.resize(N);
     if (N) {
         std::vector<float> mass(N);
         std::vector<uint32_t> fid(N);
@@ -368,6 +407,7 @@ sph_status stage_up(sph_world* w) {
         CU(cudaMemcpyAsync(w->o_fid.p, fid.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice, w->st));
         int c = w->cur;
         LAUNCH(k_iota, N, 256, (uint32_t)N, w->orig[c].p);
+        CU(cudaMemcpyAsync(w->gid[c].p, w->h_gid.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice, w->st));
         CU(cudaMemsetAsync(w->pos[c].p, 0, N * sizeof(float4), w->st));
         CU(cudaMemsetAsync(w->vel[c].p, 0, N * sizeof(float4), w->st));
         LAUNCH(k_import, N, 256, (uint32_t)N, w->orig[c].p, w->o_a.p, w->o_b.p, w->o_c.p, w->o_mass.p, w->o_fid.p, w->pos[c].p, w->vel[c].p,
@@ -423,6 +463,7 @@ sph_status apply_pending_deletes(sph_world* w) {
     if (!any) return SPH_OK;
     TRY(stage_down(w));
     std::vector<float> np, nv, nc, nvol, npr;
+    std::vector<uint32_t> ngid;
     np.reserve(w->h_pos.size());
     nv.reserve(w->h_pos.size());
     nc.reserve(w->h_pos.size());
@@ -437,6 +478,7 @@ sph_status apply_pending_deletes(sph_world* w) {
                 nc.push_back(w->h_vc[3 * g + a]);
             }
             nvol.push_back(w->h_vol[g]);
+            ngid.push_back(g < w->h_gid.size() ? w->h_gid[g] : (uint32_t)g);
             npr.push_back(g < w->h_press.size() ? w->h_press[g] : 0.f);
             ++kept;
         }
@@ -449,13 +491,14 @@ sph_status apply_pending_deletes(sph_world* w) {
     w->h_vc.swap(nc);
     w->h_vol.swap(nvol);
     w->h_press.swap(npr);
+    w->h_gid.swap(ngid);
     recompute_offsets(w);
     return SPH_OK;
 }
 
 // ---- step phases ----------------------------------------------------------------------------------
 sph_status phase_grid(sph_world* w) {
-    size_t N = w->N, B = w->B;
+    size_t N = w->Ntot, B = w->B;  // the sort covers owned + ghost slots
     int c = w->cur, bc = w->bcur;
     int init[11] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(w->d_scal.p, init, sizeof init, cudaMemcpyHostToDevice, w->st));
@@ -509,11 +552,12 @@ sph_status phase_grid(sph_world* w) {
         g.in4[2] = w->vc[c].p;  g.out4[2] = w->vc[c ^ 1].p;
         g.n4 = 3;
         g.in1[0] = w->orig[c].p; g.out1[0] = w->orig[c ^ 1].p;
-        g.n1 = 1;
+        g.in1[1] = w->gid[c].p; g.out1[1] = w->gid[c ^ 1].p;
+        g.n1 = 2;
         if (w->desc.solver == SPH_SOLVER_IISPH) {
-            g.in1[1] = reinterpret_cast<const uint32_t*>(w->press[c].p);
-            g.out1[1] = reinterpret_cast<uint32_t*>(w->press[c ^ 1].p);
-            g.n1 = 2;
+            g.in1[2] = reinterpret_cast<const uint32_t*>(w->press[c].p);
+            g.out1[2] = reinterpret_cast<uint32_t*>(w->press[c ^ 1].p);
+            g.n1 = 3;
         }
         LAUNCH(k_gather, N, 256, (uint32_t)N, w->perm.p, g);
         w->cur = c ^ 1;
@@ -537,6 +581,11 @@ sph_status phase_grid(sph_world* w) {
         w->bcur = bc ^ 1;
     }
     CU(cudaGetLastError());
+    if (w->slab.active) {
+        TRY(slab_after_sort(w));
+        fill_static_consts(w);
+        TRY(upload_consts(w));
+    }
     return SPH_OK;
 }
 
@@ -649,7 +698,8 @@ sph_status phase_neighbors(sph_world* w) {
         TRY(upload_consts(w));
     }
     if (N) {
-        k_sum_u32<<<std::min<uint32_t>(cdiv(N, 256), 1184), 256, 0, w->st>>>((uint32_t)N, w->cnt_f.p, w->cnt_b.p, w->d_cnt.p + 1);
+        k_sum_u32<<<std::min<uint32_t>(cdiv(N, 256), 1184), 256, 0, w->st>>>((uint32_t)N, w->cnt_f.p + w->own_begin, w->cnt_b.p + w->own_begin,
+                                                                             w->d_cnt.p + 1);
         w->launches++;
     }
     CU(cudaGetLastError());
@@ -662,11 +712,14 @@ sph_status read_error(sph_world* w, uint32_t nblk, float* out) {
     int nf = (int)w->fluids.size();
     k_reduce_partials<<<nf, 256, 0, w->st>>>(w->partial.p, nblk, nf, w->errsum.p);
     w->launches++;
+    TRY(slab_allreduce(w, w->errsum.p, nf));  // multi-GPU: the means are over ALL ranks' particles
     CU(cudaMemcpyAsync(w->h_pinned, w->errsum.p, nf * sizeof(float), cudaMemcpyDeviceToHost, w->st));
     CU(cudaStreamSynchronize(w->st));
     float mx = 0.f;
-    for (int f = 0; f < nf; ++f)
-        if (w->fluids[f].n) mx = std::max(mx, w->h_pinned[f] / (float)(double)w->fluids[f].n);
+    for (int f = 0; f < nf; ++f) {
+        double n = w->slab.active ? (double)w->slab.global_n : (double)w->fluids[f].n;
+        if (n > 0) mx = std::max(mx, w->h_pinned[f] / (float)n);
+    }
     *out = mx;
     return SPH_OK;
 }
@@ -726,6 +779,7 @@ sph_status launch_density_alpha(sph_world* w) {
         Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
         DISPATCH1(k_density_alpha, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->alpha.p, w->d_scal.p + 7);
     }
+    TRY(slab_refresh(w, w->dens.p, sizeof(float)));  // XSPH / artificial viscosity / Akinci gather rho_j of ghosts
     return SPH_OK;
 }
 #define BOOL3(kern, b0, b1, b2, n, threads, ...)                                                   \
@@ -772,6 +826,7 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk) {
               w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
         *nblk = cdiv(N, PASS_T);
     }
+    TRY(slab_refresh(w, w->kappa.p, sizeof(float)));  // the following update gathers kappa_j of ghosts
     return SPH_OK;
 }
 // compute_velocity_changes_for_divergence (pressure = false) / compute_velocity_changes (pressure = true)
@@ -796,6 +851,7 @@ sph_status launch_vel_update(sph_world* w, bool pressure) {
         BOOL4(k_vel_update, multi, bf, pressure, tex, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->tex_kappa,
               w->vc[c].p, w->vs.p, w->bforce.p, w->inv_dt);
     }
+    TRY(slab_refresh(w, w->vs.p, sizeof(float4)));  // the following evaluation gathers v*_j of ghosts
     return SPH_OK;
 }
 
@@ -831,7 +887,7 @@ sph_status phase_forces(sph_world* w) {
                               w->bforce.p, (uint32_t)f, p[0], p[1], p[2], p[3], p[4]);
                     break;
                 case SPH_FORCE_AKINCI2013_TENSION: {
-                    CU(w->normals.ensure(N));
+                    CU(w->normals.ensure(std::max(w->Ntot, w->N)));
                     float h = w->h;
                     float coh_norm = 32.0f / (3.14159265358979323846f * powf(h, 9.f));
                     float h6_64 = powf(h, 6.f) / 64.0f;
@@ -846,6 +902,7 @@ sph_status phase_forces(sph_world* w) {
                         break;
                     }
                     DISPATCH1(k_akinci_normals, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->dens.p, w->normals.p, (uint32_t)f);
+                    TRY(slab_refresh(w, w->normals.p, sizeof(float4)));
                     DISPATCH2(k_akinci_force, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->normals.p, w->acc.p,
                               w->bforce.p, (uint32_t)f, p[0], p[1], coh_norm, h6_64, adh_norm);
                     break;
@@ -898,12 +955,13 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     }
     CU(cudaEventRecord(w->ev[EV_DIV], w->st));
     // update_velocities :422-430, zero vc :689-691, acc += gravity :574-578
-    LAUNCH(k_fold_velocities, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2]);
+    LAUNCH(k_fold_velocities, w->Ntot, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2]);  // ghosts too (vel = v*)
     CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
     TRY(phase_forces(w));
     CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
     timestep_advance(w, dt_total);  // :702
     LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p);
+    TRY(slab_refresh(w, w->vs.p, sizeof(float4)));
     CU(cudaEventRecord(w->ev[EV_INTEG], w->st));
     // pressure_solve :432-464
     w->stats.n_pressure_iter = w->stats.n_pressure_eval = 0;
@@ -935,6 +993,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
 sph_status world_step(sph_world* w, float dt, const float g[3]) {
     TRY(enter(w));
     w->launches = 0;
+    w->stats_exchanges = 0;
     w->n_spans = 0;
     memset(&w->stats, 0, sizeof w->stats);
     TRY(apply_pending_deletes(w));  // liquid_world.rs:79-81
@@ -947,7 +1006,15 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
         return w->fail(SPH_ERR_INVALID, "too many fluids (max %d) or boundaries (max %d)", MAX_FLUIDS, MAX_BOUNDARIES);
     if (!(dt > F32_EPS)) return SPH_OK;  // timestep_manager.rs:56-58: is_done() before the first substep
     CU(cudaEventRecord(w->ev[EV_START], w->st));
-    if (N + w->B == 0) return SPH_OK;
+    if (w->slab.active) {
+        TRY(slab_begin_step(w));
+        N = w->N;
+        w->stats.n_fluid_particles = N;
+    } else {
+        w->Ntot = N;
+        w->own_begin = 0;
+    }
+    if (w->Ntot + w->B == 0) return SPH_OK;
     TRY(phase_grid(w));
     CU(cudaEventRecord(w->ev[EV_GRID], w->st));
     TRY(phase_neighbors(w));
@@ -971,6 +1038,9 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
     CU(cudaGetLastError());
     w->stats.n_contacts = cnts[0] + cnts[1];
     w->stats.kernel_launches = w->launches;
+    w->stats.n_ghost_particles = (uint32_t)(w->Ntot - w->N);
+    w->stats.n_migrated = w->slab.migrated_in + w->slab.migrated_out;
+    w->stats.n_exchanges = (uint32_t)w->stats_exchanges;
     auto el = [&](int a, int b) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, w->ev[a], w->ev[b]);
@@ -1008,6 +1078,7 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
 
 }  // namespace
 
+#include "sph_slab.inl"
 #include "sph_iisph_host.inl"
 #include "sph_elasticity_host.inl"
 
@@ -1074,7 +1145,7 @@ void sph_world_destroy(sph_world* w) {
     if (w->st) cudaStreamSynchronize(w->st);
     for (int k = 0; k < 2; ++k) {
         w->pos[k].release(); w->vel[k].release(); w->vc[k].release(); w->bpos[k].release(); w->bvel[k].release();
-        w->orig[k].release(); w->borig[k].release(); w->press[k].release();
+        w->orig[k].release(); w->borig[k].release(); w->press[k].release(); w->gid[k].release();
     }
     w->vs.release(); w->acc.release(); w->normals.release(); w->dbg_acc.release();
     w->dens.release(); w->alpha.release(); w->kappa.release(); w->divv.release(); w->pred.release(); w->bvol.release(); w->bforce.release();
@@ -1085,6 +1156,7 @@ void sph_world_destroy(sph_world* w) {
     w->partial.release(); w->errsum.release(); w->d_scal.release(); w->d_cnt.release();
     w->o_a.release(); w->o_b.release(); w->o_c.release(); w->o_mass.release(); w->o_fid.release();
     iisph_release(w);
+    slab_release(w);
     for (auto& f : w->fluids)
         for (auto& fr : f.forces) elasticity_release(fr);
     if (w->tex_vs) cudaDestroyTextureObject(w->tex_vs);
@@ -1124,6 +1196,8 @@ sph_status sph_fluid_add(sph_world* w, const float* pos, const float* vel, const
     if (volumes) w->h_vol.insert(w->h_vol.end(), volumes, volumes + n);
     else w->h_vol.insert(w->h_vol.end(), n, pv);
     w->h_press.insert(w->h_press.end(), n, 0.f);
+    w->h_gid.resize(w->h_vol.size() - n);
+    for (size_t i = 0; i < n; ++i) w->h_gid.push_back((uint32_t)i);
     w->fluids.push_back(f);
     recompute_offsets(w);
     if (handle) *handle = (uint32_t)w->fluids.size() - 1;
@@ -1161,6 +1235,12 @@ sph_status sph_fluid_append(sph_world* w, uint32_t fluid, const float* pos, cons
     w->h_vol.insert(w->h_vol.begin() + at, n, pv);
     w->h_press.resize(w->h_vol.size() - n, 0.f);
     w->h_press.insert(w->h_press.begin() + at, n, 0.f);
+    w->h_gid.resize(w->h_vol.size() - n);
+    {
+        std::vector<uint32_t> ids(n);
+        for (size_t i = 0; i < n; ++i) ids[i] = (uint32_t)(f.n + i);
+        w->h_gid.insert(w->h_gid.begin() + at, ids.begin(), ids.end());
+    }
     f.n += n;
     f.pending_delete.resize(f.n, 0);
     recompute_offsets(w);
@@ -1208,8 +1288,12 @@ sph_status sph_fluid_write(sph_world* w, uint32_t fluid, const float* pos, const
     CU(w->o_b.ensure(3 * N));
     if (pos) CU(cudaMemcpyAsync(w->o_a.p + 3 * f.offset, pos, 3 * n * sizeof(float), cudaMemcpyHostToDevice, w->st));
     if (vel) CU(cudaMemcpyAsync(w->o_b.p + 3 * f.offset, vel, 3 * n * sizeof(float), cudaMemcpyHostToDevice, w->st));
-    LAUNCH(k_import, N, 256, (uint32_t)N, w->orig[c].p, pos ? w->o_a.p : nullptr, vel ? w->o_b.p : nullptr, (const float*)nullptr,
-           (const float*)nullptr, (const uint32_t*)nullptr, w->pos[c].p, w->vel[c].p, w->vc[c].p, (uint32_t)f.offset, (uint32_t)(f.offset + n));
+    {
+        uint32_t ob = w->own_begin;
+        LAUNCH(k_import, N, 256, (uint32_t)N, w->orig[c].p + ob, pos ? w->o_a.p : nullptr, vel ? w->o_b.p : nullptr, (const float*)nullptr,
+               (const float*)nullptr, (const uint32_t*)nullptr, w->pos[c].p + ob, w->vel[c].p + ob, w->vc[c].p + ob, (uint32_t)f.offset,
+               (uint32_t)(f.offset + n));
+    }
     CU(cudaStreamSynchronize(w->st));
     w->lists_valid = false;
     return SPH_OK;
@@ -1234,11 +1318,11 @@ sph_status sph_fluid_read(sph_world* w, uint32_t fluid, float* pos, float* vel, 
     CU(w->o_a.ensure(3 * N));
     CU(w->o_b.ensure(3 * N));
     if (pos) {
-        LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, w->pos[c].p, w->o_a.p);
+        LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p + w->own_begin, w->pos[c].p + w->own_begin, w->o_a.p);
         CU(cudaMemcpyAsync(pos, w->o_a.p + 3 * f.offset, 3 * f.n * sizeof(float), cudaMemcpyDeviceToHost, w->st));
     }
     if (vel) {
-        LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, w->vel[c].p, w->o_b.p);
+        LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p + w->own_begin, w->vel[c].p + w->own_begin, w->o_b.p);
         CU(cudaMemcpyAsync(vel, w->o_b.p + 3 * f.offset, 3 * f.n * sizeof(float), cudaMemcpyDeviceToHost, w->st));
     }
     CU(cudaStreamSynchronize(w->st));
@@ -1365,11 +1449,13 @@ sph_status sph_debug_read(sph_world* w, uint32_t fluid, int what, float* out, si
         case SPH_DBG_PRESSURE: s1 = w->press[c].p; break;
         default: break;
     }
-    if (s1) LAUNCH(k_export1, N, 256, (uint32_t)N, w->orig[c].p, s1, w->o_c.p);
-    else if (what == SPH_DBG_VELOCITY_CHANGE) LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, w->vc[c].p, w->o_c.p);
-    else if (what == SPH_DBG_ACCELERATION) LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p, w->dbg_acc.p, w->o_c.p);
-    else if (what == SPH_DBG_NUM_FLUID_CONTACTS) LAUNCH(k_export1u, N, 256, (uint32_t)N, w->orig[c].p, w->cnt_f.p, w->o_c.p);
-    else if (what == SPH_DBG_NUM_BOUNDARY_CONTACTS) LAUNCH(k_export1u, N, 256, (uint32_t)N, w->orig[c].p, w->cnt_b.p, w->o_c.p);
+    const uint32_t ob = w->own_begin;
+    const uint32_t* og = w->orig[c].p + ob;
+    if (s1) LAUNCH(k_export1, N, 256, (uint32_t)N, og, s1 + ob, w->o_c.p);
+    else if (what == SPH_DBG_VELOCITY_CHANGE) LAUNCH(k_export3, N, 256, (uint32_t)N, og, w->vc[c].p + ob, w->o_c.p);
+    else if (what == SPH_DBG_ACCELERATION) LAUNCH(k_export3, N, 256, (uint32_t)N, og, w->dbg_acc.p + ob, w->o_c.p);
+    else if (what == SPH_DBG_NUM_FLUID_CONTACTS) LAUNCH(k_export1u, N, 256, (uint32_t)N, og, w->cnt_f.p + ob, w->o_c.p);
+    else if (what == SPH_DBG_NUM_BOUNDARY_CONTACTS) LAUNCH(k_export1u, N, 256, (uint32_t)N, og, w->cnt_b.p + ob, w->o_c.p);
     else return w->fail(SPH_ERR_INVALID, "sph_debug_read: unknown selector %d", what);
     CU(cudaMemcpyAsync(out, w->o_c.p + width * f.offset, width * f.n * sizeof(float), cudaMemcpyDeviceToHost, w->st));
     CU(cudaStreamSynchronize(w->st));
@@ -1379,10 +1465,94 @@ sph_status sph_debug_read(sph_world* w, uint32_t fluid, int what, float* out, si
 const char* sph_last_error(const sph_world* w) { return w ? w->err.c_str() : "null world"; }
 const char* sph_version(void) { return "salva_b200 0.1 (sm_100a)"; }
 
+sph_status sph_nccl_unique_id(char out[128]) {
+    if (!out) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    std::string err;
+    if (!nccl_load(&err)) return SPH_ERR_NCCL;
+    nccl_uid id;
+    if (g_nccl.GetUniqueId(&id) != 0) return SPH_ERR_NCCL;
+    memcpy(out, id.internal, 128);
+    return SPH_OK;
+}
+
+static sph_status slab_attach(sph_world* w, void* comm, bool own, int rank, int nranks) {
+    if (rank < 0 || nranks < 1 || rank >= nranks) return w->fail(SPH_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+    SlabState& S = w->slab;
+    S.comm = comm;
+    S.own_comm = own;
+    S.rank = rank;
+    S.nranks = nranks;
+    S.has_left = rank > 0;
+    S.has_right = rank + 1 < nranks;
+    S.active = nranks > 1;
+    w->desc.deterministic = 1;  // ghost-column order agreement relies on the stable in-cell order
+    CU(S.d_cnt.ensure(4));
+    CU(S.d_cnt64.ensure(1));
+    return SPH_OK;
+}
+
 sph_status sph_world_attach_nccl(sph_world* w, void* nccl_comm, int rank, int nranks) {
+    if (!w || !nccl_comm) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!nccl_load(&w->err)) return SPH_ERR_NCCL;
+    TRY(enter(w));
+    return slab_attach(w, nccl_comm, false, rank, nranks);
+}
+
+sph_status sph_world_create_nccl(sph_world* w, const char unique_id[128], int rank, int nranks) {
+    if (!w || !unique_id) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!nccl_load(&w->err)) return SPH_ERR_NCCL;
+    TRY(enter(w));
+    nccl_uid id;
+    memcpy(id.internal, unique_id, 128);
+    void* comm = nullptr;
+    NC(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    return slab_attach(w, comm, true, rank, nranks);
+}
+
+sph_status sph_world_set_slab(sph_world* w, int32_t cell_lo, int32_t cell_hi) {
     if (!w) return SPH_ERR_INVALID;
-    (void)nccl_comm; (void)rank; (void)nranks;
-    return w->fail(SPH_ERR_NCCL, "multi-GPU slab exchange is not built yet");
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if ((long long)cell_hi - (long long)cell_lo < 2) return w->fail(SPH_ERR_INVALID, "a slab must be at least 2 cell columns wide");
+    w->slab.lo = cell_lo;
+    w->slab.hi = cell_hi;
+    return SPH_OK;
+}
+
+sph_status sph_fluid_set_ids(sph_world* w, uint32_t fluid, const uint32_t* ids, size_t n) {
+    if (!w || !ids) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    FluidRec& f = w->fluids[fluid];
+    if (n != f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_set_ids: length %zu != particle count %zu", n, f.n);
+    TRY(enter(w));
+    TRY(stage_down(w));
+    w->h_gid.resize(w->N);
+    memcpy(w->h_gid.data() + f.offset, ids, n * sizeof(uint32_t));
+    return SPH_OK;
+}
+
+sph_status sph_fluid_read_ids(sph_world* w, uint32_t fluid, uint32_t* ids, size_t cap) {
+    if (!w || !ids) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    FluidRec& f = w->fluids[fluid];
+    if (cap < f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_read_ids: capacity %zu < particle count %zu", cap, f.n);
+    if (f.n == 0) return SPH_OK;
+    if (w->staged) {
+        memcpy(ids, w->h_gid.data() + f.offset, f.n * sizeof(uint32_t));
+        return SPH_OK;
+    }
+    TRY(enter(w));
+    size_t N = w->N;
+    int c = w->cur;
+    CU(w->o_c.ensure(3 * std::max(N, w->B)));
+    LAUNCH(k_export_u32, N, 256, (uint32_t)N, w->orig[c].p + w->own_begin, w->gid[c].p + w->own_begin, reinterpret_cast<uint32_t*>(w->o_c.p));
+    CU(cudaMemcpyAsync(ids, reinterpret_cast<uint32_t*>(w->o_c.p) + f.offset, f.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    return SPH_OK;
 }
 
 }  // extern "C"

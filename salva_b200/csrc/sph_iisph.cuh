@@ -23,8 +23,7 @@ namespace sphk {
 
 // pressures *= 0.5 (iisph_solver.rs:673-677) and prho = p / rho^2
 __global__ void k_iisph_warm_start(float* __restrict__ p, const float* __restrict__ dens, float* __restrict__ prho) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float v = p[i] * 0.5f;
     float r = dens[i];
     p[i] = v;
@@ -36,8 +35,7 @@ template <bool MULTI>
 __global__ void __launch_bounds__(PASS_T)
 k_iisph_dii(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens,
             float4* __restrict__ dii, float dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 pi = pos[i];
     float rho0 = C.fluids[MULTI ? fid_of(vel[i]) : 0].density0;
     float rhoi = dens[i];
@@ -61,8 +59,7 @@ template <bool MULTI>
 __global__ void __launch_bounds__(PASS_T)
 k_iisph_aii(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens,
             const float4* __restrict__ dii, float* __restrict__ aii, float dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 pi = pos[i];
     float rho0 = C.fluids[MULTI ? fid_of(vel[i]) : 0].density0;
     float rhoi = dens[i];
@@ -87,8 +84,7 @@ template <bool MULTI>
 __global__ void __launch_bounds__(PASS_T)
 k_iisph_dij_pjl(const float4* __restrict__ pos, Lists L, const float* __restrict__ prho, const float* __restrict__ press, const float4* __restrict__ dii,
                 float4* __restrict__ dij_pjl, float4* __restrict__ s, float dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 pi = pos[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
     for_fluid_contacts<false, true>(
@@ -114,7 +110,8 @@ k_iisph_next_pressures(const float4* __restrict__ pos, const float4* __restrict_
                        float* __restrict__ partial, float dt, float omega) {
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < C.n_fluid;
+    bool valid = i < C.n_owned;
+    i += C.i_begin;
     float e = 0.f;
     uint32_t fi = 0;
     if (valid) {
@@ -155,8 +152,7 @@ template <bool MULTI, bool BFORCE>
 __global__ void __launch_bounds__(PASS_T)
 k_iisph_velocity_changes(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
                          const float* __restrict__ prho, float4* __restrict__ vc, float* __restrict__ bforce, float dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 pi = pos[i];
     float rho0 = C.fluids[MULTI ? fid_of(vel[i]) : 0].density0;
     float pri = prho[i];
@@ -183,8 +179,7 @@ k_iisph_velocity_changes(const float4* __restrict__ pos, const float4* __restric
 
 // update_velocities_and_positions iisph_solver.rs:406-420 + zero vc :707-709
 __global__ void k_iisph_update(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restrict__ vc, float dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 p = pos[i], v = vel[i], c = vc[i];
     v.x += c.x; v.y += c.y; v.z += c.z;
     p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;

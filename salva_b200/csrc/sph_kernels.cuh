@@ -37,7 +37,9 @@ struct Consts {
     int ox, oy, oz;              // grid origin in cell coordinates (one padding cell each side)
     int nx, ny, nz;
     int ntx, nty, ntz;           // tile grid (sph_tile.cuh): 2 x 2 cell columns x TILE_Z cells per tile
-    uint32_t n_fluid, n_bound;   // particle totals
+    uint32_t n_fluid, n_bound;   // particle totals (n_fluid counts owned + ghost slots of the sorted arrays)
+    uint32_t i_begin, n_owned;   // owned slots [i_begin, i_begin + n_owned): everything on one GPU; the slab between the
+                                 // two ghost columns in a multi-GPU world (x-major order keeps ghosts at both ends)
     uint32_t stride;             // neighbour-list column stride (>= n_fluid, multiple of 32)
     uint32_t cap_f, cap_b;       // list capacities (rows)
     int n_fluids, n_bounds;      // object counts
@@ -101,6 +103,12 @@ __device__ __forceinline__ Pair make_pair(const float4& pi, const float4& pj) {
     p.g = NEED_G ? kernel_gfac(p.d2, p.r, inv_r) : 0.f;
     return p;
 }
+
+// index of the owned particle handled by this thread (returns from the kernel when out of range)
+#define SPH_OWNED_INDEX(i)                                   \
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;      \
+    if (i >= C.n_owned) return;                              \
+    i += C.i_begin;
 
 __device__ __forceinline__ uint32_t fid_of(const float4& v) { return __float_as_uint(v.w); }
 
@@ -284,7 +292,9 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
             uint32_t* __restrict__ maxcnt /* [0]=fluid,[1]=boundary */) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nf = 0, nb = 0;
-    if (i < C.n_fluid) {
+    const bool owned = i < C.n_owned;
+    i += C.i_begin;
+    if (owned) {
         float4 pi = pos[i];
         uint32_t fi = MULTI ? fid_of(vel[i]) : 0u;
         int cx = cell_coord(pi.x), cy = cell_coord(pi.y), cz = cell_coord(pi.z);
@@ -401,23 +411,21 @@ __global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __res
     vs[i] = make_float4(v.x + c.x, v.y + c.y, v.z + c.z, 0.f);
 }
 
-// a10: update_velocities dfsph_solver.rs:422-430 + zero vc :689-691 + acc = gravity (predict_advection :574-578)
-__global__ void k_fold_velocities(float4* __restrict__ vel, float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ acc, float gx, float gy,
+// a10: update_velocities dfsph_solver.rs:422-430 + zero vc :689-691 + acc = gravity (predict_advection :574-578).
+// vel += vc is written as vel = v*: v* was materialised as vel + vc by the producer, so the result is bitwise the
+// same for owned particles, and ghost particles (multi-GPU) only carry an up-to-date v*.
+__global__ void k_fold_velocities(float4* __restrict__ vel, float4* __restrict__ vc, const float4* __restrict__ vs, float4* __restrict__ acc, float gx, float gy,
                                   float gz) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C.n_fluid) return;
-    float4 v = vel[i], c = vc[i];
-    v.x += c.x; v.y += c.y; v.z += c.z;
-    vel[i] = v;
+    float4 v = vel[i], s = vs[i];
+    vel[i] = make_float4(s.x, s.y, s.z, v.w);
     vc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    vs[i] = make_float4(v.x, v.y, v.z, 0.f);
     acc[i] = make_float4(gx, gy, gz, 0.f);
 }
-
 // IISPH variant: accelerations += gravity only (vc is already zero, velocities untouched).
 __global__ void k_set_gravity(const float4* __restrict__ vel, float4* __restrict__ vs, float4* __restrict__ acc, float gx, float gy, float gz) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 v = vel[i];
     vs[i] = make_float4(v.x, v.y, v.z, 0.f);
     acc[i] = make_float4(gx, gy, gz, 0.f);
@@ -426,8 +434,7 @@ __global__ void k_set_gravity(const float4* __restrict__ vel, float4* __restrict
 // a18: integrate_and_clear_accelerations dfsph_solver.rs:505-518 (+ v* = vel + vc)
 __global__ void k_integrate_acc(const float4* __restrict__ vel, float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ acc, float dt,
                                 float4* __restrict__ dbg_acc) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 a = acc[i], c = vc[i], v = vel[i];
     if (dbg_acc) dbg_acc[i] = a;
     c.x += a.x * dt; c.y += a.y * dt; c.z += a.z * dt;
@@ -438,8 +445,7 @@ __global__ void k_integrate_acc(const float4* __restrict__ vel, float4* __restri
 
 // a22: update_positions dfsph_solver.rs:411-420: pos += (vel + vc) * dt
 __global__ void k_update_positions(float4* __restrict__ pos, const float4* __restrict__ vs, float dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 p = pos[i], v = vs[i];
     p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
     pos[i] = p;
@@ -530,6 +536,84 @@ __global__ void k_iota(uint32_t n, uint32_t* __restrict__ a) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n) a[s] = s;
 }
+// ------------------------------------------------------------------------------------------------
+// Slab decomposition helpers (sph_slab.inl): classification by cell column, stream compaction.
+// ------------------------------------------------------------------------------------------------
+// Owned slots [ob, ob + on): keep / leaves-left / leaves-right by the CURRENT cell column; flag_o (indexed by the old
+// original index) marks the particles that stay, so its exclusive scan is their new original index.
+__global__ void k_slab_classify(const float4* __restrict__ pos, const uint32_t* __restrict__ orig, uint32_t ob, uint32_t on, uint32_t n_slots, int lo, int hi,
+                                int has_left, int has_right, uint32_t* __restrict__ fk, uint32_t* __restrict__ fl, uint32_t* __restrict__ fr,
+                                uint32_t* __restrict__ flag_o) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= on) return;
+    uint32_t s = ob + t;
+    int cx = cell_coord(pos[s].x);
+    bool left = has_left && cx < lo, right = has_right && cx >= hi;
+    bool keep = !left && !right;
+    fk[s] = keep;
+    fl[s] = left;
+    fr[s] = right;
+    flag_o[orig[s]] = keep;
+}
+__global__ void k_slab_scatter(uint32_t n_slots, uint32_t ob, const uint32_t* __restrict__ fk, const uint32_t* __restrict__ fl, const uint32_t* __restrict__ fr,
+                               const uint32_t* __restrict__ sk, const uint32_t* __restrict__ sl, const uint32_t* __restrict__ sr,
+                               const uint32_t* __restrict__ scan_o, const float4* __restrict__ pos, const float4* __restrict__ vel,
+                               const float4* __restrict__ vc, const uint32_t* __restrict__ orig, const uint32_t* __restrict__ gid, float4* __restrict__ dpos,
+                               float4* __restrict__ dvel, float4* __restrict__ dvc, uint32_t* __restrict__ dorig, uint32_t* __restrict__ dgid,
+                               float4* __restrict__ lpos, float4* __restrict__ lvel, float4* __restrict__ lvc, uint32_t* __restrict__ lgid,
+                               float4* __restrict__ rpos, float4* __restrict__ rvel, float4* __restrict__ rvc, uint32_t* __restrict__ rgid) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    if (fk[s]) {
+        uint32_t d = sk[s];
+        dpos[d] = pos[s]; dvel[d] = vel[s]; dvc[d] = vc[s];
+        dorig[d] = scan_o[orig[s]];
+        dgid[d] = gid[s];
+    } else if (fl[s]) {
+        uint32_t d = sl[s];
+        lpos[d] = pos[s]; lvel[d] = vel[s]; lvc[d] = vc[s]; lgid[d] = gid[s];
+    } else if (fr[s]) {
+        uint32_t d = sr[s];
+        rpos[d] = pos[s]; rvel[d] = vel[s]; rvc[d] = vc[s]; rgid[d] = gid[s];
+    }
+}
+// boundary columns of the slab: cell column lo goes to the left neighbour, column hi - 1 to the right one
+__global__ void k_slab_column_flags(const float4* __restrict__ pos, uint32_t n, int lo, int hi, int has_left, int has_right, uint32_t* __restrict__ gl,
+                                    uint32_t* __restrict__ gr) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int cx = cell_coord(pos[s].x);
+    gl[s] = has_left && cx == lo;
+    gr[s] = has_right && cx == hi - 1;
+}
+__global__ void k_slab_pack_columns(uint32_t n, const uint32_t* __restrict__ fl, const uint32_t* __restrict__ fr, const uint32_t* __restrict__ sl,
+                                    const uint32_t* __restrict__ sr, const float4* __restrict__ pos, const float4* __restrict__ vel,
+                                    const float4* __restrict__ vc, float4* __restrict__ lpos, float4* __restrict__ lvel, float4* __restrict__ lvc,
+                                    float4* __restrict__ rpos, float4* __restrict__ rvel, float4* __restrict__ rvc) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    if (fl[s]) {
+        uint32_t d = sl[s];
+        lpos[d] = pos[s]; lvel[d] = vel[s]; lvc[d] = vc[s];
+    }
+    if (fr[s]) {
+        uint32_t d = sr[s];
+        rpos[d] = pos[s]; rvel[d] = vel[s]; rvc[d] = vc[s];
+    }
+}
+__global__ void k_iota_from(uint32_t n, uint32_t start, uint32_t* __restrict__ a) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) a[s] = start + s;
+}
+__global__ void k_export_u32(uint32_t n, const uint32_t* __restrict__ orig, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) dst[orig[s]] = src[s];
+}
+__global__ void k_import_u32(uint32_t n, const uint32_t* __restrict__ orig, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) dst[s] = src[orig[s]];
+}
+
 __global__ void k_sum_u32(uint32_t n, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, unsigned long long* __restrict__ out) {
     unsigned long long s = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)a[i] + b[i];

@@ -99,8 +99,7 @@ template <bool MULTI>
 __global__ void __launch_bounds__(PASS_T)
 k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
                 float* __restrict__ dens, float* __restrict__ alpha, int* __restrict__ err) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 pi = pos[i];
     float rho0 = C.fluids[MULTI ? fid_of(vel[i]) : 0].density0;
     float rho = 0.f, sq = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
@@ -141,7 +140,8 @@ k_vel_divergence(const float4* __restrict__ pos, const float4* __restrict__ vs, 
                  int* __restrict__ err) {
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < C.n_fluid;
+    bool valid = i < C.n_owned;
+    i += C.i_begin;
     float e = 0.f;
     uint32_t fi = 0;
     if (valid) {
@@ -194,8 +194,7 @@ template <bool MULTI, bool BFORCE, bool PRESSURE, bool TEX>
 __global__ void __launch_bounds__(PASS_T)
 k_vel_update(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ kappa,
              cudaTextureObject_t tkappa, float4* __restrict__ vc, float4* __restrict__ vs, float* __restrict__ bforce, float inv_dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 pi = pos[i];
     float4 v = vel[i];
     float rho0 = C.fluids[MULTI ? fid_of(v) : 0].density0;
@@ -239,8 +238,7 @@ template <bool MULTI, bool BFORCE>
 __global__ void __launch_bounds__(PASS_T)
 k_force_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L,
              const float* __restrict__ dens, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float cf, float cb, float inv_dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 vi = vel[i];
     if (MULTI && fid_of(vi) != which) return;
     float4 pi = pos[i];
@@ -280,8 +278,7 @@ __global__ void __launch_bounds__(PASS_T)
 k_force_artificial(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L,
                    const float* __restrict__ dens, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float cf, float cb, float alpha,
                    float beta, float cs) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     float4 vi = vel[i];
     if (MULTI && fid_of(vi) != which) return;
     float4 pi = pos[i];
@@ -331,8 +328,7 @@ template <bool MULTI>
 __global__ void __launch_bounds__(PASS_T)
 k_akinci_normals(const float4* __restrict__ pos, const float4* __restrict__ vel, Lists L, const float* __restrict__ dens, float4* __restrict__ normals,
                  uint32_t which) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     if (MULTI && fid_of(vel[i]) != which) return;
     float4 pi = pos[i];
     float nx = 0.f, ny = 0.f, nz = 0.f;
@@ -357,8 +353,7 @@ __global__ void __launch_bounds__(PASS_T)
 k_akinci_force(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens,
                const float4* __restrict__ normals, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float gamma, float adh,
                float coh_norm, float h6_64, float adh_norm) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_fluid) return;
+    SPH_OWNED_INDEX(i)
     if (MULTI && fid_of(vel[i]) != which) return;
     float4 pi = pos[i];
     float rho0 = C.fluids[which].density0;

@@ -121,6 +121,15 @@ def _fp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
 
 
+def nccl_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the host's plumbing broadcasts it)."""
+    buf = C.create_string_buffer(128)
+    st = _lib.lib().sph_nccl_unique_id(buf)
+    if st != 0:
+        raise SphError(st, "sph_nccl_unique_id failed (libnccl not loadable?)")
+    return buf.raw
+
+
 class LiquidWorld:
     """liquid_world.rs:17-158 on the GPU engine."""
 
@@ -259,6 +268,22 @@ class LiquidWorld:
         self._ck(self._L.sph_boundary_read_volumes(self._w, b, _fp(vol), n))
         self._ck(self._L.sph_boundary_read_forces(self._w, b, _fp(f), n))
         return vol, f
+
+    # -- particle ids and multi-GPU slabs (include/sph.h "Multi-GPU") --------------------------------------
+    def set_ids(self, fluid, ids):
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._ck(self._L.sph_fluid_set_ids(self._w, fluid, a.ctypes.data_as(C.POINTER(C.c_uint32)), len(a)))
+
+    def read_ids(self, fluid):
+        n = self.num_particles(fluid)
+        a = np.empty(n, np.uint32)
+        self._ck(self._L.sph_fluid_read_ids(self._w, fluid, a.ctypes.data_as(C.POINTER(C.c_uint32)), n))
+        return a
+
+    def init_slab(self, unique_id, rank, nranks, cell_lo, cell_hi):
+        """Join the slab decomposition: `unique_id` is the 128-byte NCCL id rank 0 got from nccl_unique_id()."""
+        self._ck(self._L.sph_world_create_nccl(self._w, bytes(unique_id), rank, nranks))
+        self._ck(self._L.sph_world_set_slab(self._w, int(cell_lo), int(cell_hi)))
 
     # -- parity / bench aids -----------------------------------------------------------------------
     def force_iterations(self, n_div=-1, n_press=-1):
