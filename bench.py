@@ -262,16 +262,18 @@ def native_arm(args, rank, world_size):
     # ---- e2e: the reference-facing call sequence with HOST buffers, copies inside the timed region ----
     f0 = fh[0]
     n0 = world.num_particles(f0)
-    hp = torch.empty((n0, 3), dtype=torch.float32, pin_memory=True).numpy()
-    hv = torch.empty((n0, 3), dtype=torch.float32, pin_memory=True).numpy()
-    world.read_fluid(f0, hp, hv)
+    cap0 = int(n0 * 1.25) + 1024  # slab worlds gain / lose particles through migration
+    hp_all = torch.empty((cap0, 3), dtype=torch.float32, pin_memory=True).numpy()
+    hv_all = torch.empty((cap0, 3), dtype=torch.float32, pin_memory=True).numpy()
+    world.read_fluid(f0, hp_all[:n0], hv_all[:n0])
     e2e_steps = max(3, min(args.steps, 10))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        world.write_fluid(f0, hp, hv)             # host edits of fluid.positions / velocities go in
-        world.step(sc["dt"], sc["gravity"])       # LiquidWorld::step
-        world.read_fluid(f0, hp, hv)              # results come back in original index order
+        world.write_fluid(f0, hp_all[:n0], hv_all[:n0])   # host edits of fluid.positions / velocities go in
+        world.step(sc["dt"], sc["gravity"])               # LiquidWorld::step
+        n0 = world.num_particles(f0)
+        world.read_fluid(f0, hp_all[:n0], hv_all[:n0])    # results come back in original index order
     barrier()
     e2e_wall = time.perf_counter() - t0
     t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
