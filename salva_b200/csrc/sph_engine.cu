@@ -110,9 +110,10 @@ struct SlabState {
     int lo = INT_MIN, hi = INT_MAX;  // owned cell columns [lo, hi) in absolute cell coordinates floor(x / h)
     int has_left = 0, has_right = 0;
     void* comm = nullptr;
-    DBuf<uint32_t> d_cnt, flag, flag2, flag_o, gid_l, gid_r;
+    DBuf<uint32_t> d_cnt, flag, flag_o, gid_l, gid_r;
     DBuf<unsigned long long> d_cnt64;
-    DBuf<float4> out_l[3], out_r[3];
+    DBuf<float4> out_l[3], out_r[3], col_l[3], col_r[3];
+    bool global_valid = false;
     // slot ranges of the current step (after the sort)
     uint32_t gl_count = 0, sl_begin = 0, sl_count = 0, sr_begin = 0, sr_count = 0, gr_begin = 0, gr_count = 0;
     uint32_t exp_ghost_l = 0, exp_ghost_r = 0, exp_send_l = 0, exp_send_r = 0;
@@ -136,6 +137,7 @@ struct sph_world {
     std::vector<BoundaryRec> bounds;
     size_t N = 0, B = 0;   // N = fluid particles OWNED by this world
     size_t Ntot = 0;       // slots of the sorted arrays during a step: owned + ghost (== N on one GPU)
+    int protect_buf = -1;    // double-buffer index ensure_fluid_buffers() must not reallocate (it is being read)
     uint32_t own_begin = 0;  // first owned slot (ghost columns of a slab world sit at both ends of the sorted arrays)
     SlabState slab;
     uint64_t stats_exchanges = 0;
@@ -346,6 +348,7 @@ void recompute_offsets(sph_world* w) {
 sph_status ensure_fluid_buffers(sph_world* w) {
     size_t N = std::max(w->Ntot, w->N);
     for (int k = 0; k < 2; ++k) {
+        if (k == w->protect_buf) continue;
         bool keep = k == w->cur;  // the live buffers may be grown while they hold particles (ghost append)
         CU(w->pos[k].ensure(N, keep, w->st));
         CU(w->vel[k].ensure(N, keep, w->st));
@@ -420,6 +423,7 @@ sph_status stage_up(sph_world* w) {
     }
     w->staged = false;
     w->lists_valid = false;
+    w->slab.global_valid = false;
     return SPH_OK;
 }
 
@@ -1487,7 +1491,7 @@ static sph_status slab_attach(sph_world* w, void* comm, bool own, int rank, int 
     S.has_right = rank + 1 < nranks;
     S.active = nranks > 1;
     w->desc.deterministic = 1;  // ghost-column order agreement relies on the stable in-cell order
-    CU(S.d_cnt.ensure(4));
+    CU(S.d_cnt.ensure(32));
     CU(S.d_cnt64.ensure(1));
     return SPH_OK;
 }

@@ -539,66 +539,74 @@ __global__ void k_iota(uint32_t n, uint32_t* __restrict__ a) {
 // ------------------------------------------------------------------------------------------------
 // Slab decomposition helpers (sph_slab.inl): classification by cell column, stream compaction.
 // ------------------------------------------------------------------------------------------------
-// Owned slots [ob, ob + on): keep / leaves-left / leaves-right by the CURRENT cell column; flag_o (indexed by the old
-// original index) marks the particles that stay, so its exclusive scan is their new original index.
-__global__ void k_slab_classify(const float4* __restrict__ pos, const uint32_t* __restrict__ orig, uint32_t ob, uint32_t on, uint32_t n_slots, int lo, int hi,
-                                int has_left, int has_right, uint32_t* __restrict__ fk, uint32_t* __restrict__ fl, uint32_t* __restrict__ fr,
-                                uint32_t* __restrict__ flag_o) {
+// Owned slots [ob, ob + on) are classified by their CURRENT cell column in ONE pass:
+//   keep / leaves-left / leaves-right (migration) and, for the kept ones, left / right boundary column (ghost source).
+// flag_o (indexed by the old original index) marks the particles that stay, so its exclusive scan is their new
+// original index.  counts[0..5] = #keep, #left, #right, #col-left, #col-right, #particles that jumped > 1 column.
+__global__ void k_slab_classify(const float4* __restrict__ pos, const uint32_t* __restrict__ orig, uint32_t ob, uint32_t on, int lo, int hi, int has_left,
+                                int has_right, uint32_t* __restrict__ fk, uint32_t* __restrict__ fl, uint32_t* __restrict__ fr, uint32_t* __restrict__ fcl,
+                                uint32_t* __restrict__ fcr, uint32_t* __restrict__ flag_o, uint32_t* __restrict__ counts) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= on) return;
-    uint32_t s = ob + t;
-    int cx = cell_coord(pos[s].x);
-    bool left = has_left && cx < lo, right = has_right && cx >= hi;
-    bool keep = !left && !right;
-    fk[s] = keep;
-    fl[s] = left;
-    fr[s] = right;
-    flag_o[orig[s]] = keep;
+    uint32_t v[6] = {0, 0, 0, 0, 0, 0};
+    if (t < on) {
+        uint32_t s = ob + t;
+        int cx = cell_coord(pos[s].x);
+        bool left = has_left && cx < lo, right = has_right && cx >= hi;
+        bool keep = !left && !right;
+        v[0] = keep; v[1] = left; v[2] = right;
+        v[3] = keep && has_left && cx == lo;
+        v[4] = keep && has_right && cx == hi - 1;
+        v[5] = (left && cx < lo - 1) || (right && cx > hi);
+        fk[s] = v[0]; fl[s] = v[1]; fr[s] = v[2]; fcl[s] = v[3]; fcr[s] = v[4];
+        flag_o[orig[s]] = keep;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        uint32_t x = v[a];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&counts[a], x);
+    }
 }
-__global__ void k_slab_scatter(uint32_t n_slots, uint32_t ob, const uint32_t* __restrict__ fk, const uint32_t* __restrict__ fl, const uint32_t* __restrict__ fr,
-                               const uint32_t* __restrict__ sk, const uint32_t* __restrict__ sl, const uint32_t* __restrict__ sr,
-                               const uint32_t* __restrict__ scan_o, const float4* __restrict__ pos, const float4* __restrict__ vel,
-                               const float4* __restrict__ vc, const uint32_t* __restrict__ orig, const uint32_t* __restrict__ gid, float4* __restrict__ dpos,
-                               float4* __restrict__ dvel, float4* __restrict__ dvc, uint32_t* __restrict__ dorig, uint32_t* __restrict__ dgid,
-                               float4* __restrict__ lpos, float4* __restrict__ lvel, float4* __restrict__ lvc, uint32_t* __restrict__ lgid,
-                               float4* __restrict__ rpos, float4* __restrict__ rvel, float4* __restrict__ rvc, uint32_t* __restrict__ rgid) {
+struct SlabOut {  // destination arrays of k_slab_scatter
+    float4 *pos, *vel, *vc;
+    uint32_t* gid;
+};
+__global__ void k_slab_scatter(uint32_t n_slots, const uint32_t* __restrict__ fk, const uint32_t* __restrict__ fl, const uint32_t* __restrict__ fr,
+                               const uint32_t* __restrict__ fcl, const uint32_t* __restrict__ fcr, const uint32_t* __restrict__ sk,
+                               const uint32_t* __restrict__ sl, const uint32_t* __restrict__ sr, const uint32_t* __restrict__ scl,
+                               const uint32_t* __restrict__ scr, const uint32_t* __restrict__ scan_o, const float4* __restrict__ pos,
+                               const float4* __restrict__ vel, const float4* __restrict__ vc, const uint32_t* __restrict__ orig,
+                               const uint32_t* __restrict__ gid, SlabOut keep, uint32_t* __restrict__ keep_orig, SlabOut out_l, SlabOut out_r, SlabOut col_l,
+                               SlabOut col_r) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     if (fk[s]) {
+        float4 p = pos[s], v = vel[s], c = vc[s];
         uint32_t d = sk[s];
-        dpos[d] = pos[s]; dvel[d] = vel[s]; dvc[d] = vc[s];
-        dorig[d] = scan_o[orig[s]];
-        dgid[d] = gid[s];
+        keep.pos[d] = p; keep.vel[d] = v; keep.vc[d] = c;
+        keep.gid[d] = gid[s];
+        keep_orig[d] = scan_o[orig[s]];
+        if (fcl[s]) {
+            uint32_t e = scl[s];
+            col_l.pos[e] = p; col_l.vel[e] = v; col_l.vc[e] = c;
+        }
+        if (fcr[s]) {
+            uint32_t e = scr[s];
+            col_r.pos[e] = p; col_r.vel[e] = v; col_r.vc[e] = c;
+        }
     } else if (fl[s]) {
         uint32_t d = sl[s];
-        lpos[d] = pos[s]; lvel[d] = vel[s]; lvc[d] = vc[s]; lgid[d] = gid[s];
+        out_l.pos[d] = pos[s]; out_l.vel[d] = vel[s]; out_l.vc[d] = vc[s]; out_l.gid[d] = gid[s];
     } else if (fr[s]) {
         uint32_t d = sr[s];
-        rpos[d] = pos[s]; rvel[d] = vel[s]; rvc[d] = vc[s]; rgid[d] = gid[s];
+        out_r.pos[d] = pos[s]; out_r.vel[d] = vel[s]; out_r.vc[d] = vc[s]; out_r.gid[d] = gid[s];
     }
 }
-// boundary columns of the slab: cell column lo goes to the left neighbour, column hi - 1 to the right one
-__global__ void k_slab_column_flags(const float4* __restrict__ pos, uint32_t n, int lo, int hi, int has_left, int has_right, uint32_t* __restrict__ gl,
-                                    uint32_t* __restrict__ gr) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    int cx = cell_coord(pos[s].x);
-    gl[s] = has_left && cx == lo;
-    gr[s] = has_right && cx == hi - 1;
-}
-__global__ void k_slab_pack_columns(uint32_t n, const uint32_t* __restrict__ fl, const uint32_t* __restrict__ fr, const uint32_t* __restrict__ sl,
-                                    const uint32_t* __restrict__ sr, const float4* __restrict__ pos, const float4* __restrict__ vel,
-                                    const float4* __restrict__ vc, float4* __restrict__ lpos, float4* __restrict__ lvel, float4* __restrict__ lvc,
-                                    float4* __restrict__ rpos, float4* __restrict__ rvel, float4* __restrict__ rvc) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    if (fl[s]) {
-        uint32_t d = sl[s];
-        lpos[d] = pos[s]; lvel[d] = vel[s]; lvc[d] = vc[s];
-    }
-    if (fr[s]) {
-        uint32_t d = sr[s];
-        rpos[d] = pos[s]; rvel[d] = vel[s]; rvc[d] = vc[s];
+// counts[8..9] = {#emigrants left, #col-left}, counts[10..11] = {#emigrants right, #col-right}: the two 8-byte messages
+__global__ void k_slab_pack_counts(uint32_t* __restrict__ counts) {
+    if (threadIdx.x == 0) {
+        counts[8] = counts[1]; counts[9] = counts[3];
+        counts[10] = counts[2]; counts[11] = counts[4];
     }
 }
 __global__ void k_iota_from(uint32_t n, uint32_t start, uint32_t* __restrict__ a) {

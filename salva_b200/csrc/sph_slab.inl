@@ -71,10 +71,12 @@ void slab_release(sph_world* w) {
     SlabState& S = w->slab;
     if (S.comm && S.own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S.comm);
     S.comm = nullptr;
-    S.d_cnt.release(); S.flag.release(); S.flag2.release(); S.flag_o.release(); S.gid_l.release(); S.gid_r.release(); S.d_cnt64.release();
+    S.d_cnt.release(); S.flag.release(); S.flag_o.release(); S.gid_l.release(); S.gid_r.release(); S.d_cnt64.release();
     for (int a = 0; a < 3; ++a) {
         S.out_l[a].release();
         S.out_r[a].release();
+        S.col_l[a].release();
+        S.col_r[a].release();
     }
     S.active = false;
 }
@@ -82,28 +84,6 @@ void slab_release(sph_world* w) {
 inline bool slab_on(const sph_world* w) { return w->slab.active; }
 inline int slab_left(const sph_world* w) { return w->slab.rank > 0 ? w->slab.rank - 1 : -1; }
 inline int slab_right(const sph_world* w) { return w->slab.rank + 1 < w->slab.nranks ? w->slab.rank + 1 : -1; }
-
-// Exchange element counts with both neighbours: out[0] = what the left rank sends me, out[1] = from the right.
-sph_status slab_exchange_counts(sph_world* w, uint32_t to_left, uint32_t to_right, uint32_t* from_left, uint32_t* from_right) {
-    SlabState& S = w->slab;
-    uint32_t h[4] = {to_left, to_right, 0, 0};
-    CU(cudaMemcpyAsync(S.d_cnt.p, h, sizeof h, cudaMemcpyHostToDevice, w->st));
-    NC(g_nccl.GroupStart());
-    if (slab_left(w) >= 0) {
-        NC(g_nccl.Send(S.d_cnt.p + 0, 4, NCCL_CHAR, slab_left(w), S.comm, w->st));
-        NC(g_nccl.Recv(S.d_cnt.p + 2, 4, NCCL_CHAR, slab_left(w), S.comm, w->st));
-    }
-    if (slab_right(w) >= 0) {
-        NC(g_nccl.Send(S.d_cnt.p + 1, 4, NCCL_CHAR, slab_right(w), S.comm, w->st));
-        NC(g_nccl.Recv(S.d_cnt.p + 3, 4, NCCL_CHAR, slab_right(w), S.comm, w->st));
-    }
-    NC(g_nccl.GroupEnd());
-    CU(cudaMemcpyAsync(h, S.d_cnt.p, sizeof h, cudaMemcpyDeviceToHost, w->st));
-    CU(cudaStreamSynchronize(w->st));
-    *from_left = slab_left(w) >= 0 ? h[2] : 0;
-    *from_right = slab_right(w) >= 0 ? h[3] : 0;
-    return SPH_OK;
-}
 
 // Per-iteration ghost refresh of one per-particle array (elem = bytes per particle): my boundary columns go to the
 // neighbours, their boundary columns land in my ghost ranges.  Contiguous ranges, no packing.
@@ -132,194 +112,169 @@ sph_status slab_allreduce(sph_world* w, float* buf, size_t n) {
     return SPH_OK;
 }
 
-// Step prologue in slab mode:
-//   1. drop last step's ghosts and hand particles that left [lo, hi) to the neighbour that now owns them (migration),
-//   2. send the new boundary columns (pos, vel, vc) to the neighbours and append theirs as ghosts.
-// On exit the arrays hold [owned (N) | ghosts] in arbitrary order; the counting sort follows.
+// Step prologue in slab mode — one classification pass, one count exchange, ONE host sync, one data exchange:
+//   * particles that left [lo, hi) migrate to the neighbour that now owns them (CFL: at most one cell column per step);
+//   * the kept particles of my boundary columns go to the neighbours as their ghosts;
+//   * my own emigrants stay here as ghosts (they now sit in the neighbour's boundary column), appended AFTER the
+//     neighbour's column so that both sides see that column in the same order: [neighbour's kept | my emigrants].
+// On exit the arrays hold [kept | immigrants left | immigrants right | left ghosts | right ghosts]; the counting sort
+// follows and leaves [left ghosts | owned | right ghosts] with the boundary columns at the ends of the owned range.
 sph_status slab_begin_step(sph_world* w) {
     SlabState& S = w->slab;
     if (w->fluids.size() != 1) return w->fail(SPH_ERR_INVALID, "slab decomposition supports one fluid per world");
     if (w->desc.solver != SPH_SOLVER_DFSPH || w->tile) return w->fail(SPH_ERR_INVALID, "slab decomposition supports DFSPH with gather_backend 0");
     for (auto& fr : w->fluids[0].forces)
         if (fr.d.kind == SPH_FORCE_BECKER2009_ELASTICITY) return w->fail(SPH_ERR_INVALID, "Becker2009 elasticity is not slab-decomposed");
-    const uint32_t n_slots = (uint32_t)w->Ntot;  // layout of the previous step: owned range + ghosts (or owned only)
+    const uint32_t n_slots = (uint32_t)w->Ntot;  // layout of the previous step: [ghosts | owned | ghosts] (or owned only)
     const uint32_t ob = w->own_begin, on = (uint32_t)w->N;
     int c = w->cur;
-    // ---- 1. classify the owned particles by their CURRENT cell column -------------------------------------------
-    CU(S.flag.ensure(3 * (size_t)n_slots + 8));
+    const int L = slab_left(w), R = slab_right(w);
+    // ---- classify + count ---------------------------------------------------------------------------------------------
+    CU(S.flag.ensure(10 * (size_t)n_slots + 16));
     CU(S.flag_o.ensure((size_t)on + 8));
-    uint32_t* fk = S.flag.p;                // keep
-    uint32_t* fl = S.flag.p + n_slots;      // leaves to the left
-    uint32_t* fr = S.flag.p + 2 * (size_t)n_slots;  // leaves to the right
-    CU(cudaMemsetAsync(S.flag.p, 0, 3 * (size_t)n_slots * sizeof(uint32_t), w->st));
-    LAUNCH(k_slab_classify, on, 256, w->pos[c].p, w->orig[c].p, ob, on, n_slots, S.lo, S.hi, S.has_left, S.has_right, fk, fl, fr, S.flag_o.p);
-    // counts = last flag + last scan value; scans in place (exclusive)
-    TRY(scan_exclusive(w, S.flag_o.p, on));   // new original index of kept particles (stable in old original order)
-    uint32_t tail[6];
-    // read the last flags before scanning
-    if (n_slots) {
-        CU(cudaMemcpyAsync(&tail[0], fk + n_slots - 1, 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaMemcpyAsync(&tail[1], fl + n_slots - 1, 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaMemcpyAsync(&tail[2], fr + n_slots - 1, 4, cudaMemcpyDeviceToHost, w->st));
+    CU(S.d_cnt.ensure(32));
+    uint32_t* f[5];   // keep, left, right, col-left, col-right flags
+    uint32_t* sc[5];  // their exclusive scans
+    for (int a = 0; a < 5; ++a) {
+        f[a] = S.flag.p + (size_t)a * n_slots;
+        sc[a] = S.flag.p + (size_t)(5 + a) * n_slots;
     }
-    // keep an unscanned copy of the flags for the scatter
-    CU(S.flag2.ensure(3 * (size_t)n_slots + 8));
-    CU(cudaMemcpyAsync(S.flag2.p, S.flag.p, 3 * (size_t)n_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->st));
-    TRY(scan_exclusive(w, fk, n_slots));
-    TRY(scan_exclusive(w, fl, n_slots));
-    TRY(scan_exclusive(w, fr, n_slots));
-    uint32_t nk = 0, nl = 0, nr = 0;
-    if (n_slots) {
-        CU(cudaMemcpyAsync(&tail[3], fk + n_slots - 1, 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaMemcpyAsync(&tail[4], fl + n_slots - 1, 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaMemcpyAsync(&tail[5], fr + n_slots - 1, 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaStreamSynchronize(w->st));
-        nk = tail[0] + tail[3];
-        nl = tail[1] + tail[4];
-        nr = tail[2] + tail[5];
+    CU(cudaMemsetAsync(S.flag.p, 0, 5 * (size_t)n_slots * sizeof(uint32_t), w->st));
+    CU(cudaMemsetAsync(S.d_cnt.p, 0, 32 * sizeof(uint32_t), w->st));
+    LAUNCH(k_slab_classify, on, 256, w->pos[c].p, w->orig[c].p, ob, on, S.lo, S.hi, S.has_left, S.has_right, f[0], f[1], f[2], f[3], f[4], S.flag_o.p,
+           S.d_cnt.p);
+    // counts go to the neighbours straight from the device: [#emigrants to you, #particles of my column facing you]
+    LAUNCH(k_slab_pack_counts, 1, 32, S.d_cnt.p);  // d_cnt[8..9] = {nl, ncl}, d_cnt[10..11] = {nr, ncr}
+    NC(g_nccl.GroupStart());
+    if (L >= 0) {
+        NC(g_nccl.Send(S.d_cnt.p + 8, 8, NCCL_CHAR, L, S.comm, w->st));
+        NC(g_nccl.Recv(S.d_cnt.p + 12, 8, NCCL_CHAR, L, S.comm, w->st));
     }
-    uint32_t im_l = 0, im_r = 0;
-    TRY(slab_exchange_counts(w, nl, nr, &im_l, &im_r));
+    if (R >= 0) {
+        NC(g_nccl.Send(S.d_cnt.p + 10, 8, NCCL_CHAR, R, S.comm, w->st));
+        NC(g_nccl.Recv(S.d_cnt.p + 14, 8, NCCL_CHAR, R, S.comm, w->st));
+    }
+    NC(g_nccl.GroupEnd());
+    uint32_t hc[16];
+    CU(cudaMemcpyAsync(hc, S.d_cnt.p, sizeof hc, cudaMemcpyDeviceToHost, w->st));
+    CU(cudaMemcpyAsync(sc[0], f[0], 5 * (size_t)n_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->st));
+    for (int a = 0; a < 5; ++a) TRY(scan_exclusive(w, sc[a], n_slots));
+    TRY(scan_exclusive(w, S.flag_o.p, on));  // new original index of the kept particles (stable in the old order)
+    CU(cudaStreamSynchronize(w->st));        // the only host sync of the prologue
+    const uint32_t nk = hc[0], nl = hc[1], nr = hc[2], ncl = hc[3], ncr = hc[4];
+    if (hc[5]) return w->fail(SPH_ERR_INVALID, "%u particles crossed more than one cell column in a step (CFL violated)", hc[5]);
+    const uint32_t im_l = L >= 0 ? hc[12] : 0, gcol_l = L >= 0 ? hc[13] : 0;  // from the left rank: its emigrants to me, its column
+    const uint32_t im_r = R >= 0 ? hc[14] : 0, gcol_r = R >= 0 ? hc[15] : 0;
     const uint32_t n_new = nk + im_l + im_r;
-    // ---- migrate: kept particles compact into the other buffer, emigrants into send buffers -----------------------
+    const uint32_t ghl = gcol_l + nl, ghr = gcol_r + nr;
+    // ---- buffers ------------------------------------------------------------------------------------------------------------
     for (int a = 0; a < 3; ++a) {
         CU(S.out_l[a].ensure(std::max<uint32_t>(nl, 1)));
         CU(S.out_r[a].ensure(std::max<uint32_t>(nr, 1)));
+        CU(S.col_l[a].ensure(std::max<uint32_t>(ncl, 1)));
+        CU(S.col_r[a].ensure(std::max<uint32_t>(ncr, 1)));
     }
     CU(S.gid_l.ensure(std::max<uint32_t>(nl, 1)));
     CU(S.gid_r.ensure(std::max<uint32_t>(nr, 1)));
-    w->Ntot = n_new;  // sizes the destination buffers (ghost room is added below)
     w->N = n_new;
+    w->Ntot = (size_t)n_new + ghl + ghr;
     w->fluids[0].n = n_new;
     w->fluids[0].pending_delete.assign(n_new, 0);
     recompute_offsets(w);
-    {   // make sure the destination (c^1) buffers can hold kept + immigrants (+ ghosts appended later grow again)
-        size_t need = n_new;
-        CU(w->pos[c ^ 1].ensure(need));
-        CU(w->vel[c ^ 1].ensure(need));
-        CU(w->vc[c ^ 1].ensure(need));
-        CU(w->orig[c ^ 1].ensure(need));
-        CU(w->gid[c ^ 1].ensure(need));
-    }
-    LAUNCH(k_slab_scatter, n_slots, 256, n_slots, ob, S.flag2.p, S.flag2.p + n_slots, S.flag2.p + 2 * (size_t)n_slots, fk, fl, fr, S.flag_o.p, w->pos[c].p,
-           w->vel[c].p, w->vc[c].p, w->orig[c].p, w->gid[c].p, w->pos[c ^ 1].p, w->vel[c ^ 1].p, w->vc[c ^ 1].p, w->orig[c ^ 1].p, w->gid[c ^ 1].p,
-           S.out_l[0].p, S.out_l[1].p, S.out_l[2].p, S.gid_l.p, S.out_r[0].p, S.out_r[1].p, S.out_r[2].p, S.gid_r.p);
-    c ^= 1;
-    w->cur = c;
+    w->cur = c ^ 1;          // the compacted state is built in the other buffer ...
+    w->protect_buf = c;      // ... while the old one is still being read by the scatter
+    TRY(ensure_fluid_buffers(w));
+    const int d = c ^ 1;
+    SlabOut keep{w->pos[d].p, w->vel[d].p, w->vc[d].p, w->gid[d].p};
+    SlabOut ol{S.out_l[0].p, S.out_l[1].p, S.out_l[2].p, S.gid_l.p}, orr{S.out_r[0].p, S.out_r[1].p, S.out_r[2].p, S.gid_r.p};
+    SlabOut cl{S.col_l[0].p, S.col_l[1].p, S.col_l[2].p, nullptr}, cr{S.col_r[0].p, S.col_r[1].p, S.col_r[2].p, nullptr};
+    LAUNCH(k_slab_scatter, n_slots, 256, n_slots, f[0], f[1], f[2], f[3], f[4], sc[0], sc[1], sc[2], sc[3], sc[4], S.flag_o.p, w->pos[c].p, w->vel[c].p,
+           w->vc[c].p, w->orig[c].p, w->gid[c].p, keep, w->orig[d].p, ol, orr, cl, cr);
+    // ---- one data exchange: emigrants + boundary columns out, immigrants + ghost columns in --------------------------------
+    float4* dst4[3] = {w->pos[d].p, w->vel[d].p, w->vc[d].p};
+    const uint32_t g0 = n_new, g1 = n_new + ghl;  // first left / right ghost slot
     NC(g_nccl.GroupStart());
-    float4* dst4[3] = {w->pos[c].p, w->vel[c].p, w->vc[c].p};
-    if (slab_left(w) >= 0) {
+    if (L >= 0) {
         for (int a = 0; a < 3; ++a) {
-            if (nl) NC(g_nccl.Send(S.out_l[a].p, (size_t)nl * 16, NCCL_CHAR, slab_left(w), S.comm, w->st));
-            if (im_l) NC(g_nccl.Recv(dst4[a] + nk, (size_t)im_l * 16, NCCL_CHAR, slab_left(w), S.comm, w->st));
+            if (nl) NC(g_nccl.Send(S.out_l[a].p, (size_t)nl * 16, NCCL_CHAR, L, S.comm, w->st));
+            if (ncl) NC(g_nccl.Send(S.col_l[a].p, (size_t)ncl * 16, NCCL_CHAR, L, S.comm, w->st));
+            if (im_l) NC(g_nccl.Recv(dst4[a] + nk, (size_t)im_l * 16, NCCL_CHAR, L, S.comm, w->st));
+            if (gcol_l) NC(g_nccl.Recv(dst4[a] + g0, (size_t)gcol_l * 16, NCCL_CHAR, L, S.comm, w->st));
         }
-        if (nl) NC(g_nccl.Send(S.gid_l.p, (size_t)nl * 4, NCCL_CHAR, slab_left(w), S.comm, w->st));
-        if (im_l) NC(g_nccl.Recv(w->gid[c].p + nk, (size_t)im_l * 4, NCCL_CHAR, slab_left(w), S.comm, w->st));
+        if (nl) NC(g_nccl.Send(S.gid_l.p, (size_t)nl * 4, NCCL_CHAR, L, S.comm, w->st));
+        if (im_l) NC(g_nccl.Recv(w->gid[d].p + nk, (size_t)im_l * 4, NCCL_CHAR, L, S.comm, w->st));
     }
-    if (slab_right(w) >= 0) {
+    if (R >= 0) {
         for (int a = 0; a < 3; ++a) {
-            if (nr) NC(g_nccl.Send(S.out_r[a].p, (size_t)nr * 16, NCCL_CHAR, slab_right(w), S.comm, w->st));
-            if (im_r) NC(g_nccl.Recv(dst4[a] + nk + im_l, (size_t)im_r * 16, NCCL_CHAR, slab_right(w), S.comm, w->st));
+            if (nr) NC(g_nccl.Send(S.out_r[a].p, (size_t)nr * 16, NCCL_CHAR, R, S.comm, w->st));
+            if (ncr) NC(g_nccl.Send(S.col_r[a].p, (size_t)ncr * 16, NCCL_CHAR, R, S.comm, w->st));
+            if (im_r) NC(g_nccl.Recv(dst4[a] + nk + im_l, (size_t)im_r * 16, NCCL_CHAR, R, S.comm, w->st));
+            if (gcol_r) NC(g_nccl.Recv(dst4[a] + g1, (size_t)gcol_r * 16, NCCL_CHAR, R, S.comm, w->st));
         }
-        if (nr) NC(g_nccl.Send(S.gid_r.p, (size_t)nr * 4, NCCL_CHAR, slab_right(w), S.comm, w->st));
-        if (im_r) NC(g_nccl.Recv(w->gid[c].p + nk + im_l, (size_t)im_r * 4, NCCL_CHAR, slab_right(w), S.comm, w->st));
+        if (nr) NC(g_nccl.Send(S.gid_r.p, (size_t)nr * 4, NCCL_CHAR, R, S.comm, w->st));
+        if (im_r) NC(g_nccl.Recv(w->gid[d].p + nk + im_l, (size_t)im_r * 4, NCCL_CHAR, R, S.comm, w->st));
     }
     NC(g_nccl.GroupEnd());
-    if (im_l + im_r) LAUNCH(k_iota_from, im_l + im_r, 256, im_l + im_r, nk, w->orig[c].p + nk);
+    // my own emigrants are my ghosts now (after the neighbour's column, see the header comment)
+    for (int a = 0; a < 3; ++a) {
+        if (nl) CU(cudaMemcpyAsync(dst4[a] + g0 + gcol_l, S.out_l[a].p, (size_t)nl * 16, cudaMemcpyDeviceToDevice, w->st));
+        if (nr) CU(cudaMemcpyAsync(dst4[a] + g1 + gcol_r, S.out_r[a].p, (size_t)nr * 16, cudaMemcpyDeviceToDevice, w->st));
+    }
+    if (im_l + im_r) LAUNCH(k_iota_from, im_l + im_r, 256, im_l + im_r, nk, w->orig[d].p + nk);
+    if (ghl + ghr) {  // ghosts carry no original index / id
+        CU(cudaMemsetAsync(w->orig[d].p + n_new, 0xFF, (size_t)(ghl + ghr) * 4, w->st));
+        CU(cudaMemsetAsync(w->gid[d].p + n_new, 0xFF, (size_t)(ghl + ghr) * 4, w->st));
+    }
     S.migrated_out = nl + nr;
     S.migrated_in = im_l + im_r;
-    // ---- 2. boundary columns -> neighbours' ghosts ------------------------------------------------------------------
-    CU(S.flag.ensure(2 * (size_t)n_new + 8));
-    uint32_t* gl = S.flag.p;
-    uint32_t* gr = S.flag.p + n_new;
-    CU(cudaMemsetAsync(S.flag.p, 0, 2 * (size_t)n_new * sizeof(uint32_t), w->st));
-    LAUNCH(k_slab_column_flags, n_new, 256, w->pos[c].p, n_new, S.lo, S.hi, S.has_left, S.has_right, gl, gr);
-    uint32_t t2[4] = {0, 0, 0, 0};
-    if (n_new) {
-        CU(cudaMemcpyAsync(&t2[0], gl + n_new - 1, 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaMemcpyAsync(&t2[1], gr + n_new - 1, 4, cudaMemcpyDeviceToHost, w->st));
-        CU(S.flag2.ensure(2 * (size_t)n_new + 8));
-        CU(cudaMemcpyAsync(S.flag2.p, S.flag.p, 2 * (size_t)n_new * sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->st));
-        TRY(scan_exclusive(w, gl, n_new));
-        TRY(scan_exclusive(w, gr, n_new));
-        CU(cudaMemcpyAsync(&t2[2], gl + n_new - 1, 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaMemcpyAsync(&t2[3], gr + n_new - 1, 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaStreamSynchronize(w->st));
-    }
-    uint32_t sl = t2[0] + t2[2], sr = t2[1] + t2[3];
-    uint32_t ghl = 0, ghr = 0;
-    TRY(slab_exchange_counts(w, sl, sr, &ghl, &ghr));
-    for (int a = 0; a < 3; ++a) {
-        CU(S.out_l[a].ensure(std::max<uint32_t>(sl, 1)));
-        CU(S.out_r[a].ensure(std::max<uint32_t>(sr, 1)));
-    }
-    if (n_new) LAUNCH(k_slab_pack_columns, n_new, 256, n_new, S.flag2.p, S.flag2.p + n_new, gl, gr, w->pos[c].p, w->vel[c].p, w->vc[c].p, S.out_l[0].p,
-                      S.out_l[1].p, S.out_l[2].p, S.out_r[0].p, S.out_r[1].p, S.out_r[2].p);
-    w->Ntot = (size_t)n_new + ghl + ghr;
-    TRY(ensure_fluid_buffers(w));  // grows (keeping contents) every per-particle array to Ntot
-    dst4[0] = w->pos[c].p; dst4[1] = w->vel[c].p; dst4[2] = w->vc[c].p;
-    NC(g_nccl.GroupStart());
-    if (slab_left(w) >= 0)
-        for (int a = 0; a < 3; ++a) {
-            if (sl) NC(g_nccl.Send(S.out_l[a].p, (size_t)sl * 16, NCCL_CHAR, slab_left(w), S.comm, w->st));
-            if (ghl) NC(g_nccl.Recv(dst4[a] + n_new, (size_t)ghl * 16, NCCL_CHAR, slab_left(w), S.comm, w->st));
-        }
-    if (slab_right(w) >= 0)
-        for (int a = 0; a < 3; ++a) {
-            if (sr) NC(g_nccl.Send(S.out_r[a].p, (size_t)sr * 16, NCCL_CHAR, slab_right(w), S.comm, w->st));
-            if (ghr) NC(g_nccl.Recv(dst4[a] + n_new + ghl, (size_t)ghr * 16, NCCL_CHAR, slab_right(w), S.comm, w->st));
-        }
-    NC(g_nccl.GroupEnd());
-    if (ghl + ghr) {  // ghosts carry no original index / id
-        CU(cudaMemsetAsync(w->orig[c].p + n_new, 0xFF, (size_t)(ghl + ghr) * 4, w->st));
-        CU(cudaMemsetAsync(w->gid[c].p + n_new, 0xFF, (size_t)(ghl + ghr) * 4, w->st));
-    }
-    S.exp_ghost_l = ghl;
-    S.exp_ghost_r = ghr;
-    S.exp_send_l = sl;
-    S.exp_send_r = sr;
-    // global particle count of the fluid (mean errors are global means)
-    {
+    // slot ranges after the sort follow from the counts alone (CFL: immigrants land in my boundary columns)
+    S.gl_count = ghl;
+    S.sl_begin = ghl;
+    S.sl_count = L >= 0 ? ncl + im_l : 0;
+    S.sr_count = R >= 0 ? ncr + im_r : 0;
+    S.sr_begin = ghl + n_new - S.sr_count;
+    S.gr_begin = ghl + n_new;
+    S.gr_count = ghr;
+    if (!S.global_valid) {  // particles are conserved by migration: the global count only changes through the host API
         unsigned long long cnt = n_new;
         CU(cudaMemcpyAsync(S.d_cnt64.p, &cnt, 8, cudaMemcpyHostToDevice, w->st));
         NC(g_nccl.AllReduce(S.d_cnt64.p, S.d_cnt64.p, 1, NCCL_UINT64, NCCL_SUM, S.comm, w->st));
         CU(cudaMemcpyAsync(&cnt, S.d_cnt64.p, 8, cudaMemcpyDeviceToHost, w->st));
         CU(cudaStreamSynchronize(w->st));
         S.global_n = cnt;
+        S.global_valid = true;
     }
-    w->own_begin = 0;
+    w->own_begin = 0;  // until the sort
+    w->protect_buf = -1;
+    TRY(ensure_fluid_buffers(w));  // now the old buffer may grow too (it is the sort's destination)
     return SPH_OK;
 }
 
-// After the sort: locate the owned range and the boundary / ghost column ranges in the sorted arrays.
+// After the sort the owned range starts behind the left ghosts.  With SALVA_B200_SLAB_CHECK=1 the ranges derived from
+// the exchanged counts are verified against the sorted cell table.
 sph_status slab_after_sort(sph_world* w) {
     SlabState& S = w->slab;
+    w->own_begin = S.gl_count;
+    static const bool check = getenv("SALVA_B200_SLAB_CHECK") && atoi(getenv("SALVA_B200_SLAB_CHECK")) != 0;
+    if (!check) return SPH_OK;
     const Consts& c = w->hc;
-    auto col_start_index = [&](long long cx) -> long long {  // index into cstart of the first cell of column cx (absolute)
+    auto col_start_index = [&](long long cx) -> long long {
         long long gx = cx - c.ox;
         if (gx <= 0) return 0;
         if (gx >= c.nx) return (long long)c.nx * c.ny * c.nz;
         return gx * (long long)c.ny * c.nz;
     };
+    const long long far = 1LL << 40;
     long long idx[4] = {S.has_left ? col_start_index(S.lo) : 0, S.has_left ? col_start_index((long long)S.lo + 1) : 0,
-                        S.has_right ? col_start_index((long long)S.hi - 1) : col_start_index(1LL << 40),
-                        S.has_right ? col_start_index(S.hi) : col_start_index(1LL << 40)};
+                        S.has_right ? col_start_index((long long)S.hi - 1) : col_start_index(far), S.has_right ? col_start_index(S.hi) : col_start_index(far)};
     uint32_t v[4];
     for (int a = 0; a < 4; ++a) CU(cudaMemcpyAsync(&v[a], w->cstart.p + idx[a], 4, cudaMemcpyDeviceToHost, w->st));
     CU(cudaStreamSynchronize(w->st));
     uint32_t ntot = (uint32_t)w->Ntot;
-    S.gl_count = S.has_left ? v[0] : 0;
-    S.sl_begin = v[0];
-    S.sl_count = S.has_left ? v[1] - v[0] : 0;
-    S.sr_begin = v[2];
-    S.sr_count = S.has_right ? v[3] - v[2] : 0;
-    S.gr_begin = S.has_right ? v[3] : ntot;
-    S.gr_count = ntot - S.gr_begin;
-    if (S.gl_count != S.exp_ghost_l || S.gr_count != S.exp_ghost_r || S.sl_count != S.exp_send_l || S.sr_count != S.exp_send_r)
-        return w->fail(SPH_ERR_NCCL, "slab layout mismatch after sort: ghosts %u/%u (expected %u/%u), columns %u/%u (expected %u/%u)", S.gl_count,
-                       S.gr_count, S.exp_ghost_l, S.exp_ghost_r, S.sl_count, S.sr_count, S.exp_send_l, S.exp_send_r);
-    w->own_begin = S.gl_count;
-    if (S.gr_begin - S.gl_count != (uint32_t)w->N) return w->fail(SPH_ERR_NCCL, "slab layout mismatch: owned range %u != %zu", S.gr_begin - S.gl_count, w->N);
+    uint32_t gl = S.has_left ? v[0] : 0, sl = S.has_left ? v[1] - v[0] : 0, sr = S.has_right ? v[3] - v[2] : 0, grb = S.has_right ? v[3] : ntot;
+    if (gl != S.gl_count || sl != S.sl_count || sr != S.sr_count || grb != S.gr_begin || (S.has_right && v[2] != S.sr_begin))
+        return w->fail(SPH_ERR_NCCL, "slab layout mismatch after sort: ghosts-left %u (expected %u), columns %u/%u (expected %u/%u), right ghosts at %u (expected %u)",
+                       gl, S.gl_count, sl, sr, S.sl_count, S.sr_count, grb, S.gr_begin);
     return SPH_OK;
 }
 
