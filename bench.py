@@ -50,7 +50,12 @@ class ClockSampler:
         self.proc = None
         self.lines = []
 
+    def mark(self):
+        """Samples taken from here on belong to the timed region."""
+        self.t_mark = len(self.lines)
+
     def start(self):
+        self.t_mark = 0
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -74,7 +79,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[self.t_mark:] if len(self.lines) - self.t_mark >= 2 else self.lines
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -225,13 +231,14 @@ def native_arm(args, rank, world_size):
     if args.force_iters:
         world.force_iterations(*args.force_iters)
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi needs ~0.2 s to emit its first sample: start it before the warm-up steps
     for _ in range(warm):
         world.step(sc["dt"], sc["gravity"])
 
     # ---- timed region: device-resident inputs, CUDA-event time of every step -------------------------
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     acc = {}
     launches = 0
@@ -294,7 +301,7 @@ def native_arm(args, rank, world_size):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.config)
+        traffic = (json.load(open(tp)).get(args.config) or {}).get("pair")
     roofline = {"bound": "hbm", "kernel": "k_predict_density + k_pressure_update (one DFSPH pressure iteration)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": it_bytes, "ms_per_launch_pair": it_ms,
