@@ -49,7 +49,7 @@ sph_status elasticity_init(sph_world* w, uint32_t fluid, ForceRec& fr) {
     LAUNCH(k_el_identity, n - keep, 256, (uint32_t)n, (uint32_t)keep, E.rot);
     CU(cudaMemsetAsync(E.stress, 0, 6 * n * sizeof(float), w->st));
     int c = w->cur;
-    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
     LAUNCH(k_el_to_orig, w->N, 256, w->pos[c].p, w->orig[c].p, (uint32_t)f.offset, (uint32_t)(f.offset + n), E.cur, E.slot_of);
     CU(cudaMemsetAsync(w->d_scal.p + 11, 0, sizeof(int), w->st));
     LAUNCH(k_el_capture_lists, n, 128, L, w->vel[c].p, w->orig[c].p, E.slot_of, (uint32_t)f.offset, (uint32_t)n, fluid, cap0, stride0, E.nbr0, E.cnt0,

@@ -81,6 +81,7 @@ struct FluidRec {
     std::vector<ForceRec> forces;
     std::vector<uint8_t> pending_delete;
     size_t n_pending = 0;
+    float uniform_mass = 0.f;  // common particle mass if all volumes are equal, else 0
 };
 struct BoundaryRec {
     size_t n = 0, offset = 0;
@@ -164,12 +165,23 @@ struct sph_world {
     DBuf<float> dens, alpha, kappa, divv, pred, bvol, bforce;
     DBuf<uint32_t> cid, rank, perm, cstart, bcid, brank, bperm, bstart, scan_aux[3];
     DBuf<uint32_t> nbr_f, nbr_b, cnt_f, cnt_b;
+    DBuf<float4> g_f;  // cached gradient scalars, one float4 per group of 4 contacts (same layout as nbr_f)
     // gather_backend 1 (sph_tile.cuh): 16-bit tile-local fluid contact indices
     DBuf<uint16_t> nbr16;
     uint32_t tile_slots = 2048;  // widest tile halo seen by the last neighbour build (local index space size)
     uint32_t n_tiles = 0;
     bool tile = false;
     // gather_backend 0: the second per-contact gather (v* / kappa) can go through the texture pipe
+    // uniform-mass packed gather records (sph_passes.cuh): pvx4 = (x,y,z,v*x), vyz2 = (v*y,v*z), pk4 = (x,y,z,kappa)
+    bool unimass = false;
+    int uni_eval_mode = 1, uni_upd_mode = 1;  // 1: position record through the texture pipe, 2: through the LSU pipe
+    DBuf<float4> pvx4, pk4;
+    DBuf<float2> vyz2;
+    cudaTextureObject_t tex_pvx = 0, tex_vyz = 0, tex_pk = 0;
+    const void* tex_pvx_ptr = nullptr;
+    const void* tex_vyz_ptr = nullptr;
+    const void* tex_pk_ptr = nullptr;
+    int use_gcache = 0;
     bool use_tex = false;
     cudaTextureObject_t tex_vs = 0, tex_kappa = 0;
     const void* tex_vs_ptr = nullptr;
@@ -269,11 +281,12 @@ void fill_static_consts(sph_world* w) {
     c.n_fluids = (int)w->fluids.size();
     c.n_bounds = (int)w->bounds.size();
     for (size_t f = 0; f < w->fluids.size(); ++f)
-        c.fluids[f] = {w->fluids[f].density0, w->fluids[f].memberships, w->fluids[f].filter, (uint32_t)w->fluids[f].n};
+        c.fluids[f] = {w->fluids[f].density0, w->fluids[f].memberships, w->fluids[f].filter, w->fluids[f].uniform_mass};
     for (size_t b = 0; b < w->bounds.size(); ++b) c.bounds[b] = {w->bounds[b].memberships, w->bounds[b].filter};
     c.stride = w->stride;
     c.cap_f = w->cap_f;
     c.cap_b = w->cap_b;
+    c.use_gcache = w->use_gcache;
 }
 
 // ---- exclusive scan over n u32 (in place) -------------------------------------------------------
@@ -358,6 +371,9 @@ sph_status ensure_fluid_buffers(sph_world* w) {
         if (w->desc.solver == SPH_SOLVER_IISPH) CU(w->press[k].ensure(N, keep, w->st));
     }
     CU(w->vs.ensure(N));
+    CU(w->pvx4.ensure(N));
+    CU(w->pk4.ensure(N));
+    CU(w->vyz2.ensure(N));
     CU(w->acc.ensure(N));
     CU(w->dbg_acc.ensure(N));
     CU(w->dens.ensure(N + 8));
@@ -372,7 +388,10 @@ sph_status ensure_fluid_buffers(sph_world* w) {
     CU(w->cnt_b.ensure(N));
     w->stride = (uint32_t)((N + 31) / 32 * 32);
     if (w->tile) CU(w->nbr16.ensure((size_t)w->cap_f * w->stride));
-    else CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
+    else {
+        CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
+        CU(w->g_f.ensure((size_t)(w->cap_f / 4) * w->stride));
+    }
     CU(w->nbr_b.ensure((size_t)w->cap_b * w->stride));
     uint32_t nblk = cdiv(std::max<size_t>(N, 1), PASS_T);
     CU(w->partial.ensure((size_t)nblk * std::max<size_t>(1, w->fluids.size())));
@@ -392,12 +411,16 @@ sph_status stage_up(sph_world* w) {
     if (N) {
         std::vector<float> mass(N);
         std::vector<uint32_t> fid(N);
-        for (size_t f = 0; f < w->fluids.size(); ++f)
+        for (size_t f = 0; f < w->fluids.size(); ++f) {
+            bool uniform = w->fluids[f].n > 0;
             for (size_t i = 0; i < w->fluids[f].n; ++i) {
                 size_t g = w->fluids[f].offset + i;
                 mass[g] = w->h_vol[g] * w->fluids[f].density0;  // fluid.rs:183-185
                 fid[g] = (uint32_t)f;
+                uniform = uniform && w->h_vol[g] == w->h_vol[w->fluids[f].offset];
             }
+            w->fluids[f].uniform_mass = uniform ? mass[w->fluids[f].offset] : 0.f;
+        }
         CU(w->o_a.ensure(3 * N));
         CU(w->o_b.ensure(3 * N));
         CU(w->o_c.ensure(3 * N));
@@ -424,6 +447,14 @@ sph_status stage_up(sph_world* w) {
     w->staged = false;
     w->lists_valid = false;
     w->slab.global_valid = false;
+    {
+        const char* t = getenv("SALVA_B200_UNIMASS");
+        bool allow = t ? atoi(t) != 0 : true;
+        // a slab world takes the fast path on every rank or on none: volumes default to uniform there, and an empty
+        // slab inherits the constant from its first immigrant only through the classic path -> keep it simple: require
+        // particles with uniform volumes on this rank, otherwise fall back (all ranks are built by the same host code).
+        w->unimass = allow && !w->tile && w->desc.solver == SPH_SOLVER_DFSPH && w->fluids.size() == 1 && w->fluids[0].uniform_mass > 0.f;
+    }
     return SPH_OK;
 }
 
@@ -565,7 +596,8 @@ sph_status phase_grid(sph_world* w) {
         }
         LAUNCH(k_gather, N, 256, (uint32_t)N, w->perm.p, g);
         w->cur = c ^ 1;
-        LAUNCH(k_make_vstar, N, 256, w->vel[w->cur].p, w->vc[w->cur].p, w->vs.p);
+        LAUNCH(k_make_vstar, N, 256, w->vel[w->cur].p, w->vc[w->cur].p, w->vs.p, w->pos[w->cur].p, w->unimass ? w->pvx4.p : nullptr,
+               w->unimass ? w->vyz2.p : nullptr);
     }
     // boundaries: same sort
     CU(cudaMemsetAsync(w->bstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));
@@ -696,7 +728,10 @@ sph_status phase_neighbors(sph_world* w) {
         }
         if (!grow) break;
         if (w->tile) CU(w->nbr16.ensure((size_t)w->cap_f * w->stride));
-        else CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
+        else {
+            CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
+            CU(w->g_f.ensure((size_t)(w->cap_f / 4) * w->stride));
+        }
         CU(w->nbr_b.ensure((size_t)w->cap_b * w->stride));
         fill_static_consts(w);
         TRY(upload_consts(w));
@@ -770,6 +805,17 @@ sph_status ensure_tex(sph_world* w, cudaTextureObject_t* tex, const void** cur, 
     return SPH_OK;
 }
 
+// ghost refresh of v* in whichever representation the evaluations gather
+sph_status refresh_vstar(sph_world* w) {
+    if (!w->slab.active) return SPH_OK;
+    if (w->unimass) {
+        TRY(slab_refresh(w, w->pvx4.p, sizeof(float4)));
+        TRY(slab_refresh(w, w->vyz2.p, sizeof(float2)));
+        return SPH_OK;
+    }
+    return slab_refresh(w, w->vs.p, sizeof(float4));
+}
+
 sph_status launch_density_alpha(sph_world* w) {
     size_t N = w->N;
     int c = w->cur, bc = w->bcur;
@@ -780,8 +826,8 @@ sph_status launch_density_alpha(sph_world* w) {
         TDISPATCH1(k_tile_density_alpha, multi, 16, cap, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->cstart.p, cap, L, w->dens.p, w->alpha.p,
                    w->d_scal.p + 7);
     } else {
-        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
-        DISPATCH1(k_density_alpha, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->alpha.p, w->d_scal.p + 7);
+        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
+        DISPATCH1(k_density_alpha, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->g_f.p, w->dens.p, w->alpha.p, w->d_scal.p + 7);
     }
     TRY(slab_refresh(w, w->dens.p, sizeof(float)));  // XSPH / artificial viscosity / Akinci gather rho_j of ghosts
     return SPH_OK;
@@ -823,8 +869,28 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk) {
         TDISPATCH2(k_tile_vel_divergence, multi, predict, 32, cap, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, w->cstart.p, cap, L,
                    w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
         *nblk = w->n_tiles;
+    } else if (w->unimass) {
+        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
+        TRY(ensure_tex(w, &w->tex_pvx, &w->tex_pvx_ptr, w->pvx4.p, w->pvx4.cap));
+        TRY(ensure_tex(w, &w->tex_vyz, &w->tex_vyz_ptr, w->vyz2.p, w->vyz2.cap));
+        float* out = predict ? w->pred.p : w->divv.p;
+        const bool ptex = w->uni_eval_mode == 1;
+        if (predict) {
+            if (ptex) LAUNCH((k_vel_divergence_u<true, true>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
+                             w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7);
+            else LAUNCH((k_vel_divergence_u<true, false>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
+                        w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7);
+        } else {
+            if (ptex) LAUNCH((k_vel_divergence_u<false, true>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
+                             w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7);
+            else LAUNCH((k_vel_divergence_u<false, false>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
+                        w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7);
+        }
+        *nblk = cdiv(N, PASS_T);
+        TRY(slab_refresh(w, w->pk4.p, sizeof(float4)));  // the following update gathers (x, kappa) of ghosts
+        return SPH_OK;
     } else {
-        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
         if (w->use_tex) TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
         BOOL3(k_vel_divergence, multi, predict, w->use_tex, N, PASS_T, w->pos[c].p, w->vs.p, w->tex_vs, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L,
               w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
@@ -847,8 +913,16 @@ sph_status launch_vel_update(sph_world* w, bool pressure) {
         else
             TDISPATCH3(k_tile_vel_update, multi, bf, false, 20, cap, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->cstart.p, cap, L, w->kappa.p, w->vc[c].p,
                        w->vs.p, w->bforce.p, w->inv_dt);
+    } else if (w->unimass) {
+        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
+        TRY(ensure_tex(w, &w->tex_pk, &w->tex_pk_ptr, w->pk4.p, w->pk4.cap));
+        const bool ptex = w->uni_upd_mode == 1;
+        BOOL3(k_vel_update_u, bf, pressure, ptex, N, PASS_T, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p,
+              w->vyz2.p, w->bforce.p, w->inv_dt);
+        TRY(refresh_vstar(w));
+        return SPH_OK;
     } else {
-        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
         // measured (profiles/r1_v1_*): the texture pipe helps the float4 v* gather (-12 %) but not the 4-byte kappa gather
         const bool tex = false;
         if (tex) TRY(ensure_tex(w, &w->tex_kappa, &w->tex_kappa_ptr, w->kappa.p, w->kappa.cap));
@@ -864,7 +938,7 @@ sph_status phase_forces(sph_world* w) {
     size_t N = w->N;
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1, bf = any_bforce(w);
-    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
     TileLists TL{w->nbr16.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
     for (size_t f = 0; f < w->fluids.size(); ++f)
         for (ForceRec& fr : w->fluids[f].forces) {
@@ -959,13 +1033,15 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     }
     CU(cudaEventRecord(w->ev[EV_DIV], w->st));
     // update_velocities :422-430, zero vc :689-691, acc += gravity :574-578
+    if (w->unimass) TRY(slab_refresh(w, w->vs.p, sizeof(float4)));  // ghosts' v* in vs form (the fold reads vel = v*)
     LAUNCH(k_fold_velocities, w->Ntot, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2]);  // ghosts too (vel = v*)
     CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
     TRY(phase_forces(w));
     CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
     timestep_advance(w, dt_total);  // :702
-    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p);
-    TRY(slab_refresh(w, w->vs.p, sizeof(float4)));
+    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p, w->unimass ? w->pvx4.p : nullptr,
+           w->unimass ? w->vyz2.p : nullptr);
+    TRY(refresh_vstar(w));
     CU(cudaEventRecord(w->ev[EV_INTEG], w->st));
     // pressure_solve :432-464
     w->stats.n_pressure_iter = w->stats.n_pressure_eval = 0;
@@ -1123,6 +1199,9 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     w->desc = *desc;
     w->h = desc->particle_radius * desc->smoothing_factor * 2.0f;  // liquid_world.rs:44
     w->tile = desc->gather_backend == 1 && desc->solver == SPH_SOLVER_DFSPH;  // the tile backend covers the DFSPH passes only
+    if (const char* t = getenv("SALVA_B200_GCACHE")) w->use_gcache = atoi(t);
+    if (const char* t = getenv("SALVA_B200_UNI_EVAL")) w->uni_eval_mode = atoi(t);
+    if (const char* t = getenv("SALVA_B200_UNI_UPD")) w->uni_upd_mode = atoi(t);
     {
         const char* t = getenv("SALVA_B200_TEX");
         w->use_tex = t ? atoi(t) != 0 : SALVA_B200_TEX_DEFAULT;
@@ -1156,13 +1235,16 @@ void sph_world_destroy(sph_world* w) {
     w->cid.release(); w->rank.release(); w->perm.release(); w->cstart.release(); w->bcid.release(); w->brank.release(); w->bperm.release();
     w->bstart.release();
     for (auto& a : w->scan_aux) a.release();
-    w->nbr_f.release(); w->nbr16.release(); w->nbr_b.release(); w->cnt_f.release(); w->cnt_b.release();
+    w->nbr_f.release(); w->g_f.release(); w->nbr16.release(); w->nbr_b.release(); w->cnt_f.release(); w->cnt_b.release();
     w->partial.release(); w->errsum.release(); w->d_scal.release(); w->d_cnt.release();
     w->o_a.release(); w->o_b.release(); w->o_c.release(); w->o_mass.release(); w->o_fid.release();
     iisph_release(w);
     slab_release(w);
     for (auto& f : w->fluids)
         for (auto& fr : f.forces) elasticity_release(fr);
+    for (cudaTextureObject_t t : {w->tex_pvx, w->tex_vyz, w->tex_pk})
+        if (t) cudaDestroyTextureObject(t);
+    w->pvx4.release(); w->pk4.release(); w->vyz2.release();
     if (w->tex_vs) cudaDestroyTextureObject(w->tex_vs);
     if (w->tex_kappa) cudaDestroyTextureObject(w->tex_kappa);
     for (auto& s : w->spans) {

@@ -44,13 +44,13 @@ sph_status iisph_step(sph_world* w, float dt_total, const float g[3]) {
     const bool multi = w->fluids.size() > 1, bf = any_bforce(w);
     TRY(iisph_ensure(w));
     IisphState& S = w->iisph;
-    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
+    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
     // predict_advection :653-660 (forces see the PREVIOUS step's dt / inv_dt), then timestep.advance :661
     LAUNCH(k_set_gravity, N, 256, w->vel[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2]);
     TRY(phase_forces(w));
     CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
     timestep_advance(w, dt_total);
-    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p);  // :662
+    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p, (float4*)nullptr, (float2*)nullptr);  // :662
     CU(cudaEventRecord(w->ev[EV_INTEG], w->st));
     DISPATCH1(k_iisph_dii, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, S.dii, w->dt);            // :665-671
     LAUNCH(k_iisph_warm_start, N, 256, w->press[c].p, w->dens.p, S.prho);                                                        // :673-677

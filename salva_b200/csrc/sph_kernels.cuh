@@ -25,7 +25,7 @@ constexpr float F32_EPS = 1.1920929e-07f;
 struct FluidParams {  // per fluid, in __constant__ memory
     float density0;
     uint32_t memberships, filter;
-    uint32_t count;
+    float mass;  // the particles' common mass when every particle of the fluid has the same volume, else 0
 };
 struct BoundaryParams {
     uint32_t memberships, filter;
@@ -42,6 +42,7 @@ struct Consts {
                                  // two ghost columns in a multi-GPU world (x-major order keeps ghosts at both ends)
     uint32_t stride;             // neighbour-list column stride (>= n_fluid, multiple of 32)
     uint32_t cap_f, cap_b;       // list capacities (rows)
+    int use_gcache;              // gradient passes read the cached g_ij (1) or recompute it from positions (0)
     int n_fluids, n_bounds;      // object counts
     FluidParams fluids[MAX_FLUIDS];
     BoundaryParams bounds[MAX_BOUNDARIES];
@@ -333,6 +334,7 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
                     }
                 }
             }
+        for (uint32_t t = nf; t < ((nf + 3u) & ~3u) && t < C.cap_f; ++t) nbr_f[((size_t)(t >> 2) * C.stride + i) * 4 + (t & 3)] = i;  // pad the last group
         cnt_f[i] = nf;
         cnt_b[i] = nb;
     }
@@ -404,11 +406,18 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, uint32_t nb
 constexpr int PASS_T = 128;  // threads per block of the gather passes
 
 // v* = vel + vc after the reorder (the divergence solve works on vel + vc carried over from the previous step, Appendix A.3.2)
-__global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __restrict__ vc, float4* __restrict__ vs) {
+__global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __restrict__ vc, float4* __restrict__ vs, const float4* __restrict__ pos,
+                             float4* __restrict__ pvx, float2* __restrict__ vyz) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C.n_fluid) return;
     float4 v = vel[i], c = vc[i];
-    vs[i] = make_float4(v.x + c.x, v.y + c.y, v.z + c.z, 0.f);
+    float sx = v.x + c.x, sy = v.y + c.y, sz = v.z + c.z;
+    vs[i] = make_float4(sx, sy, sz, 0.f);
+    if (pvx) {  // uniform-mass packed records (sph_passes.cuh)
+        float4 p = pos[i];
+        pvx[i] = make_float4(p.x, p.y, p.z, sx);
+        vyz[i] = make_float2(sy, sz);
+    }
 }
 
 // a10: update_velocities dfsph_solver.rs:422-430 + zero vc :689-691 + acc = gravity (predict_advection :574-578).
@@ -433,13 +442,18 @@ __global__ void k_set_gravity(const float4* __restrict__ vel, float4* __restrict
 
 // a18: integrate_and_clear_accelerations dfsph_solver.rs:505-518 (+ v* = vel + vc)
 __global__ void k_integrate_acc(const float4* __restrict__ vel, float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ acc, float dt,
-                                float4* __restrict__ dbg_acc) {
+                                float4* __restrict__ dbg_acc, float4* __restrict__ pvx, float2* __restrict__ vyz) {
     SPH_OWNED_INDEX(i)
     float4 a = acc[i], c = vc[i], v = vel[i];
     if (dbg_acc) dbg_acc[i] = a;
     c.x += a.x * dt; c.y += a.y * dt; c.z += a.z * dt;
     vc[i] = c;
-    vs[i] = make_float4(v.x + c.x, v.y + c.y, v.z + c.z, 0.f);
+    float sx = v.x + c.x, sy = v.y + c.y, sz = v.z + c.z;
+    vs[i] = make_float4(sx, sy, sz, 0.f);
+    if (pvx) {
+        pvx[i].w = sx;  // xyz already hold the position
+        vyz[i] = make_float2(sy, sz);
+    }
     acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 

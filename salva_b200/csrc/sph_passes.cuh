@@ -12,17 +12,21 @@
 namespace sphk {
 
 struct Lists {
-    const uint4* nbr_f;     // nbr_f[(k / 4) * stride + i] = contacts 4*(k/4) .. 4*(k/4)+3 of particle i (sorted indices)
+    const uint4* nbr_f;     // nbr_f[(k / 4) * stride + i] = contacts 4*(k/4) .. 4*(k/4)+3 of particle i (sorted indices);
+                            // tail slots of the last group hold i itself (a self contact has zero gradient)
     const uint32_t* nbr_b;  // nbr_b[k * stride + i]
     const uint32_t* cnt_f;
     const uint32_t* cnt_b;
+    const float4* g_f;      // g_f[(k / 4) * stride + i]: cached gradient scalars g_ij = W'(|x_ij|) / |x_ij| of the same 4 contacts
+                            // (contact.gradient = g * x_ij, helper.rs:24-25); written by k_density_alpha once per step, 0 in tail slots
 };
 
 struct NoAux {};
 
-// ld(j) -> Aux loads whatever else the pass needs from neighbour j; ff(j, pair, pos_j, aux) consumes one contact.
-template <bool W, bool G, class LD, class FF>
-__device__ __forceinline__ void for_fluid_contacts(uint32_t i, const float4& pi, const Lists& L, const float4* __restrict__ pos, LD ld, FF ff) {
+// ldpos(j) -> float4 whose xyz is the neighbour position (w = whatever the array packs there); ld(j) -> Aux loads
+// whatever else the pass needs from neighbour j; ff(j, pair, posrec_j, aux) consumes one contact.
+template <bool W, bool G, class LP, class LD, class FF>
+__device__ __forceinline__ void for_fluid_contacts_g(uint32_t i, const float4& pi, const Lists& L, LP ldpos, LD ld, FF ff) {
     const uint32_t n = min(L.cnt_f[i], C.cap_f);
     const uint32_t nq = (n + 3u) >> 2;
     const uint4* col = L.nbr_f + i;
@@ -40,7 +44,7 @@ __device__ __forceinline__ void for_fluid_contacts(uint32_t i, const float4& pi,
         }
         float4 pj[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) pj[u] = __ldg(&pos[j[u]]);
+        for (int u = 0; u < 4; ++u) pj[u] = ldpos(j[u]);
         decltype(ld(0u)) aux[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) aux[u] = ld(j[u]);
@@ -53,6 +57,88 @@ __device__ __forceinline__ void for_fluid_contacts(uint32_t i, const float4& pi,
         }
         J = Jn;
     }
+}
+// Gradient-only passes, software pipelined: the gathers of group q+1 are issued BEFORE group q is evaluated and the
+// list indices are fetched two groups ahead, so a thread keeps 8-16 independent loads in flight while it computes
+// (ncu: these passes are latency-bound — issue slots ~63 % busy, long-scoreboard stalls dominate).
+// C.use_gcache selects where the gradient scalar g_ij = W'(|x_ij|)/|x_ij| comes from: the per-step cache written by
+// k_density_alpha (fewer instructions, +4 B/contact of traffic) or recomputed from the positions.
+// No tail masking: padded slots are (j = i, g = 0) and a self contact has zero gradient either way.
+template <bool NEED_D2, class LP, class LD, class FF>
+__device__ __forceinline__ void for_fluid_grads(uint32_t i, const float4& pi, const Lists& L, LP ldpos, LD ld, FF ff) {
+    const uint32_t n = min(L.cnt_f[i], C.cap_f);
+    const uint32_t nq = (n + 3u) >> 2;
+    if (nq == 0) return;
+    const bool cached = C.use_gcache != 0;
+    const uint4* col = L.nbr_f + i;
+    const float4* gcol = L.g_f + i;
+    typedef decltype(ld(0u)) Aux;
+    // stage 0: indices of groups 0 and 1, gathers of group 0
+    uint4 J0 = __ldg(col);
+    uint4 J1 = nq > 1 ? __ldg(col + (size_t)C.stride) : J0;
+    float4 G0 = cached ? __ldg(gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 P0[4];
+    Aux A0[4];
+    {
+        const uint32_t j[4] = {J0.x, J0.y, J0.z, J0.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) P0[u] = ldpos(j[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) A0[u] = ld(j[u]);
+    }
+    for (uint32_t q = 0; q < nq; ++q) {
+        // issue the next group's loads first
+        uint4 J2 = J1;
+        float4 G1 = G0;
+        float4 P1[4];
+        Aux A1[4];
+        const bool more = q + 1 < nq;
+        if (more) {
+            if (q + 2 < nq) J2 = __ldg(col + (size_t)(q + 2) * C.stride);
+            if (cached) G1 = __ldg(gcol + (size_t)(q + 1) * C.stride);
+            const uint32_t j[4] = {J1.x, J1.y, J1.z, J1.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) P1[u] = ldpos(j[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) A1[u] = ld(j[u]);
+        }
+        // evaluate the current group
+        const uint32_t j0[4] = {J0.x, J0.y, J0.z, J0.w};
+        const float g0[4] = {G0.x, G0.y, G0.z, G0.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            Pair p;
+            if (cached) {
+                p.dx = pi.x - P0[u].x;
+                p.dy = pi.y - P0[u].y;
+                p.dz = pi.z - P0[u].z;
+                p.g = g0[u];
+                if (NEED_D2) p.d2 = fmaf(p.dz, p.dz, fmaf(p.dy, p.dy, p.dx * p.dx));
+            } else {
+                p = make_pair<false, true>(pi, P0[u]);
+            }
+            ff(j0[u], p, P0[u], A0[u]);
+        }
+        if (more) {
+            J0 = J1;
+            J1 = J2;
+            G0 = G1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                P0[u] = P1[u];
+                A0[u] = A1[u];
+            }
+        }
+    }
+}
+template <bool NEED_D2, class LD, class FF>
+__device__ __forceinline__ void for_fluid_grads_pos(uint32_t i, const float4& pi, const Lists& L, const float4* __restrict__ pos, LD ld, FF ff) {
+    for_fluid_grads<NEED_D2>(i, pi, L, [&](uint32_t j) { return __ldg(&pos[j]); }, ld, ff);
+}
+
+template <bool W, bool G, class LD, class FF>
+__device__ __forceinline__ void for_fluid_contacts(uint32_t i, const float4& pi, const Lists& L, const float4* __restrict__ pos, LD ld, FF ff) {
+    for_fluid_contacts_g<W, G>(i, pi, L, [&](uint32_t j) { return __ldg(&pos[j]); }, ld, ff);
 }
 template <bool W, bool G, class FB>
 __device__ __forceinline__ void for_boundary_contacts(uint32_t i, const float4& pi, const Lists& L, const float4* __restrict__ bpos, FB fb) {
@@ -97,21 +183,42 @@ __device__ __forceinline__ void reduce_error(float e, uint32_t fi, bool valid, f
 // ------------------------------------------------------------------------------------------------
 template <bool MULTI>
 __global__ void __launch_bounds__(PASS_T)
-k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
+k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, float4* __restrict__ g_out,
                 float* __restrict__ dens, float* __restrict__ alpha, int* __restrict__ err) {
     SPH_OWNED_INDEX(i)
     float4 pi = pos[i];
     float rho0 = C.fluids[MULTI ? fid_of(vel[i]) : 0].density0;
     float rho = 0.f, sq = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-    for_fluid_contacts<true, true>(
-        i, pi, L, pos, [](uint32_t) { return NoAux{}; },
-        [&](uint32_t, const Pair& p, const float4& pj, NoAux) {
-            rho = fmaf(pj.w, p.w, rho);
-            float s = p.g * pj.w;  // m_j * gradient
-            float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
-            sq += ax * ax + ay * ay + az * az;
-            gx += ax; gy += ay; gz += az;
-        });
+    {
+        const uint32_t n = min(L.cnt_f[i], C.cap_f);
+        const uint32_t nq = (n + 3u) >> 2;
+        const uint4* col = L.nbr_f + i;
+        uint4 J = nq ? __ldg(col) : make_uint4(i, i, i, i);
+        for (uint32_t q = 0; q < nq; ++q) {
+            uint4 Jn = J;
+            if (q + 1 < nq) Jn = __ldg(col + (size_t)(q + 1) * C.stride);
+            const uint32_t j[4] = {J.x, J.y, J.z, J.w};
+            float4 pj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pj[u] = __ldg(&pos[j[u]]);  // tail slots point at i itself
+            float g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = q * 4u + u < n;
+                Pair p = make_pair<true, true>(pi, pj[u]);
+                g[u] = ok ? p.g : 0.f;
+                if (ok) {
+                    rho = fmaf(pj[u].w, p.w, rho);
+                    float s = p.g * pj[u].w;  // m_j * gradient
+                    float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
+                    sq += ax * ax + ay * ay + az * az;
+                    gx += ax; gy += ay; gz += az;
+                }
+            }
+            g_out[(size_t)q * C.stride + i] = make_float4(g[0], g[1], g[2], g[3]);  // evaluate_kernels helper.rs:24-25, cached for the step
+            J = Jn;
+        }
+    }
     for_boundary_contacts<true, true>(i, pi, L, bpos, [&](uint32_t, const Pair& p, const float4& pj) {
         float mb = pj.w * rho0;  // boundary pseudo mass: vol_b * rho0_i
         rho = fmaf(mb, p.w, rho);
@@ -151,7 +258,7 @@ k_vel_divergence(const float4* __restrict__ pos, const float4* __restrict__ vs, 
         float rho0 = C.fluids[fi].density0;
         float d = 0.f;
         if (PREDICT || L.cnt_f[i] + L.cnt_b[i] >= 20u) {
-            for_fluid_contacts<false, true>(
+            for_fluid_grads_pos<false>(
                 i, pi, L, pos, [&](uint32_t j) { return fetch4<TEX>(vs, tvs, j); },
                 [&](uint32_t, const Pair& p, const float4& pj, const float4& vj) {
                     float dv = (vi.x - vj.x) * p.dx + (vi.y - vj.y) * p.dy + (vi.z - vj.z) * p.dz;
@@ -201,7 +308,7 @@ k_vel_update(const float4* __restrict__ pos, const float4* __restrict__ vel, con
     float ki = kappa[i];
     const float scale = PRESSURE ? inv_dt : 1.0f;
     float ax = 0.f, ay = 0.f, az = 0.f;
-    for_fluid_contacts<false, true>(
+    for_fluid_grads_pos<false>(
         i, pi, L, pos, [&](uint32_t j) { return fetch1<TEX>(kappa, tkappa, j); },
         [&](uint32_t, const Pair& p, const float4& pj, float kj) {
             float c = (ki + kj) * pj.w * scale * p.g;
@@ -223,6 +330,110 @@ k_vel_update(const float4* __restrict__ pos, const float4* __restrict__ vel, con
     c4.x -= ax; c4.y -= ay; c4.z -= az;
     vc[i] = c4;
     vs[i] = make_float4(v.x + c4.x, v.y + c4.y, v.z + c4.z, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Uniform-mass fast path (one fluid whose particles all have the same volume — every default-constructed Fluid,
+// fluid.rs:110-120): the mass is a constant, so the per-contact gathers shrink to packed records
+//   pvx4 = (x, y, z, v*x), vyz2 = (v*y, v*z)   for the evaluations  (24 B instead of 32 B per contact)
+//   pk4  = (x, y, z, kappa)                     for the updates      (16 B instead of 20 B per contact)
+// and the two records of an evaluation travel through DIFFERENT data pipes (LSU / TEX).  The records are written
+// by the kernels that produce v* / kappa.  Same arithmetic as k_vel_divergence / k_vel_update.
+// ------------------------------------------------------------------------------------------------
+template <bool PREDICT, bool POS_TEX>
+__global__ void __launch_bounds__(PASS_T)
+k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, const float2* __restrict__ vyz, cudaTextureObject_t tvyz,
+                   const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
+                   const float* __restrict__ alpha, float* __restrict__ out, float4* __restrict__ pk4, float* __restrict__ partial, float dt,
+                   int* __restrict__ err) {
+    __shared__ float sm[32];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < C.n_owned;
+    i += C.i_begin;
+    float e = 0.f;
+    if (valid) {
+        const float4 a = pvx[i];
+        const float2 b = vyz[i];
+        const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
+        const float vix = a.w, viy = b.x, viz = b.y;
+        const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
+        float d = 0.f;
+        if (PREDICT || L.cnt_f[i] + L.cnt_b[i] >= 20u) {
+            for_fluid_grads<false>(
+                i, pi, L, [&](uint32_t j) { return POS_TEX ? tex1Dfetch<float4>(tpvx, (int)j) : __ldg(&pvx[j]); },
+                [&](uint32_t j) { return POS_TEX ? __ldg(&vyz[j]) : tex1Dfetch<float2>(tvyz, (int)j); },
+                [&](uint32_t, const Pair& p, const float4& pj, const float2& wj) {
+                    float dv = (vix - pj.w) * p.dx + (viy - wj.x) * p.dy + (viz - wj.y) * p.dz;
+                    d = fmaf(dv * p.g, mass, d);
+                });
+            for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+                float dv;
+                if (PREDICT) {
+                    float4 vj = __ldg(&bvel[j]);
+                    dv = (vix - vj.x) * p.dx + (viy - vj.y) * p.dy + (viz - vj.z) * p.dz;
+                } else {
+                    dv = vix * p.dx + viy * p.dy + viz * p.dz;
+                }
+                d = fmaf(dv * p.g, pj.w * rho0, d);
+            });
+        }
+        float kap;
+        if (PREDICT) {
+            float pd = fmaf(d, dt, dens[i]);
+            if (pd == 0.f) atomicOr(err, 1);
+            out[i] = pd;
+            kap = fmaxf((pd - rho0) * alpha[i], 0.f);
+            e = pd < rho0 ? 0.f : pd / rho0 - 1.0f;
+        } else {
+            d = fmaxf(d, 0.f);
+            out[i] = d;
+            kap = d * alpha[i];
+            e = d / rho0;
+        }
+        pk4[i] = make_float4(a.x, a.y, a.z, kap);
+    }
+    reduce_error<false>(e, 0u, valid, partial, sm);
+}
+
+template <bool BFORCE, bool PRESSURE, bool POS_TEX>
+__global__ void __launch_bounds__(PASS_T)
+k_vel_update_u(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
+               float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ pvx, float2* __restrict__ vyz, float* __restrict__ bforce,
+               float inv_dt) {
+    SPH_OWNED_INDEX(i)
+    const float4 a = pk4[i];
+    const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
+    const float ki = a.w;
+    const float4 v = vel[i];
+    const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
+    const float scale = (PRESSURE ? inv_dt : 1.0f) * mass;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for_fluid_grads<false>(
+        i, pi, L, [&](uint32_t j) { return POS_TEX ? tex1Dfetch<float4>(tpk, (int)j) : __ldg(&pk4[j]); }, [](uint32_t) { return NoAux{}; },
+        [&](uint32_t, const Pair& p, const float4& pj, NoAux) {
+            float c = (ki + pj.w) * scale * p.g;
+            ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
+        });
+    if (!PRESSURE || ki > 0.f) {
+        const float bscale = PRESSURE ? inv_dt : 1.0f;
+        for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+            float c = ki * pj.w * rho0 * bscale * p.g;
+            ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
+            if (BFORCE) {
+                float s = c * inv_dt * mass;
+                atomicAdd(&bforce[3 * (size_t)j + 0], s * p.dx);
+                atomicAdd(&bforce[3 * (size_t)j + 1], s * p.dy);
+                atomicAdd(&bforce[3 * (size_t)j + 2], s * p.dz);
+            }
+        });
+    }
+    float4 c4 = vc[i];
+    c4.x -= ax; c4.y -= ay; c4.z -= az;
+    vc[i] = c4;
+    const float sx = v.x + c4.x, sy = v.y + c4.y, sz = v.z + c4.z;
+    vs[i] = make_float4(sx, sy, sz, 0.f);
+    pvx[i] = make_float4(a.x, a.y, a.z, sx);
+    vyz[i] = make_float2(sy, sz);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -287,7 +498,7 @@ k_force_artificial(const float4* __restrict__ pos, const float4* __restrict__ ve
     float eta2 = C.h * C.h * 0.01f;
     float fx = 0.f, fy = 0.f, fz = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
     if (cf != 0.f)
-        for_fluid_contacts<false, true>(
+        for_fluid_grads_pos<true>(
             i, pi, L, pos, [&](uint32_t j) { return VelRho{__ldg(&vel[j]), __ldg(&dens[j])}; },
             [&](uint32_t, const Pair& p, const float4& pj, const VelRho& a) {
                 if (MULTI && fid_of(a.v) != which) return;
@@ -332,7 +543,7 @@ k_akinci_normals(const float4* __restrict__ pos, const float4* __restrict__ vel,
     if (MULTI && fid_of(vel[i]) != which) return;
     float4 pi = pos[i];
     float nx = 0.f, ny = 0.f, nz = 0.f;
-    for_fluid_contacts<false, true>(
+    for_fluid_grads_pos<false>(
         i, pi, L, pos, [&](uint32_t j) { return FidRho{MULTI ? fid_of(__ldg(&vel[j])) : 0u, __ldg(&dens[j])}; },
         [&](uint32_t, const Pair& p, const float4& pj, const FidRho& a) {
             if (MULTI && a.fid != which) return;
