@@ -296,5 +296,61 @@ class NumpyDFSPH:
             f["v"] = self.V[o:o + n].copy()
             o += n
 
+    def step_iisph(self, dt, gravity=(0.0, -9.81, 0.0), omega=F(0.5)):
+        """liquid_world.rs:67-158 + iisph_solver.rs:643-711 (dense restatement)."""
+        self.contacts()
+        self.densities_alphas()
+        if not hasattr(self, "press") or len(self.press) != len(self.P):
+            self.press = np.zeros(len(self.P), F)
+        acc = self._forces(gravity)            # predict_advection sees the previous dt / inv_dt
+        self.acc = acc
+        self.dt = F(dt)
+        self.inv_dt = F(0) if self.dt == 0 else F(1.0) / self.dt
+        dt = self.dt
+        self.vc = (self.vc + acc * dt).astype(F)
+        rho = self.dens
+        factor = (-dt * dt / (rho * rho)).astype(F)
+        dii = ((self.Gff * (self.mass[None, :] * factor[:, None])[..., None]).sum(axis=1, dtype=F) +
+               (self.Gfb * (self.mb * factor[:, None])[..., None]).sum(axis=1, dtype=F)).astype(F)
+        self.press = (self.press * F(0.5)).astype(F)
+        self.predicted()
+        fac2 = (dt * dt * self.mass / (rho * rho)).astype(F)
+        dji = (self.Gff * fac2[:, None, None]).astype(F)
+        aii = ((((dii[:, None, :] - dji) * self.Gff).sum(axis=2, dtype=F) * self.mass[None, :]).sum(axis=1, dtype=F))
+        djib = (self.Gfb * fac2[:, None, None]).astype(F)
+        aii = (aii + (((dii[:, None, :] - djib) * self.Gfb).sum(axis=2, dtype=F) * self.mb).sum(axis=1, dtype=F)).astype(F)
+        self.n_press_iter = 0
+        nmax = self.force_press if self.force_press >= 0 else self.max_p_iter
+        for i in range(nmax):
+            p = self.press
+            dijpj = ((self.Gff * (-self.mass * p / (rho * rho))[None, :, None]).sum(axis=1, dtype=F) * (dt * dt)).astype(F)
+            fct = (dijpj[:, None, :] - dii[None, :, :] * p[None, :, None] - (dijpj[None, :, :] - dji * p[:, None, None])).astype(F)
+            ssum = ((fct * self.Gff).sum(axis=2, dtype=F) * self.mass[None, :]).sum(axis=1, dtype=F)
+            ssum = (ssum + ((dijpj[:, None, :] * self.Gfb).sum(axis=2, dtype=F) * self.mb).sum(axis=1, dtype=F)).astype(F)
+            ok = np.abs(aii) > F(1.0e-9)
+            safe = np.where(ok, aii, F(1))
+            npr = ((F(1) - omega) * p + omega * (self.rho0 - self.pred - ssum) / safe).astype(F)
+            pos = ok & (npr > 0)
+            err = np.where(pos, (-ssum - aii * npr) / self.rho0, F(0)).astype(F)
+            self.press = np.where(pos, npr, F(0)).astype(F)
+            self.n_press_iter += 1
+            if self.force_press < 0 and self._mean_max(err) <= self.max_dens_err and i >= self.min_p_iter:
+                break
+        p = self.press
+        pr = (p / (rho * rho)).astype(F)
+        c = (dt * self.mass[None, :] * (pr[:, None] + pr[None, :])).astype(F)
+        self.vc = (self.vc - (self.Gff * c[..., None]).sum(axis=1, dtype=F)).astype(F)
+        cb = (self.mb * pr[:, None] * dt).astype(F)
+        self.vc = (self.vc - (self.Gfb * cb[..., None]).sum(axis=1, dtype=F)).astype(F)
+        self.V = (self.V + self.vc).astype(F)
+        self.P = (self.P + self.V * dt).astype(F)
+        self.vc = np.zeros_like(self.vc)
+        o = 0
+        for f in self.fl:
+            n = len(f["p"])
+            f["p"] = self.P[o:o + n].copy()
+            f["v"] = self.V[o:o + n].copy()
+            o += n
+
     def read_fluid(self, k):
         return self.fl[k]["p"].copy(), self.fl[k]["v"].copy()

@@ -71,3 +71,28 @@ def test_two_fluids_free_running_match():
     # boundary volumes (dfsph_solver.rs:72-96)
     vol, _ = o.read_boundary(0)
     assert np.allclose(vol, n.bvol, rtol=1e-5)
+
+
+@pytest.mark.parametrize("two", [False, True], ids=["one-fluid", "two-fluids"])
+def test_iisph_steps_match(two):
+    """IISPHSolver::step (iisph_solver.rs:643-711): oracle vs the dense restatement, forced and free-running."""
+    for forced in (3, -1):
+        sc = _scene(15, two_fluids=two, forces=(scenes.artificial_viscosity(1.0, 0.0),))
+        o = OracleWorld(sc["particle_radius"], 2.0, solver=1)
+        n = NumpyDFSPH(sc["particle_radius"], 2.0)
+        fo, _ = scenes.populate(o, sc)
+        fn, _ = scenes.populate(n, sc)
+        o.force_iterations(-1, forced)
+        n.force_press = forced
+        for _ in range(3):
+            o.step(0.005)
+            n.step_iisph(0.005)
+            assert o.stats()["n_pressure_iter"] == n.n_press_iter
+        off = 0
+        for a, b in zip(fo, fn):
+            po, vo = o.read_fluid(a)
+            pn, vn = n.read_fluid(b)
+            cnt = len(po)
+            assert np.abs(po - pn).max() < 1e-4 * float(o.h)
+            assert np.allclose(o.debug(a, "pressure"), n.press[off:off + cnt], rtol=2e-3, atol=1e-2)
+            off += cnt
