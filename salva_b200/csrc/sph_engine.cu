@@ -182,6 +182,8 @@ struct sph_world {
     const void* tex_vyz_ptr = nullptr;
     const void* tex_pk_ptr = nullptr;
     int use_gcache = 0;
+    bool fuse_div = true, fused_first_div = false;  // first compute_divergences evaluation rides with the density pass
+    uint32_t fused_nblk = 0;
     bool use_tex = false;
     cudaTextureObject_t tex_vs = 0, tex_kappa = 0;
     const void* tex_vs_ptr = nullptr;
@@ -832,6 +834,32 @@ sph_status launch_density_alpha(sph_world* w) {
     TRY(slab_refresh(w, w->dens.p, sizeof(float)));  // XSPH / artificial viscosity / Akinci gather rho_j of ghosts
     return SPH_OK;
 }
+// DFSPH: densities + alphas + the first divergence evaluation in one sweep (k_density_alpha_div)
+sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
+    size_t N = w->N;
+    int c = w->cur, bc = w->bcur;
+    const bool multi = w->fluids.size() > 1;
+    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
+    if (w->unimass) {
+        TRY(ensure_tex(w, &w->tex_vyz, &w->tex_vyz_ptr, w->vyz2.p, w->vyz2.cap));
+        LAUNCH((k_density_alpha_div<false, true>), N, PASS_T, w->pvx4.p, w->vs.p, (cudaTextureObject_t)0, w->vyz2.p, w->tex_vyz, w->vel[c].p, w->bpos[bc].p, L,
+               w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, w->partial.p, w->d_scal.p + 7);
+    } else {
+        TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
+        if (multi)
+            LAUNCH((k_density_alpha_div<true, false>), N, PASS_T, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p,
+                   w->bpos[bc].p, L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, w->partial.p, w->d_scal.p + 7);
+        else
+            LAUNCH((k_density_alpha_div<false, false>), N, PASS_T, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p,
+                   w->bpos[bc].p, L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, w->partial.p, w->d_scal.p + 7);
+    }
+    *nblk = cdiv(N, PASS_T);
+    TRY(slab_refresh(w, w->dens.p, sizeof(float)));
+    if (w->unimass) TRY(slab_refresh(w, w->pk4.p, sizeof(float4)));
+    else TRY(slab_refresh(w, w->kappa.p, sizeof(float)));
+    return SPH_OK;
+}
+
 #define BOOL3(kern, b0, b1, b2, n, threads, ...)                                                   \
     do {                                                                                           \
         if (b0) {                                                                                  \
@@ -1013,9 +1041,13 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     w->stats.n_divergence_iter = w->stats.n_divergence_eval = 0;
     uint32_t maxit = w->force_div >= 0 ? (uint32_t)w->force_div + 1 : w->desc.max_divergence_iter;
     for (uint32_t i = 0; i < maxit; ++i) {
-        TRY(span_begin(w, SP_DIV_EVAL));
-        TRY(launch_vel_divergence(w, false, &nblk));
-        TRY(span_end(w));
+        if (i == 0 && w->fused_first_div) {
+            nblk = w->fused_nblk;  // evaluation 0 was computed by k_density_alpha_div
+        } else {
+            TRY(span_begin(w, SP_DIV_EVAL));
+            TRY(launch_vel_divergence(w, false, &nblk));
+            TRY(span_end(w));
+        }
         w->stats.n_divergence_eval++;
         if (w->force_div >= 0) {
             if ((int)i >= w->force_div) break;
@@ -1103,7 +1135,15 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
     const bool multi = w->fluids.size() > 1;
     (void)c; (void)bc; (void)multi;
     // evaluate_kernels + compute_densities (liquid_world.rs:123-134) + compute_alphas (dfsph_solver.rs:679-684)
-    if (N) TRY(launch_density_alpha(w));
+    w->fused_first_div = false;
+    if (N) {
+        if (w->desc.solver == SPH_SOLVER_DFSPH && !w->tile && w->fuse_div) {
+            TRY(launch_density_alpha_div(w, &w->fused_nblk));
+            w->fused_first_div = true;
+        } else {
+            TRY(launch_density_alpha(w));
+        }
+    }
     CU(cudaEventRecord(w->ev[EV_DENS], w->st));
     if (N) {
         if (w->desc.solver == SPH_SOLVER_DFSPH) TRY(dfsph_step(w, dt, g));
@@ -1200,6 +1240,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     w->h = desc->particle_radius * desc->smoothing_factor * 2.0f;  // liquid_world.rs:44
     w->tile = desc->gather_backend == 1 && desc->solver == SPH_SOLVER_DFSPH;  // the tile backend covers the DFSPH passes only
     if (const char* t = getenv("SALVA_B200_GCACHE")) w->use_gcache = atoi(t);
+    if (const char* t = getenv("SALVA_B200_FUSE_DIV")) w->fuse_div = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_UNI_EVAL")) w->uni_eval_mode = atoi(t);
     if (const char* t = getenv("SALVA_B200_UNI_UPD")) w->uni_upd_mode = atoi(t);
     {

@@ -58,11 +58,13 @@ __device__ __forceinline__ void for_fluid_contacts_g(uint32_t i, const float4& p
         J = Jn;
     }
 }
-// Gradient-only passes, software pipelined: the gathers of group q+1 are issued BEFORE group q is evaluated and the
-// list indices are fetched two groups ahead, so a thread keeps 8-16 independent loads in flight while it computes
-// (ncu: these passes are latency-bound — issue slots ~63 % busy, long-scoreboard stalls dominate).
+// Gradient-only passes.  Contacts are consumed in groups of four: the group's 4 position gathers and 4 auxiliary
+// gathers are issued back to back before any arithmetic, and the next group's list indices are prefetched.
+// (A deeper software pipeline — gathers one group ahead — was measured SLOWER: 80-96 registers halve the occupancy,
+// C2 predicted-density pass 0.127 ms vs 0.099 ms; profiles/r1_v1_batching_tex_c2.md.)
 // C.use_gcache selects where the gradient scalar g_ij = W'(|x_ij|)/|x_ij| comes from: the per-step cache written by
-// k_density_alpha (fewer instructions, +4 B/contact of traffic) or recomputed from the positions.
+// k_density_alpha (fewer instructions, +4 B/contact of traffic; measured neutral at 1M, slower at 10M where the list
+// traffic already puts DRAM at ~50 %) or recomputed from the positions (default).
 // No tail masking: padded slots are (j = i, g = 0) and a self contact has zero gradient either way.
 template <bool NEED_D2, class LP, class LD, class FF>
 __device__ __forceinline__ void for_fluid_grads(uint32_t i, const float4& pi, const Lists& L, LP ldpos, LD ld, FF ff) {
@@ -72,63 +74,39 @@ __device__ __forceinline__ void for_fluid_grads(uint32_t i, const float4& pi, co
     const bool cached = C.use_gcache != 0;
     const uint4* col = L.nbr_f + i;
     const float4* gcol = L.g_f + i;
-    typedef decltype(ld(0u)) Aux;
-    // stage 0: indices of groups 0 and 1, gathers of group 0
-    uint4 J0 = __ldg(col);
-    uint4 J1 = nq > 1 ? __ldg(col + (size_t)C.stride) : J0;
-    float4 G0 = cached ? __ldg(gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 P0[4];
-    Aux A0[4];
-    {
-        const uint32_t j[4] = {J0.x, J0.y, J0.z, J0.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) P0[u] = ldpos(j[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) A0[u] = ld(j[u]);
-    }
+    uint4 J = __ldg(col);
+    float4 Gq = cached ? __ldg(gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t q = 0; q < nq; ++q) {
-        // issue the next group's loads first
-        uint4 J2 = J1;
-        float4 G1 = G0;
-        float4 P1[4];
-        Aux A1[4];
-        const bool more = q + 1 < nq;
-        if (more) {
-            if (q + 2 < nq) J2 = __ldg(col + (size_t)(q + 2) * C.stride);
-            if (cached) G1 = __ldg(gcol + (size_t)(q + 1) * C.stride);
-            const uint32_t j[4] = {J1.x, J1.y, J1.z, J1.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) P1[u] = ldpos(j[u]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) A1[u] = ld(j[u]);
+        uint4 Jn = J;
+        float4 Gn = Gq;
+        if (q + 1 < nq) {  // prefetch the next group
+            Jn = __ldg(col + (size_t)(q + 1) * C.stride);
+            if (cached) Gn = __ldg(gcol + (size_t)(q + 1) * C.stride);
         }
-        // evaluate the current group
-        const uint32_t j0[4] = {J0.x, J0.y, J0.z, J0.w};
-        const float g0[4] = {G0.x, G0.y, G0.z, G0.w};
+        const uint32_t j[4] = {J.x, J.y, J.z, J.w};
+        const float g[4] = {Gq.x, Gq.y, Gq.z, Gq.w};
+        float4 pj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pj[u] = ldpos(j[u]);
+        decltype(ld(0u)) aux[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) aux[u] = ld(j[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             Pair p;
             if (cached) {
-                p.dx = pi.x - P0[u].x;
-                p.dy = pi.y - P0[u].y;
-                p.dz = pi.z - P0[u].z;
-                p.g = g0[u];
+                p.dx = pi.x - pj[u].x;
+                p.dy = pi.y - pj[u].y;
+                p.dz = pi.z - pj[u].z;
+                p.g = g[u];
                 if (NEED_D2) p.d2 = fmaf(p.dz, p.dz, fmaf(p.dy, p.dy, p.dx * p.dx));
             } else {
-                p = make_pair<false, true>(pi, P0[u]);
+                p = make_pair<false, true>(pi, pj[u]);
             }
-            ff(j0[u], p, P0[u], A0[u]);
+            ff(j[u], p, pj[u], aux[u]);
         }
-        if (more) {
-            J0 = J1;
-            J1 = J2;
-            G0 = G1;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                P0[u] = P1[u];
-                A0[u] = A1[u];
-            }
-        }
+        J = Jn;
+        Gq = Gn;
     }
 }
 template <bool NEED_D2, class LD, class FF>
@@ -215,7 +193,7 @@ k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, 
                     gx += ax; gy += ay; gz += az;
                 }
             }
-            g_out[(size_t)q * C.stride + i] = make_float4(g[0], g[1], g[2], g[3]);  // evaluate_kernels helper.rs:24-25, cached for the step
+            if (C.use_gcache) g_out[(size_t)q * C.stride + i] = make_float4(g[0], g[1], g[2], g[3]);  // helper.rs:24-25, cached for the step
             J = Jn;
         }
     }
@@ -231,6 +209,110 @@ k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, 
     float den = sq + (gx * gx + gy * gy + gz * gz);
     dens[i] = rho;
     alpha[i] = den <= 1.0e-5f ? 0.f : 1.0f / den;  // dfsph_solver.rs:209-213
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 + first K4a fused (DFSPH): densities, alphas AND the first compute_divergences evaluation in ONE gather pass.
+// The first divergence evaluation of divergence_solve (dfsph_solver.rs:474-480) reads the same neighbour positions
+// and the step-start v* = vel + vc, and needs alpha_i only for kappa_i = div_i * alpha_i at the very end, so it can
+// ride along with the density pass: one full neighbour sweep less per step.  Arithmetic per quantity is unchanged.
+// UNI: uniform-mass packed records (positions from pvx4, v* from pvx4.w + vyz2), else pos4 / vs4.
+// ------------------------------------------------------------------------------------------------
+struct Vel3 {
+    float x, y, z;
+};
+template <bool MULTI, bool UNI>
+__global__ void __launch_bounds__(PASS_T)
+k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, const float4* __restrict__ vs, cudaTextureObject_t tvs,
+                    const float2* __restrict__ vyz, cudaTextureObject_t tvyz, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
+                    float4* __restrict__ g_out, float* __restrict__ dens, float* __restrict__ alpha, float* __restrict__ divv, float* __restrict__ kappa,
+                    float4* __restrict__ pk4, float* __restrict__ partial, int* __restrict__ err) {
+    __shared__ float sm[32];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < C.n_owned;
+    i += C.i_begin;
+    float e = 0.f;
+    uint32_t fi = 0;
+    if (valid) {
+        const float4 a = posrec[i];
+        const float4 pi = make_float4(a.x, a.y, a.z, a.w);
+        fi = MULTI ? fid_of(vel[i]) : 0u;
+        const float rho0 = C.fluids[fi].density0;
+        const float umass = C.fluids[0].mass;
+        Vel3 vi;
+        if (UNI) {
+            float2 b = vyz[i];
+            vi = Vel3{a.w, b.x, b.y};
+        } else {
+            float4 s = vs[i];
+            vi = Vel3{s.x, s.y, s.z};
+        }
+        float rho = 0.f, sq = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, d = 0.f;
+        const uint32_t n = min(L.cnt_f[i], C.cap_f);
+        const uint32_t nq = (n + 3u) >> 2;
+        const uint4* col = L.nbr_f + i;
+        uint4 J = nq ? __ldg(col) : make_uint4(i, i, i, i);
+        for (uint32_t q = 0; q < nq; ++q) {
+            uint4 Jn = J;
+            if (q + 1 < nq) Jn = __ldg(col + (size_t)(q + 1) * C.stride);
+            const uint32_t j[4] = {J.x, J.y, J.z, J.w};
+            float4 pj[4];
+            Vel3 vj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pj[u] = __ldg(&posrec[j[u]]);  // tail slots point at i itself
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (UNI) {
+                    float2 b = tex1Dfetch<float2>(tvyz, (int)j[u]);
+                    vj[u] = Vel3{pj[u].w, b.x, b.y};
+                } else {
+                    float4 s = tex1Dfetch<float4>(tvs, (int)j[u]);
+                    vj[u] = Vel3{s.x, s.y, s.z};
+                }
+            }
+            float g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = q * 4u + u < n;
+                Pair p = make_pair<true, true>(pi, pj[u]);
+                g[u] = ok ? p.g : 0.f;
+                if (ok) {
+                    const float mj = UNI ? umass : pj[u].w;
+                    rho = fmaf(mj, p.w, rho);
+                    float s = p.g * mj;  // m_j * gradient
+                    float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
+                    sq += ax * ax + ay * ay + az * az;
+                    gx += ax; gy += ay; gz += az;
+                    float dv = (vi.x - vj[u].x) * p.dx + (vi.y - vj[u].y) * p.dy + (vi.z - vj[u].z) * p.dz;
+                    d = fmaf(dv * p.g, mj, d);
+                }
+            }
+            if (C.use_gcache) g_out[(size_t)q * C.stride + i] = make_float4(g[0], g[1], g[2], g[3]);
+            J = Jn;
+        }
+        for_boundary_contacts<true, true>(i, pi, L, bpos, [&](uint32_t, const Pair& p, const float4& pj) {
+            float mb = pj.w * rho0;  // boundary pseudo mass: vol_b * rho0_i
+            rho = fmaf(mb, p.w, rho);
+            float s = p.g * mb;
+            float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
+            sq += ax * ax + ay * ay + az * az;
+            gx += ax; gy += ay; gz += az;
+            float dv = vi.x * p.dx + vi.y * p.dy + vi.z * p.dz;  // boundary velocity ignored (dfsph_solver.rs:336-338)
+            d = fmaf(dv * p.g, mb, d);
+        });
+        if (rho == 0.f) atomicOr(err, 1);  // assert!(!density.is_zero()) dfsph_solver.rs:662
+        float den = sq + (gx * gx + gy * gy + gz * gz);
+        float al = den <= 1.0e-5f ? 0.f : 1.0f / den;  // dfsph_solver.rs:209-213
+        dens[i] = rho;
+        alpha[i] = al;
+        if (L.cnt_f[i] + L.cnt_b[i] < 20u) d = 0.f;  // min_neighbors_for_divergence_solve :62,301-314
+        d = fmaxf(d, 0.f);
+        divv[i] = d;
+        if (UNI) pk4[i] = make_float4(a.x, a.y, a.z, d * al);
+        else kappa[i] = d * al;
+        e = d / rho0;
+    }
+    reduce_error<MULTI>(e, fi, valid, partial, sm);
 }
 
 // ------------------------------------------------------------------------------------------------
