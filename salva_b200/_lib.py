@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsalva_b200.so")
+LIB_PATH = os.environ.get("SALVA_B200_LIB") or os.path.join(_HERE, "libsalva_b200.so")  # env override: A/B builds
 _LIB = None
 
 SPH_OK = 0

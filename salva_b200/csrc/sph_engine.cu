@@ -181,6 +181,9 @@ struct sph_world {
     const void* tex_pvx_ptr = nullptr;
     const void* tex_vyz_ptr = nullptr;
     const void* tex_pk_ptr = nullptr;
+    DBuf<LoopCtl> d_ctl;          // device-side Jacobi loop control (sph_kernels.cuh LoopCtl)
+    LoopCtl* h_ctl = nullptr;     // pinned host mirror
+    bool device_loops = false;  // measured slower at C2 (gated no-op launches cost more than the syncs they save)
     int use_gcache = 0;
     bool fuse_div = true, fused_first_div = false;  // first compute_divergences evaluation rides with the density pass
     uint32_t fused_nblk = 0;
@@ -887,7 +890,7 @@ sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
     } while (0)
 
 // compute_divergences (predict = false) / compute_predicted_densities (predict = true); returns #partials
-sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk) {
+sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, const int* gate = nullptr) {
     size_t N = w->N;
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1;
@@ -905,14 +908,14 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk) {
         const bool ptex = w->uni_eval_mode == 1;
         if (predict) {
             if (ptex) LAUNCH((k_vel_divergence_u<true, true>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                             w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7);
+                             w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
             else LAUNCH((k_vel_divergence_u<true, false>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                        w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7);
+                        w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
         } else {
             if (ptex) LAUNCH((k_vel_divergence_u<false, true>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                             w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7);
+                             w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
             else LAUNCH((k_vel_divergence_u<false, false>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                        w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7);
+                        w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
         }
         *nblk = cdiv(N, PASS_T);
         TRY(slab_refresh(w, w->pk4.p, sizeof(float4)));  // the following update gathers (x, kappa) of ghosts
@@ -921,14 +924,14 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk) {
         Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
         if (w->use_tex) TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
         BOOL3(k_vel_divergence, multi, predict, w->use_tex, N, PASS_T, w->pos[c].p, w->vs.p, w->tex_vs, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L,
-              w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
+              w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
         *nblk = cdiv(N, PASS_T);
     }
     TRY(slab_refresh(w, w->kappa.p, sizeof(float)));  // the following update gathers kappa_j of ghosts
     return SPH_OK;
 }
 // compute_velocity_changes_for_divergence (pressure = false) / compute_velocity_changes (pressure = true)
-sph_status launch_vel_update(sph_world* w, bool pressure) {
+sph_status launch_vel_update(sph_world* w, bool pressure, const int* gate = nullptr) {
     size_t N = w->N;
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1, bf = any_bforce(w);
@@ -946,7 +949,7 @@ sph_status launch_vel_update(sph_world* w, bool pressure) {
         TRY(ensure_tex(w, &w->tex_pk, &w->tex_pk_ptr, w->pk4.p, w->pk4.cap));
         const bool ptex = w->uni_upd_mode == 1;
         BOOL3(k_vel_update_u, bf, pressure, ptex, N, PASS_T, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p,
-              w->vyz2.p, w->bforce.p, w->inv_dt);
+              w->vyz2.p, w->bforce.p, w->inv_dt, gate);
         TRY(refresh_vstar(w));
         return SPH_OK;
     } else {
@@ -955,7 +958,7 @@ sph_status launch_vel_update(sph_world* w, bool pressure) {
         const bool tex = false;
         if (tex) TRY(ensure_tex(w, &w->tex_kappa, &w->tex_kappa_ptr, w->kappa.p, w->kappa.cap));
         BOOL4(k_vel_update, multi, bf, pressure, tex, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->tex_kappa,
-              w->vc[c].p, w->vs.p, w->bforce.p, w->inv_dt);
+              w->vc[c].p, w->vs.p, w->bforce.p, w->inv_dt, gate);
     }
     TRY(slab_refresh(w, w->vs.p, sizeof(float4)));  // the following evaluation gathers v*_j of ghosts
     return SPH_OK;
@@ -1030,6 +1033,64 @@ void timestep_advance(sph_world* w, float total) {
     w->inv_dt = total == 0.f ? 0.f : 1.0f / total;
 }
 
+// One Jacobi loop of DFSPHSolver (divergence_solve :466-503 when pressure == false, pressure_solve :432-464 otherwise)
+// with the break decision taken on the device: iterations are enqueued SPEC at a time, kernels past the break are
+// gated off, and the host synchronises once per batch to learn whether the loop has ended.
+sph_status jacobi_loop_device(sph_world* w, bool pressure, bool first_eval_done, uint32_t first_nblk, float tol, uint32_t min_iter, uint32_t max_iter,
+                              int forced, uint32_t* n_upd, uint32_t* n_eval, float* last_err) {
+    LoopCtl hc;
+    memset(&hc, 0, sizeof hc);
+    hc.active = 1;
+    hc.tol = tol;
+    hc.min_iter = min_iter;
+    hc.max_iter = forced >= 0 ? (uint32_t)forced + 1 : max_iter;
+    hc.forced = forced;
+    hc.n_fluids = (int)w->fluids.size();
+    for (int f = 0; f < hc.n_fluids; ++f) {
+        double n = w->slab.active ? (double)w->slab.global_n : (double)w->fluids[f].n;
+        hc.inv_count[f] = n > 0 ? (float)(1.0 / n) : 0.f;
+    }
+    if (hc.max_iter == 0) {
+        *n_upd = *n_eval = 0;
+        return SPH_OK;
+    }
+    *w->h_ctl = hc;
+    CU(cudaMemcpyAsync(w->d_ctl.p, w->h_ctl, sizeof(LoopCtl), cudaMemcpyHostToDevice, w->st));
+    const int* g_active = &w->d_ctl.p->active;
+    const int* g_update = &w->d_ctl.p->do_update;
+    const int nf = hc.n_fluids;
+    const uint32_t SPEC = 2;  // iterations enqueued per host sync (typical loops run 1-2 updates)
+    uint32_t enq = 0;
+    bool first = true;
+    for (;;) {
+        for (uint32_t s = 0; s < SPEC && enq < hc.max_iter; ++s, ++enq) {
+            uint32_t nblk = first_nblk;
+            if (!(first && first_eval_done)) {
+                TRY(span_begin(w, pressure ? SP_PRED : SP_DIV_EVAL));
+                TRY(launch_vel_divergence(w, pressure, &nblk, g_active));
+                TRY(span_end(w));
+            }
+            first = false;
+            k_reduce_partials<<<nf, 256, 0, w->st>>>(w->partial.p, nblk, nf, w->errsum.p);
+            w->launches++;
+            TRY(slab_allreduce(w, w->errsum.p, nf));
+            k_loop_decide<<<1, 32, 0, w->st>>>(w->d_ctl.p, w->errsum.p);
+            w->launches++;
+            TRY(span_begin(w, pressure ? SP_PUPD : SP_DIV_UPD));
+            TRY(launch_vel_update(w, pressure, g_update));
+            TRY(span_end(w));
+        }
+        CU(cudaMemcpyAsync(w->h_ctl, w->d_ctl.p, sizeof(LoopCtl), cudaMemcpyDeviceToHost, w->st));
+        CU(cudaStreamSynchronize(w->st));
+        if (!w->h_ctl->active || enq >= hc.max_iter) break;
+    }
+    // `for i in 0..max`: when the loop ran out of iterations the last update is not followed by an evaluation
+    *n_upd = w->h_ctl->iter;
+    *n_eval = w->h_ctl->n_eval;
+    *last_err = w->h_ctl->last_err;
+    return SPH_OK;
+}
+
 // DFSPHSolver::step dfsph_solver.rs:667-708
 sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     size_t N = w->N;
@@ -1040,6 +1101,12 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     // divergence_solve :466-503 (uses the PREVIOUS step's inv_dt; 0 on the first step)
     w->stats.n_divergence_iter = w->stats.n_divergence_eval = 0;
     uint32_t maxit = w->force_div >= 0 ? (uint32_t)w->force_div + 1 : w->desc.max_divergence_iter;
+    const bool dev_loops = w->device_loops && !w->tile;
+    if (dev_loops && w->force_div < 0) {
+        TRY(jacobi_loop_device(w, false, w->fused_first_div, w->fused_nblk, w->desc.max_divergence_error * w->inv_dt * 0.01f, w->desc.min_divergence_iter,
+                               w->desc.max_divergence_iter, -1, &w->stats.n_divergence_iter, &w->stats.n_divergence_eval, &w->stats.last_divergence_error));
+        maxit = 0;
+    }
     for (uint32_t i = 0; i < maxit; ++i) {
         if (i == 0 && w->fused_first_div) {
             nblk = w->fused_nblk;  // evaluation 0 was computed by k_density_alpha_div
@@ -1078,6 +1145,11 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     // pressure_solve :432-464
     w->stats.n_pressure_iter = w->stats.n_pressure_eval = 0;
     maxit = w->force_press >= 0 ? (uint32_t)w->force_press + 1 : w->desc.max_pressure_iter;
+    if (dev_loops && w->force_press < 0) {
+        TRY(jacobi_loop_device(w, true, false, 0, w->desc.max_density_error, w->desc.min_pressure_iter, w->desc.max_pressure_iter, -1,
+                               &w->stats.n_pressure_iter, &w->stats.n_pressure_eval, &w->stats.last_density_error));
+        maxit = 0;
+    }
     for (uint32_t i = 0; i < maxit; ++i) {
         TRY(span_begin(w, SP_PRED));
         TRY(launch_vel_divergence(w, true, &nblk));
@@ -1239,6 +1311,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     w->desc = *desc;
     w->h = desc->particle_radius * desc->smoothing_factor * 2.0f;  // liquid_world.rs:44
     w->tile = desc->gather_backend == 1 && desc->solver == SPH_SOLVER_DFSPH;  // the tile backend covers the DFSPH passes only
+    if (const char* t = getenv("SALVA_B200_DEVICE_LOOPS")) w->device_loops = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_GCACHE")) w->use_gcache = atoi(t);
     if (const char* t = getenv("SALVA_B200_FUSE_DIV")) w->fuse_div = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_UNI_EVAL")) w->uni_eval_mode = atoi(t);
@@ -1252,6 +1325,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     bool ok = cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < EV_COUNT; ++i) ok = cudaEventCreate(&w->ev[i]) == cudaSuccess;
     ok = ok && cudaMallocHost(&w->h_pinned, 64 * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&w->h_ctl, sizeof(LoopCtl)) == cudaSuccess && w->d_ctl.ensure(1) == cudaSuccess;
     ok = ok && w->d_scal.ensure(16) == cudaSuccess && w->d_cnt.ensure(2) == cudaSuccess;
     if (!ok) {
         delete w;
@@ -1293,6 +1367,8 @@ void sph_world_destroy(sph_world* w) {
         cudaEventDestroy(s.b);
     }
     if (w->h_pinned) cudaFreeHost(w->h_pinned);
+    if (w->h_ctl) cudaFreeHost(w->h_ctl);
+    w->d_ctl.release();
     for (auto& e : w->ev)
         if (e) cudaEventDestroy(e);
     if (w->st) cudaStreamDestroy(w->st);

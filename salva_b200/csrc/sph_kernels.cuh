@@ -403,7 +403,53 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, uint32_t nb
     if (threadIdx.x == 0) out[f] = s;
 }
 
-constexpr int PASS_T = 128;  // threads per block of the gather passes
+#ifndef SPH_PASS_T
+#define SPH_PASS_T 128
+#endif
+#ifndef SPH_PASS_MINB
+#define SPH_PASS_MINB 9   // Jacobi-loop / density kernels: 56 registers, 9 blocks of 128 per SM (measured best, profiles/r1_v2_*)
+#endif
+#ifndef SPH_FORCE_MINB
+#define SPH_FORCE_MINB 8  // force kernels gather more per contact: 64 registers avoid spills
+#endif
+constexpr int PASS_T = SPH_PASS_T;  // threads per block of the gather passes
+
+// Device-side control of the Jacobi loops (`for i in 0..max { eval; if err <= tol && i >= min { break } update }`,
+// dfsph_solver.rs:439-463,474-502).  The host enqueues a few iterations ahead; k_loop_decide takes the reference's
+// break decision on the device and the evaluation / update kernels of iterations that must not run exit immediately
+// (`active` gates evaluations, `do_update` gates updates).  One host sync per loop instead of one per evaluation.
+struct LoopCtl {
+    int active;       // further evaluations may run
+    int do_update;    // the update following the last evaluation must run
+    uint32_t iter;    // updates decided so far
+    uint32_t n_eval;  // evaluations executed
+    float last_err;
+    float tol;
+    uint32_t min_iter, max_iter;
+    int forced;       // >= 0: run exactly this many updates (parity aid), ignore the error
+    int n_fluids;
+    float inv_count[MAX_FLUIDS];  // 1 / particle count per fluid (global count in a slab world); 0 for empty fluids
+};
+__global__ void k_loop_decide(LoopCtl* __restrict__ ctl, const float* __restrict__ errsum) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!ctl->active) {
+        ctl->do_update = 0;
+        return;
+    }
+    ctl->n_eval++;
+    float err = 0.f;
+    for (int f = 0; f < ctl->n_fluids; ++f) err = fmaxf(err, errsum[f] * ctl->inv_count[f]);  // per-fluid mean, max over fluids
+    ctl->last_err = err;
+    bool stop = ctl->forced >= 0 ? (int)ctl->iter >= ctl->forced : (err <= ctl->tol && ctl->iter >= ctl->min_iter);
+    if (stop) {
+        ctl->active = 0;
+        ctl->do_update = 0;
+    } else {
+        ctl->do_update = 1;
+        ctl->iter++;
+        if (ctl->iter >= ctl->max_iter) ctl->active = 0;  // the loop ends after this update without another evaluation
+    }
+}
 
 // v* = vel + vc after the reorder (the divergence solve works on vel + vc carried over from the previous step, Appendix A.3.2)
 __global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __restrict__ vc, float4* __restrict__ vs, const float4* __restrict__ pos,

@@ -160,7 +160,7 @@ __device__ __forceinline__ void reduce_error(float e, uint32_t fi, bool valid, f
 // kernel evaluation of helper.rs:9-65.
 // ------------------------------------------------------------------------------------------------
 template <bool MULTI>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, float4* __restrict__ g_out,
                 float* __restrict__ dens, float* __restrict__ alpha, int* __restrict__ err) {
     SPH_OWNED_INDEX(i)
@@ -222,7 +222,7 @@ struct Vel3 {
     float x, y, z;
 };
 template <bool MULTI, bool UNI>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, const float4* __restrict__ vs, cudaTextureObject_t tvs,
                     const float2* __restrict__ vyz, cudaTextureObject_t tvyz, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
                     float4* __restrict__ g_out, float* __restrict__ dens, float* __restrict__ alpha, float* __restrict__ divv, float* __restrict__ kappa,
@@ -322,11 +322,12 @@ k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, const 
 //   else   : out = div_i (0 below 20 contacts, :62,301-314), kappa = div * alpha, boundary velocity ignored (:336-338).
 // ------------------------------------------------------------------------------------------------
 template <bool MULTI, bool PREDICT, bool TEX>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_divergence(const float4* __restrict__ pos, const float4* __restrict__ vs, cudaTextureObject_t tvs, const float4* __restrict__ vel,
                  const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
                  const float* __restrict__ alpha, float* __restrict__ out, float* __restrict__ kappa, float* __restrict__ partial, float dt,
-                 int* __restrict__ err) {
+                 int* __restrict__ err, const int* __restrict__ gate) {
+    if (gate && !*gate) return;  // device-side loop control: this evaluation is past the break
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < C.n_owned;
@@ -380,9 +381,11 @@ k_vel_divergence(const float4* __restrict__ pos, const float4* __restrict__ vs, 
 // PRESSURE: k = kappa+ (>= 0), scale = inv_dt, boundary term only if k_i > 0 (:257); else k = div*alpha, scale = 1.
 // ------------------------------------------------------------------------------------------------
 template <bool MULTI, bool BFORCE, bool PRESSURE, bool TEX>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_update(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ kappa,
-             cudaTextureObject_t tkappa, float4* __restrict__ vc, float4* __restrict__ vs, float* __restrict__ bforce, float inv_dt) {
+             cudaTextureObject_t tkappa, float4* __restrict__ vc, float4* __restrict__ vs, float* __restrict__ bforce, float inv_dt,
+             const int* __restrict__ gate) {
+    if (gate && !*gate) return;
     SPH_OWNED_INDEX(i)
     float4 pi = pos[i];
     float4 v = vel[i];
@@ -423,11 +426,12 @@ k_vel_update(const float4* __restrict__ pos, const float4* __restrict__ vel, con
 // by the kernels that produce v* / kappa.  Same arithmetic as k_vel_divergence / k_vel_update.
 // ------------------------------------------------------------------------------------------------
 template <bool PREDICT, bool POS_TEX>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, const float2* __restrict__ vyz, cudaTextureObject_t tvyz,
                    const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
                    const float* __restrict__ alpha, float* __restrict__ out, float4* __restrict__ pk4, float* __restrict__ partial, float dt,
-                   int* __restrict__ err) {
+                   int* __restrict__ err, const int* __restrict__ gate) {
+    if (gate && !*gate) return;
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < C.n_owned;
@@ -478,10 +482,11 @@ k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, con
 }
 
 template <bool BFORCE, bool PRESSURE, bool POS_TEX>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_update_u(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
                float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ pvx, float2* __restrict__ vyz, float* __restrict__ bforce,
-               float inv_dt) {
+               float inv_dt, const int* __restrict__ gate) {
+    if (gate && !*gate) return;
     SPH_OWNED_INDEX(i)
     const float4 a = pk4[i];
     const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
@@ -528,7 +533,7 @@ struct VelRho {
 };
 // a12: XSPHViscosity::solve xsph_viscosity.rs:30-95
 template <bool MULTI, bool BFORCE>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
 k_force_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L,
              const float* __restrict__ dens, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float cf, float cb, float inv_dt) {
     SPH_OWNED_INDEX(i)
@@ -567,7 +572,7 @@ k_force_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel, con
 
 // a13: ArtificialViscosity::solve artificial_viscosity.rs:40-124
 template <bool MULTI, bool BFORCE>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
 k_force_artificial(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L,
                    const float* __restrict__ dens, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float cf, float cb, float alpha,
                    float beta, float cs) {
@@ -618,7 +623,7 @@ struct FidRho {
 };
 // a14 pass 1: Akinci2013 compute_normals akinci2013_surface_tension.rs:43-68
 template <bool MULTI>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
 k_akinci_normals(const float4* __restrict__ pos, const float4* __restrict__ vel, Lists L, const float* __restrict__ dens, float4* __restrict__ normals,
                  uint32_t which) {
     SPH_OWNED_INDEX(i)
@@ -642,7 +647,7 @@ struct NrmRho {
 };
 // a14 pass 2: Akinci2013SurfaceTension::solve akinci2013_surface_tension.rs:113-192
 template <bool MULTI, bool BFORCE>
-__global__ void __launch_bounds__(PASS_T)
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
 k_akinci_force(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens,
                const float4* __restrict__ normals, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float gamma, float adh,
                float coh_norm, float h6_64, float adh_norm) {
