@@ -97,8 +97,10 @@ class OracleWorld:
 
     def __init__(self, particle_radius, smoothing_factor=2.0, solver=0, min_pressure_iter=1, max_pressure_iter=50,
                  max_density_error=0.05, min_divergence_iter=1, max_divergence_iter=50, max_divergence_error=0.1,
-                 omega=0.5, sort_contacts=True, num_threads=0):
+                 omega=0.5, sort_contacts=True, num_threads=None):
         self._L = lib()
+        if num_threads is None:  # small test scenes: a handful of threads (128 spinning OpenMP threads are far slower)
+            num_threads = min(8, os.cpu_count() or 1)
         d = OrcDesc(solver, particle_radius, smoothing_factor, min_pressure_iter, max_pressure_iter,
                     max_density_error, min_divergence_iter, max_divergence_iter, max_divergence_error, omega,
                     int(sort_contacts), num_threads)

@@ -152,6 +152,12 @@ struct sph_world {
     std::vector<float> h_pos, h_vel, h_vc, h_vol, h_press;
     // boundaries: host copy is always kept (static data); b_dirty => re-upload
     bool b_dirty = true;
+    int b_aabb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};  // boundary cell-coordinate AABB (host side, static)
+    bool b_bad = false;
+    // the boundary sort / volumes are reused while the boundaries and the grid mapping are unchanged
+    bool b_sorted_valid = false, b_reused = false;
+    unsigned long long bb_contacts = 0;
+    int b_sorted_grid[6] = {0, 0, 0, 0, 0, 0};
     std::vector<float> hb_pos, hb_vel;
 
     // sorted device state (double buffered for the counting sort)
@@ -479,6 +485,17 @@ sph_status upload_boundaries(sph_world* w) {
     CU(w->bforce.ensure(3 * B));
     if (B) {
         std::vector<float4> p(B), v(B);
+        int aabb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+        bool bad = false;
+        for (size_t g = 0; g < B; ++g)
+            for (int a = 0; a < 3; ++a) {
+                float cf = floorf(w->hb_pos[3 * g + a] / w->h);  // hgrid.rs:41-43, same IEEE division as the device
+                if (!(fabsf(cf) < 1.0e9f)) { bad = true; continue; }
+                aabb[a] = std::min(aabb[a], (int)cf);
+                aabb[3 + a] = std::max(aabb[3 + a], (int)cf);
+            }
+        memcpy(w->b_aabb, aabb, sizeof aabb);
+        w->b_bad = bad;
         for (size_t b = 0; b < w->bounds.size(); ++b)
             for (size_t i = 0; i < w->bounds[b].n; ++i) {
                 size_t g = w->bounds[b].offset + i;
@@ -491,7 +508,13 @@ sph_status upload_boundaries(sph_world* w) {
         LAUNCH(k_iota, B, 256, (uint32_t)B, w->borig[c].p);
         CU(cudaStreamSynchronize(w->st));
     }
+    if (!B) {
+        int none[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+        memcpy(w->b_aabb, none, sizeof none);
+        w->b_bad = false;
+    }
     w->b_dirty = false;
+    w->b_sorted_valid = false;
     w->lists_valid = false;
     return SPH_OK;
 }
@@ -544,17 +567,17 @@ sph_status phase_grid(sph_world* w) {
     CU(cudaMemcpyAsync(w->d_scal.p, init, sizeof init, cudaMemcpyHostToDevice, w->st));
     CU(cudaMemsetAsync(w->d_cnt.p, 0, 2 * sizeof(unsigned long long), w->st));
     if (N) {
-        k_bounds<<<std::min<uint32_t>(cdiv(N, 256), 1184), 256, 0, w->st>>>(w->pos[c].p, (uint32_t)N, w->d_scal.p);
-        w->launches++;
-    }
-    if (B) {
-        k_bounds<<<std::min<uint32_t>(cdiv(B, 256), 1184), 256, 0, w->st>>>(w->bpos[bc].p, (uint32_t)B, w->d_scal.p);
+        k_bounds<<<std::min<uint32_t>(cdiv(N, 256), 296), 256, 0, w->st>>>(w->pos[c].p, (uint32_t)N, w->d_scal.p);
         w->launches++;
     }
     int hb[7];
     CU(cudaMemcpyAsync(hb, w->d_scal.p, sizeof hb, cudaMemcpyDeviceToHost, w->st));
     CU(cudaStreamSynchronize(w->st));
-    if (hb[6]) return w->fail(SPH_ERR_INVALID, "non-finite or out-of-range particle coordinates");
+    if (hb[6] || w->b_bad) return w->fail(SPH_ERR_INVALID, "non-finite or out-of-range particle coordinates");
+    for (int a = 0; a < 3; ++a) {  // boundary AABB: static, kept on the host
+        hb[a] = std::min(hb[a], w->b_aabb[a]);
+        hb[3 + a] = std::max(hb[3 + a], w->b_aabb[3 + a]);
+    }
     long long dims[3];
     for (int a = 0; a < 3; ++a) dims[a] = (long long)hb[3 + a] - hb[a] + 3;  // one padding cell each side
     double ncell_d = (double)dims[0] * (double)dims[1] * (double)dims[2];
@@ -604,9 +627,12 @@ sph_status phase_grid(sph_world* w) {
         LAUNCH(k_make_vstar, N, 256, w->vel[w->cur].p, w->vc[w->cur].p, w->vs.p, w->pos[w->cur].p, w->unimass ? w->pvx4.p : nullptr,
                w->unimass ? w->vyz2.p : nullptr);
     }
-    // boundaries: same sort
-    CU(cudaMemsetAsync(w->bstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));
-    if (B) {
+    // boundaries: same sort — reused while neither the boundaries nor the cell mapping changed (static tanks)
+    const int gridkey[6] = {w->hc.ox, w->hc.oy, w->hc.oz, w->hc.nx, w->hc.ny, w->hc.nz};
+    const bool reuse_b = w->b_sorted_valid && memcmp(gridkey, w->b_sorted_grid, sizeof gridkey) == 0;
+    w->b_reused = reuse_b;
+    if (!reuse_b) CU(cudaMemsetAsync(w->bstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));
+    if (B && !reuse_b) {
         LAUNCH(k_cell_hist, B, 256, w->bpos[bc].p, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p);
         TRY(scan_exclusive(w, w->bstart.p, ncell + 1));
         LAUNCH(k_cell_scatter, B, 256, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p, w->bperm.p);
@@ -620,6 +646,10 @@ sph_status phase_grid(sph_world* w) {
         g.n1 = 1;
         LAUNCH(k_gather, B, 256, (uint32_t)B, w->bperm.p, g);
         w->bcur = bc ^ 1;
+    }
+    if (!reuse_b) {
+        memcpy(w->b_sorted_grid, gridkey, sizeof gridkey);
+        w->b_sorted_valid = true;
     }
     CU(cudaGetLastError());
     if (w->slab.active) {
@@ -688,9 +718,12 @@ sph_status phase_neighbors(sph_world* w) {
     size_t N = w->N, B = w->B;
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1;
-    if (B) {  // compute_boundary_volumes dfsph_solver.rs:72-96 (every substep, as the reference)
-        LAUNCH(k_boundary_volumes, B, 128, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->bvol.p, w->d_cnt.p, w->d_scal.p + 7);
-        LAUNCH(k_set_w, B, 256, (uint32_t)B, w->bpos[bc].p, w->bvol.p);
+    if (B) {  // compute_boundary_volumes dfsph_solver.rs:72-96: the reference recomputes them every substep; they only
+              // depend on the boundary positions, so they are reused while the boundaries are unchanged
+        if (!w->b_reused) {
+            LAUNCH(k_boundary_volumes, B, 128, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->bvol.p, w->d_cnt.p, w->d_scal.p + 7);
+            LAUNCH(k_set_w, B, 256, (uint32_t)B, w->bpos[bc].p, w->bvol.p);
+        }
         for (auto& b : w->bounds)
             if (b.want_forces) {
                 CU(cudaMemsetAsync(w->bforce.p, 0, 3 * B * sizeof(float), w->st));
@@ -1228,7 +1261,8 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
     CU(cudaMemcpyAsync(cnts, w->d_cnt.p, sizeof cnts, cudaMemcpyDeviceToHost, w->st));
     CU(cudaStreamSynchronize(w->st));
     CU(cudaGetLastError());
-    w->stats.n_contacts = cnts[0] + cnts[1];
+    if (!w->b_reused) w->bb_contacts = cnts[0];
+    w->stats.n_contacts = w->bb_contacts + cnts[1];
     w->stats.kernel_launches = w->launches;
     w->stats.n_ghost_particles = (uint32_t)(w->Ntot - w->N);
     w->stats.n_migrated = w->slab.migrated_in + w->slab.migrated_out;

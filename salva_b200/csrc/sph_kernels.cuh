@@ -164,13 +164,31 @@ __global__ void k_bounds(const float4* __restrict__ pos, uint32_t n, int* __rest
         }
     }
     bad = __any_sync(0xffffffffu, bad);
-    if ((threadIdx.x & 31) == 0) {
+    __shared__ int s_mn[3][8], s_mx[3][8], s_bad[8];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(&out[a], mn[a]);
-            atomicMax(&out[3 + a], mx[a]);
+            s_mn[a][wid] = mn[a];
+            s_mx[a][wid] = mx[a];
         }
-        if (bad) atomicOr(&out[6], 1);
+        s_bad[wid] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {  // one atomic pair per axis per block
+        int a = threadIdx.x, nw = (blockDim.x + 31) >> 5;
+        int m0 = INT_MAX, m1 = INT_MIN;
+        for (int k = 0; k < nw; ++k) {
+            m0 = min(m0, s_mn[a][k]);
+            m1 = max(m1, s_mx[a][k]);
+        }
+        atomicMin(&out[a], m0);
+        atomicMax(&out[3 + a], m1);
+        if (a == 0) {
+            int b = 0;
+            for (int k = 0; k < nw; ++k) b |= s_bad[k];
+            if (b) atomicOr(&out[6], 1);
+        }
     }
 }
 

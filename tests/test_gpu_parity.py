@@ -256,6 +256,32 @@ def test_boundary_forces_accumulate_like_reference(backend):
     assert _rel(fgp, fcp) <= 1e-3
 
 
+def test_boundary_rewrite_between_steps():
+    """CouplingManager::update_boundaries rewrites boundary particles every substep (coupling_manager.rs:12-20);
+    the engine caches the boundary sort / volumes only while they are unchanged."""
+    sc = _small_scene(seed=19, forces=(scenes.xsph_viscosity(0.5, 0.3),))
+    gpu, cpu, fg, fc, bg, bc = _pair(sc)
+    tank = sc["boundaries"][0]["positions"]
+    for w in (gpu, cpu):
+        w.force_iterations(1, 2)
+    for k in range(6):
+        if k in (2, 3, 5):
+            shift = np.array([0.004 * k, 0.002 * k, -0.003 * k], np.float32)
+            vel = np.tile(np.array([0.8, 0.4, -0.6], np.float32), (len(tank), 1))
+            for w, b in ((gpu, bg[0]), (cpu, bc[0])):
+                w.write_boundary(b, positions=(tank + shift).astype(np.float32), velocities=vel)
+        gpu.step(0.005)
+        cpu.step(0.005)
+    pg, vg = gpu.read_fluid(fg[0])
+    pc, vc = cpu.read_fluid(fc[0])
+    volg, _ = gpu.read_boundary(bg[0])
+    volc, _ = cpu.read_boundary(bc[0])
+    assert _rel(volg, volc) <= 1e-5
+    assert np.array_equal(gpu.debug(fg[0], "num_boundary_contacts"), cpu.debug(fc[0], "num_boundary_contacts"))
+    assert np.abs(pg - pc).max() <= 1e-3 * float(gpu.h)
+    assert gpu.stats()["n_contacts"] == cpu.stats()["n_contacts"]
+
+
 def test_deterministic_mode_is_bit_reproducible():
     sc = _small_scene(seed=21)
     outs = []
