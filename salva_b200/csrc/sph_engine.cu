@@ -93,6 +93,11 @@ sph_status iisph_step(sph_world* w, float dt_total, const float g[3]);
 sph_status slab_begin_step(sph_world* w);
 sph_status slab_after_sort(sph_world* w);
 sph_status slab_refresh(sph_world* w, void* array, size_t elem);
+struct SlabArray {
+    void* p;
+    size_t elem;
+};
+sph_status slab_refresh_n(sph_world* w, const SlabArray* arrays, int n_arrays);
 sph_status slab_allreduce(sph_world* w, float* buf, size_t n);
 void iisph_release(sph_world* w);
 void slab_release(sph_world* w);
@@ -843,15 +848,21 @@ sph_status ensure_tex(sph_world* w, cudaTextureObject_t* tex, const void** cur, 
     return SPH_OK;
 }
 
-// ghost refresh of v* in whichever representation the evaluations gather
+// ghost refresh of v* in whichever representation the evaluations gather (one NCCL group); vs itself is included
+// because the velocity fold reads vel = v* for ghosts too
 sph_status refresh_vstar(sph_world* w) {
     if (!w->slab.active) return SPH_OK;
     if (w->unimass) {
-        TRY(slab_refresh(w, w->pvx4.p, sizeof(float4)));
-        TRY(slab_refresh(w, w->vyz2.p, sizeof(float2)));
-        return SPH_OK;
+        SlabArray a[3] = {{w->pvx4.p, sizeof(float4)}, {w->vyz2.p, sizeof(float2)}, {w->vs.p, sizeof(float4)}};
+        return slab_refresh_n(w, a, 3);
     }
     return slab_refresh(w, w->vs.p, sizeof(float4));
+}
+// ghost refresh of the evaluation's output (kappa) — only needed when an update follows
+sph_status refresh_kappa(sph_world* w) {
+    if (!w->slab.active) return SPH_OK;
+    if (w->unimass) return slab_refresh(w, w->pk4.p, sizeof(float4));
+    return slab_refresh(w, w->kappa.p, sizeof(float));
 }
 
 sph_status launch_density_alpha(sph_world* w) {
@@ -890,9 +901,10 @@ sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
                    w->bpos[bc].p, L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, w->partial.p, w->d_scal.p + 7);
     }
     *nblk = cdiv(N, PASS_T);
-    TRY(slab_refresh(w, w->dens.p, sizeof(float)));
-    if (w->unimass) TRY(slab_refresh(w, w->pk4.p, sizeof(float4)));
-    else TRY(slab_refresh(w, w->kappa.p, sizeof(float)));
+    if (w->slab.active) {
+        SlabArray a[2] = {{w->dens.p, sizeof(float)}, {w->unimass ? (void*)w->pk4.p : (void*)w->kappa.p, w->unimass ? sizeof(float4) : sizeof(float)}};
+        TRY(slab_refresh_n(w, a, 2));
+    }
     return SPH_OK;
 }
 
@@ -951,7 +963,6 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
                         w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
         }
         *nblk = cdiv(N, PASS_T);
-        TRY(slab_refresh(w, w->pk4.p, sizeof(float4)));  // the following update gathers (x, kappa) of ghosts
         return SPH_OK;
     } else {
         Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
@@ -960,7 +971,6 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
               w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
         *nblk = cdiv(N, PASS_T);
     }
-    TRY(slab_refresh(w, w->kappa.p, sizeof(float)));  // the following update gathers kappa_j of ghosts
     return SPH_OK;
 }
 // compute_velocity_changes_for_divergence (pressure = false) / compute_velocity_changes (pressure = true)
@@ -1109,6 +1119,7 @@ sph_status jacobi_loop_device(sph_world* w, bool pressure, bool first_eval_done,
             TRY(slab_allreduce(w, w->errsum.p, nf));
             k_loop_decide<<<1, 32, 0, w->st>>>(w->d_ctl.p, w->errsum.p);
             w->launches++;
+            TRY(refresh_kappa(w));
             TRY(span_begin(w, pressure ? SP_PUPD : SP_DIV_UPD));
             TRY(launch_vel_update(w, pressure, g_update));
             TRY(span_end(w));
@@ -1158,6 +1169,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
             float max_err = w->desc.max_divergence_error * w->inv_dt * 0.01f;
             if (avg <= max_err && i >= w->desc.min_divergence_iter) break;
         }
+        if (!(i == 0 && w->fused_first_div)) TRY(refresh_kappa(w));  // the update gathers kappa_j of ghosts
         TRY(span_begin(w, SP_DIV_UPD));
         TRY(launch_vel_update(w, false));
         TRY(span_end(w));
@@ -1165,7 +1177,6 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     }
     CU(cudaEventRecord(w->ev[EV_DIV], w->st));
     // update_velocities :422-430, zero vc :689-691, acc += gravity :574-578
-    if (w->unimass) TRY(slab_refresh(w, w->vs.p, sizeof(float4)));  // ghosts' v* in vs form (the fold reads vel = v*)
     LAUNCH(k_fold_velocities, w->Ntot, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2]);  // ghosts too (vel = v*)
     CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
     TRY(phase_forces(w));
@@ -1196,6 +1207,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
             w->stats.last_density_error = avg;
             if (avg <= w->desc.max_density_error && i >= w->desc.min_pressure_iter) break;
         }
+        TRY(refresh_kappa(w));
         TRY(span_begin(w, SP_PUPD));
         TRY(launch_vel_update(w, true));
         TRY(span_end(w));

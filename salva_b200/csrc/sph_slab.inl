@@ -85,24 +85,31 @@ inline bool slab_on(const sph_world* w) { return w->slab.active; }
 inline int slab_left(const sph_world* w) { return w->slab.rank > 0 ? w->slab.rank - 1 : -1; }
 inline int slab_right(const sph_world* w) { return w->slab.rank + 1 < w->slab.nranks ? w->slab.rank + 1 : -1; }
 
-// Per-iteration ghost refresh of one per-particle array (elem = bytes per particle): my boundary columns go to the
-// neighbours, their boundary columns land in my ghost ranges.  Contiguous ranges, no packing.
-sph_status slab_refresh(sph_world* w, void* array, size_t elem) {
+// Per-iteration ghost refresh of up to 4 per-particle arrays in ONE NCCL group (elem = bytes per particle): my boundary
+// columns go to the neighbours, their boundary columns land in my ghost ranges.  Contiguous ranges, no packing.
+sph_status slab_refresh_n(sph_world* w, const SlabArray* arrays, int n_arrays) {
     if (!slab_on(w)) return SPH_OK;
     SlabState& S = w->slab;
-    char* a = static_cast<char*>(array);
     NC(g_nccl.GroupStart());
-    if (slab_left(w) >= 0) {
-        if (S.sl_count) NC(g_nccl.Send(a + (size_t)S.sl_begin * elem, (size_t)S.sl_count * elem, NCCL_CHAR, slab_left(w), S.comm, w->st));
-        if (S.gl_count) NC(g_nccl.Recv(a, (size_t)S.gl_count * elem, NCCL_CHAR, slab_left(w), S.comm, w->st));
-    }
-    if (slab_right(w) >= 0) {
-        if (S.sr_count) NC(g_nccl.Send(a + (size_t)S.sr_begin * elem, (size_t)S.sr_count * elem, NCCL_CHAR, slab_right(w), S.comm, w->st));
-        if (S.gr_count) NC(g_nccl.Recv(a + (size_t)S.gr_begin * elem, (size_t)S.gr_count * elem, NCCL_CHAR, slab_right(w), S.comm, w->st));
+    for (int k = 0; k < n_arrays; ++k) {
+        char* a = static_cast<char*>(arrays[k].p);
+        const size_t elem = arrays[k].elem;
+        if (slab_left(w) >= 0) {
+            if (S.sl_count) NC(g_nccl.Send(a + (size_t)S.sl_begin * elem, (size_t)S.sl_count * elem, NCCL_CHAR, slab_left(w), S.comm, w->st));
+            if (S.gl_count) NC(g_nccl.Recv(a, (size_t)S.gl_count * elem, NCCL_CHAR, slab_left(w), S.comm, w->st));
+        }
+        if (slab_right(w) >= 0) {
+            if (S.sr_count) NC(g_nccl.Send(a + (size_t)S.sr_begin * elem, (size_t)S.sr_count * elem, NCCL_CHAR, slab_right(w), S.comm, w->st));
+            if (S.gr_count) NC(g_nccl.Recv(a + (size_t)S.gr_begin * elem, (size_t)S.gr_count * elem, NCCL_CHAR, slab_right(w), S.comm, w->st));
+        }
     }
     NC(g_nccl.GroupEnd());
     w->stats_exchanges++;
     return SPH_OK;
+}
+sph_status slab_refresh(sph_world* w, void* array, size_t elem) {
+    SlabArray a{array, elem};
+    return slab_refresh_n(w, &a, 1);
 }
 
 // Sum a small device float buffer over all ranks (error means of the Jacobi loops: dfsph_solver.rs:153-158).
