@@ -97,7 +97,8 @@ struct SlabArray {
     void* p;
     size_t elem;
 };
-sph_status slab_refresh_n(sph_world* w, const SlabArray* arrays, int n_arrays);
+sph_status slab_refresh_n(sph_world* w, const SlabArray* arrays, int n_arrays, cudaStream_t st = nullptr);
+sph_status slab_wait(sph_world* w);
 sph_status slab_allreduce(sph_world* w, float* buf, size_t n);
 void iisph_release(sph_world* w);
 void slab_release(sph_world* w);
@@ -120,6 +121,10 @@ struct SlabState {
     DBuf<unsigned long long> d_cnt64;
     DBuf<float4> out_l[3], out_r[3], col_l[3], col_r[3];
     bool global_valid = false;
+    // exchange / compute overlap: boundary columns first, their exchange on comm_st behind the interior launch
+    bool overlap = false, pending = false;  // measured (2xB200): 1.687 ms with overlap vs 1.660 without — the step is host-launch bound there
+    cudaStream_t comm_st = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     // slot ranges of the current step (after the sort)
     uint32_t gl_count = 0, sl_begin = 0, sl_count = 0, sr_begin = 0, sr_count = 0, gr_begin = 0, gr_count = 0;
     uint32_t exp_ghost_l = 0, exp_ghost_r = 0, exp_send_l = 0, exp_send_r = 0;
@@ -860,7 +865,7 @@ sph_status refresh_vstar(sph_world* w) {
 }
 // ghost refresh of the evaluation's output (kappa) — only needed when an update follows
 sph_status refresh_kappa(sph_world* w) {
-    if (!w->slab.active) return SPH_OK;
+    if (!w->slab.active || w->slab.overlap) return SPH_OK;  // overlap mode: the evaluation exchanged kappa speculatively
     if (w->unimass) return slab_refresh(w, w->pk4.p, sizeof(float4));
     return slab_refresh(w, w->kappa.p, sizeof(float));
 }
@@ -882,61 +887,112 @@ sph_status launch_density_alpha(sph_world* w) {
     return SPH_OK;
 }
 // DFSPH: densities + alphas + the first divergence evaluation in one sweep (k_density_alpha_div)
-sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
-    size_t N = w->N;
-    int c = w->cur, bc = w->bcur;
-    const bool multi = w->fluids.size() > 1;
-    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
-    if (w->unimass) {
-        TRY(ensure_tex(w, &w->tex_vyz, &w->tex_vyz_ptr, w->vyz2.p, w->vyz2.cap));
-        LAUNCH((k_density_alpha_div<false, true>), N, PASS_T, w->pvx4.p, w->vs.p, (cudaTextureObject_t)0, w->vyz2.p, w->tex_vyz, w->vel[c].p, w->bpos[bc].p, L,
-               w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, w->partial.p, w->d_scal.p + 7);
-    } else {
-        TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
-        if (multi)
-            LAUNCH((k_density_alpha_div<true, false>), N, PASS_T, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p,
-                   w->bpos[bc].p, L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, w->partial.p, w->d_scal.p + 7);
-        else
-            LAUNCH((k_density_alpha_div<false, false>), N, PASS_T, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p,
-                   w->bpos[bc].p, L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, w->partial.p, w->d_scal.p + 7);
-    }
-    *nblk = cdiv(N, PASS_T);
-    if (w->slab.active) {
-        SlabArray a[2] = {{w->dens.p, sizeof(float)}, {w->unimass ? (void*)w->pk4.p : (void*)w->kappa.p, w->unimass ? sizeof(float4) : sizeof(float)}};
-        TRY(slab_refresh_n(w, a, 2));
+// Launch over a slot range with n = range count (kernels index rg.begin + thread)
+#define LAUNCH_R(kern, rg, ...)                                                                   \
+    do {                                                                                          \
+        if ((rg).count > 0) {                                                                     \
+            kern<<<cdiv((rg).count, PASS_T), PASS_T, 0, w->st>>>(__VA_ARGS__, (rg));              \
+            w->launches++;                                                                        \
+        }                                                                                         \
+    } while (0)
+
+#define BOOL3(kern, b0, b1, b2, n, ...)                                                   \
+    do {                                                                                           \
+        if (b0) {                                                                                  \
+            if (b1) { if (b2) LAUNCH_R((kern<true, true, true>), n, __VA_ARGS__); else LAUNCH_R((kern<true, true, false>), n, __VA_ARGS__); } \
+            else    { if (b2) LAUNCH_R((kern<true, false, true>), n, __VA_ARGS__); else LAUNCH_R((kern<true, false, false>), n, __VA_ARGS__); } \
+        } else {                                                                                   \
+            if (b1) { if (b2) LAUNCH_R((kern<false, true, true>), n, __VA_ARGS__); else LAUNCH_R((kern<false, true, false>), n, __VA_ARGS__); } \
+            else    { if (b2) LAUNCH_R((kern<false, false, true>), n, __VA_ARGS__); else LAUNCH_R((kern<false, false, false>), n, __VA_ARGS__); } \
+        }                                                                                          \
+    } while (0)
+#define BOOL4(kern, b0, b1, b2, b3, n, ...)                                               \
+    do {                                                                                           \
+        if (b3) BOOL3_T(kern, b0, b1, b2, true, n, __VA_ARGS__);                          \
+        else BOOL3_T(kern, b0, b1, b2, false, n, __VA_ARGS__);                            \
+    } while (0)
+#define BOOL3_T(kern, b0, b1, b2, B3, n, ...)                                             \
+    do {                                                                                           \
+        if (b0) {                                                                                  \
+            if (b1) { if (b2) LAUNCH_R((kern<true, true, true, B3>), n, __VA_ARGS__); else LAUNCH_R((kern<true, true, false, B3>), n, __VA_ARGS__); } \
+            else    { if (b2) LAUNCH_R((kern<true, false, true, B3>), n, __VA_ARGS__); else LAUNCH_R((kern<true, false, false, B3>), n, __VA_ARGS__); } \
+        } else {                                                                                   \
+            if (b1) { if (b2) LAUNCH_R((kern<false, true, true, B3>), n, __VA_ARGS__); else LAUNCH_R((kern<false, true, false, B3>), n, __VA_ARGS__); } \
+            else    { if (b2) LAUNCH_R((kern<false, false, true, B3>), n, __VA_ARGS__); else LAUNCH_R((kern<false, false, false, B3>), n, __VA_ARGS__); } \
+        }                                                                                          \
+    } while (0)
+
+
+// ---- slot ranges of a launch and the producer/exchange overlap of a slab world ---------------------------------------
+// A pass that PRODUCES data its neighbours' ghosts need (kappa after an evaluation, v* after an update) is launched on
+// the two boundary columns first; their exchange then runs on the communication stream while the interior launch
+// proceeds on the main stream.  Every pass waits for the previous exchange before it reads ghost slots.
+sph_status slab_wait(sph_world* w) {
+    SlabState& S = w->slab;
+    if (S.pending) {
+        CU(cudaStreamWaitEvent(w->st, S.ev_done, 0));
+        S.pending = false;
     }
     return SPH_OK;
 }
+template <class Fn>  // fn(Range rg, uint32_t first_partial_block) -> sph_status
+sph_status run_parts(sph_world* w, const SlabArray* arrays, int n_arrays, uint32_t* nblk_total, Fn fn) {
+    SlabState& S = w->slab;
+    TRY(slab_wait(w));
+    uint32_t off = 0;
+    auto part = [&](uint32_t b, uint32_t cnt) -> sph_status {
+        if (!cnt) return SPH_OK;
+        TRY(fn(Range{b, cnt}, off));
+        off += cdiv(cnt, PASS_T);
+        return SPH_OK;
+    };
+    const uint32_t N = (uint32_t)w->N;
+    if (!S.active || !S.overlap || n_arrays == 0) {
+        TRY(part(w->own_begin, N));
+        if (S.active && n_arrays) TRY(slab_refresh_n(w, arrays, n_arrays));
+    } else {
+        TRY(part(S.sl_begin, S.sl_count));
+        TRY(part(S.sr_begin, S.sr_count));
+        CU(cudaEventRecord(S.ev_ready, w->st));
+        CU(cudaStreamWaitEvent(S.comm_st, S.ev_ready, 0));
+        TRY(slab_refresh_n(w, arrays, n_arrays, S.comm_st));
+        CU(cudaEventRecord(S.ev_done, S.comm_st));
+        S.pending = true;
+        const uint32_t ib = S.sl_begin + S.sl_count, ie = S.has_right ? S.sr_begin : w->own_begin + N;
+        TRY(part(ib, ie > ib ? ie - ib : 0));
+    }
+    if (nblk_total) *nblk_total = off;
+    return SPH_OK;
+}
 
-#define BOOL3(kern, b0, b1, b2, n, threads, ...)                                                   \
-    do {                                                                                           \
-        if (b0) {                                                                                  \
-            if (b1) { if (b2) LAUNCH((kern<true, true, true>), n, threads, __VA_ARGS__); else LAUNCH((kern<true, true, false>), n, threads, __VA_ARGS__); } \
-            else    { if (b2) LAUNCH((kern<true, false, true>), n, threads, __VA_ARGS__); else LAUNCH((kern<true, false, false>), n, threads, __VA_ARGS__); } \
-        } else {                                                                                   \
-            if (b1) { if (b2) LAUNCH((kern<false, true, true>), n, threads, __VA_ARGS__); else LAUNCH((kern<false, true, false>), n, threads, __VA_ARGS__); } \
-            else    { if (b2) LAUNCH((kern<false, false, true>), n, threads, __VA_ARGS__); else LAUNCH((kern<false, false, false>), n, threads, __VA_ARGS__); } \
-        }                                                                                          \
-    } while (0)
-#define BOOL4(kern, b0, b1, b2, b3, n, threads, ...)                                               \
-    do {                                                                                           \
-        if (b3) BOOL3_T(kern, b0, b1, b2, true, n, threads, __VA_ARGS__);                          \
-        else BOOL3_T(kern, b0, b1, b2, false, n, threads, __VA_ARGS__);                            \
-    } while (0)
-#define BOOL3_T(kern, b0, b1, b2, B3, n, threads, ...)                                             \
-    do {                                                                                           \
-        if (b0) {                                                                                  \
-            if (b1) { if (b2) LAUNCH((kern<true, true, true, B3>), n, threads, __VA_ARGS__); else LAUNCH((kern<true, true, false, B3>), n, threads, __VA_ARGS__); } \
-            else    { if (b2) LAUNCH((kern<true, false, true, B3>), n, threads, __VA_ARGS__); else LAUNCH((kern<true, false, false, B3>), n, threads, __VA_ARGS__); } \
-        } else {                                                                                   \
-            if (b1) { if (b2) LAUNCH((kern<false, true, true, B3>), n, threads, __VA_ARGS__); else LAUNCH((kern<false, true, false, B3>), n, threads, __VA_ARGS__); } \
-            else    { if (b2) LAUNCH((kern<false, false, true, B3>), n, threads, __VA_ARGS__); else LAUNCH((kern<false, false, false, B3>), n, threads, __VA_ARGS__); } \
-        }                                                                                          \
-    } while (0)
+// DFSPH: densities + alphas + the first divergence evaluation in one sweep (k_density_alpha_div)
+sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
+    int c = w->cur, bc = w->bcur;
+    const bool multi = w->fluids.size() > 1;
+    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
+    if (w->unimass) TRY(ensure_tex(w, &w->tex_vyz, &w->tex_vyz_ptr, w->vyz2.p, w->vyz2.cap));
+    else TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
+    const size_t nf = std::max<size_t>(1, w->fluids.size());
+    SlabArray a[2] = {{w->dens.p, sizeof(float)}, {w->unimass ? (void*)w->pk4.p : (void*)w->kappa.p, w->unimass ? sizeof(float4) : sizeof(float)}};
+    return run_parts(w, a, 2, nblk, [&](Range rg, uint32_t blk) -> sph_status {
+        float* partial = w->partial.p + (size_t)blk * nf;
+        if (w->unimass)
+            LAUNCH_R((k_density_alpha_div<false, true>), rg, w->pvx4.p, w->vs.p, (cudaTextureObject_t)0, w->vyz2.p, w->tex_vyz, w->vel[c].p, w->bpos[bc].p, L,
+                     w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7);
+        else if (multi)
+            LAUNCH_R((k_density_alpha_div<true, false>), rg, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p, w->bpos[bc].p,
+                     L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7);
+        else
+            LAUNCH_R((k_density_alpha_div<false, false>), rg, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p, w->bpos[bc].p,
+                     L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7);
+        return SPH_OK;
+    });
+}
 
-// compute_divergences (predict = false) / compute_predicted_densities (predict = true); returns #partials
+// compute_divergences (predict = false) / compute_predicted_densities (predict = true); returns #partials.
+// In a slab world with overlap the kappa ghosts are exchanged speculatively (the evaluation may turn out to be the
+// loop's last one) behind the interior launch; otherwise refresh_kappa() does it only when an update follows.
 sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, const int* gate = nullptr) {
-    size_t N = w->N;
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1;
     if (w->tile) {
@@ -945,37 +1001,43 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
         TDISPATCH2(k_tile_vel_divergence, multi, predict, 32, cap, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, w->cstart.p, cap, L,
                    w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
         *nblk = w->n_tiles;
-    } else if (w->unimass) {
-        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
+        return SPH_OK;
+    }
+    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
+    if (w->unimass) {
         TRY(ensure_tex(w, &w->tex_pvx, &w->tex_pvx_ptr, w->pvx4.p, w->pvx4.cap));
         TRY(ensure_tex(w, &w->tex_vyz, &w->tex_vyz_ptr, w->vyz2.p, w->vyz2.cap));
-        float* out = predict ? w->pred.p : w->divv.p;
-        const bool ptex = w->uni_eval_mode == 1;
-        if (predict) {
-            if (ptex) LAUNCH((k_vel_divergence_u<true, true>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                             w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
-            else LAUNCH((k_vel_divergence_u<true, false>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                        w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
-        } else {
-            if (ptex) LAUNCH((k_vel_divergence_u<false, true>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                             w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
-            else LAUNCH((k_vel_divergence_u<false, false>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                        w->dens.p, w->alpha.p, out, w->pk4.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
-        }
-        *nblk = cdiv(N, PASS_T);
-        return SPH_OK;
-    } else {
-        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
-        if (w->use_tex) TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
-        BOOL3(k_vel_divergence, multi, predict, w->use_tex, N, PASS_T, w->pos[c].p, w->vs.p, w->tex_vs, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L,
-              w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7, gate);
-        *nblk = cdiv(N, PASS_T);
+    } else if (w->use_tex) {
+        TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
     }
-    return SPH_OK;
+    float* out = predict ? w->pred.p : w->divv.p;
+    const size_t nf = std::max<size_t>(1, w->fluids.size());
+    SlabArray a[1] = {{w->unimass ? (void*)w->pk4.p : (void*)w->kappa.p, w->unimass ? sizeof(float4) : sizeof(float)}};
+    const int n_arrays = (w->slab.active && w->slab.overlap) ? 1 : 0;
+    return run_parts(w, a, n_arrays, nblk, [&](Range rg, uint32_t blk) -> sph_status {
+        float* partial = w->partial.p + (size_t)blk * nf;
+        if (w->unimass) {
+            const bool ptex = w->uni_eval_mode == 1;
+            if (predict) {
+                if (ptex) LAUNCH_R((k_vel_divergence_u<true, true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
+                                   w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate);
+                else LAUNCH_R((k_vel_divergence_u<true, false>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
+                              w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate);
+            } else {
+                if (ptex) LAUNCH_R((k_vel_divergence_u<false, true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
+                                   w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate);
+                else LAUNCH_R((k_vel_divergence_u<false, false>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
+                              w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate);
+            }
+        } else {
+            BOOL3(k_vel_divergence, multi, predict, w->use_tex, rg, w->pos[c].p, w->vs.p, w->tex_vs, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p,
+                  w->alpha.p, out, w->kappa.p, partial, w->dt, w->d_scal.p + 7, gate);
+        }
+        return SPH_OK;
+    });
 }
 // compute_velocity_changes_for_divergence (pressure = false) / compute_velocity_changes (pressure = true)
 sph_status launch_vel_update(sph_world* w, bool pressure, const int* gate = nullptr) {
-    size_t N = w->N;
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1, bf = any_bforce(w);
     if (w->tile) {
@@ -987,24 +1049,25 @@ sph_status launch_vel_update(sph_world* w, bool pressure, const int* gate = null
         else
             TDISPATCH3(k_tile_vel_update, multi, bf, false, 20, cap, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->cstart.p, cap, L, w->kappa.p, w->vc[c].p,
                        w->vs.p, w->bforce.p, w->inv_dt);
-    } else if (w->unimass) {
-        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
-        TRY(ensure_tex(w, &w->tex_pk, &w->tex_pk_ptr, w->pk4.p, w->pk4.cap));
-        const bool ptex = w->uni_upd_mode == 1;
-        BOOL3(k_vel_update_u, bf, pressure, ptex, N, PASS_T, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p,
-              w->vyz2.p, w->bforce.p, w->inv_dt, gate);
-        TRY(refresh_vstar(w));
         return SPH_OK;
-    } else {
-        Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
-        // measured (profiles/r1_v1_*): the texture pipe helps the float4 v* gather (-12 %) but not the 4-byte kappa gather
-        const bool tex = false;
-        if (tex) TRY(ensure_tex(w, &w->tex_kappa, &w->tex_kappa_ptr, w->kappa.p, w->kappa.cap));
-        BOOL4(k_vel_update, multi, bf, pressure, tex, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->tex_kappa,
-              w->vc[c].p, w->vs.p, w->bforce.p, w->inv_dt, gate);
     }
-    TRY(slab_refresh(w, w->vs.p, sizeof(float4)));  // the following evaluation gathers v*_j of ghosts
-    return SPH_OK;
+    Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
+    if (w->unimass) TRY(ensure_tex(w, &w->tex_pk, &w->tex_pk_ptr, w->pk4.p, w->pk4.cap));
+    // the following evaluation gathers v*_j of ghosts (vs itself too: the velocity fold reads vel = v* for ghosts)
+    SlabArray a[3] = {{w->pvx4.p, sizeof(float4)}, {w->vyz2.p, sizeof(float2)}, {w->vs.p, sizeof(float4)}};
+    SlabArray a1[1] = {{w->vs.p, sizeof(float4)}};
+    return run_parts(w, w->unimass ? a : a1, w->unimass ? 3 : 1, nullptr, [&](Range rg, uint32_t) -> sph_status {
+        if (w->unimass) {
+            const bool ptex = w->uni_upd_mode == 1;
+            BOOL3(k_vel_update_u, bf, pressure, ptex, rg, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p,
+                  w->bforce.p, w->inv_dt, gate);
+        } else {
+            // measured (profiles/r1_v1_*): the texture pipe helps the float4 v* gather (-12 %) but not the 4-byte kappa gather
+            BOOL4(k_vel_update, multi, bf, pressure, false, rg, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->tex_kappa, w->vc[c].p, w->vs.p,
+                  w->bforce.p, w->inv_dt, gate);
+        }
+        return SPH_OK;
+    });
 }
 
 // predict_advection dfsph_solver.rs:580-603: every fluid's forces in push order
@@ -1177,6 +1240,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     }
     CU(cudaEventRecord(w->ev[EV_DIV], w->st));
     // update_velocities :422-430, zero vc :689-691, acc += gravity :574-578
+    TRY(slab_wait(w));
     LAUNCH(k_fold_velocities, w->Ntot, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2]);  // ghosts too (vel = v*)
     CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
     TRY(phase_forces(w));
@@ -1214,6 +1278,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
         w->stats.n_pressure_iter++;
     }
     CU(cudaEventRecord(w->ev[EV_PRESS], w->st));
+    TRY(slab_wait(w));  // a speculative exchange may still be in flight: it must land before the arrays are reused
     LAUNCH(k_update_positions, N, 256, w->pos[c].p, w->vs.p, w->dt);  // :411-420
     CU(cudaGetLastError());
     return SPH_OK;
@@ -1738,6 +1803,14 @@ static sph_status slab_attach(sph_world* w, void* comm, bool own, int rank, int 
     w->desc.deterministic = 1;  // ghost-column order agreement relies on the stable in-cell order
     CU(S.d_cnt.ensure(32));
     CU(S.d_cnt64.ensure(1));
+    if (!S.comm_st) {
+        int lo_pri = 0, hi_pri = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CU(cudaStreamCreateWithPriority(&S.comm_st, cudaStreamNonBlocking, hi_pri));
+        CU(cudaEventCreateWithFlags(&S.ev_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+    }
+    if (const char* t = getenv("SALVA_B200_SLAB_OVERLAP")) S.overlap = atoi(t) != 0;
     return SPH_OK;
 }
 

@@ -23,6 +23,26 @@ struct Lists {
 
 struct NoAux {};
 
+// Slot range a launch covers.  One launch normally covers all owned slots; a slab world splits the Jacobi-loop kernels
+// into [boundary columns] + [interior] so the ghost exchange of the boundary columns overlaps the interior launch.
+struct Range {
+    uint32_t begin, count;
+};
+
+// The contact lists are streamed exactly once per pass: load them with the evict-first policy so they do not push the
+// gathered particle data out of L1/L2, and pull the rows a few groups ahead into L2 (each group row of a warp is a
+// separate 512-byte segment `stride` elements apart, which no hardware prefetcher follows).
+#ifndef SPH_LIST_PREFETCH
+#define SPH_LIST_PREFETCH 0
+#endif
+__device__ __forceinline__ uint4 ld_list(const uint4* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_list(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void prefetch_list(const void* p) {
+#if SPH_LIST_PREFETCH > 0
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 // ldpos(j) -> float4 whose xyz is the neighbour position (w = whatever the array packs there); ld(j) -> Aux loads
 // whatever else the pass needs from neighbour j; ff(j, pair, posrec_j, aux) consumes one contact.
 template <bool W, bool G, class LP, class LD, class FF>
@@ -30,10 +50,11 @@ __device__ __forceinline__ void for_fluid_contacts_g(uint32_t i, const float4& p
     const uint32_t n = min(L.cnt_f[i], C.cap_f);
     const uint32_t nq = (n + 3u) >> 2;
     const uint4* col = L.nbr_f + i;
-    uint4 J = nq ? __ldg(col) : make_uint4(i, i, i, i);
+    uint4 J = nq ? ld_list(col) : make_uint4(i, i, i, i);
     for (uint32_t q = 0; q < nq; ++q) {
         uint4 Jn = J;
-        if (q + 1 < nq) Jn = __ldg(col + (size_t)(q + 1) * C.stride);  // prefetch the next group of indices
+        if (q + 1 < nq) Jn = ld_list(col + (size_t)(q + 1) * C.stride);  // fetch the next group of indices early
+        if (q + 1 + SPH_LIST_PREFETCH < nq) prefetch_list(col + (size_t)(q + 1 + SPH_LIST_PREFETCH) * C.stride);
         uint32_t j[4] = {J.x, J.y, J.z, J.w};
         const uint32_t k0 = q * 4u;
         bool ok[4];
@@ -74,15 +95,16 @@ __device__ __forceinline__ void for_fluid_grads(uint32_t i, const float4& pi, co
     const bool cached = C.use_gcache != 0;
     const uint4* col = L.nbr_f + i;
     const float4* gcol = L.g_f + i;
-    uint4 J = __ldg(col);
-    float4 Gq = cached ? __ldg(gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 J = ld_list(col);
+    float4 Gq = cached ? ld_list(gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t q = 0; q < nq; ++q) {
         uint4 Jn = J;
         float4 Gn = Gq;
-        if (q + 1 < nq) {  // prefetch the next group
-            Jn = __ldg(col + (size_t)(q + 1) * C.stride);
-            if (cached) Gn = __ldg(gcol + (size_t)(q + 1) * C.stride);
+        if (q + 1 < nq) {  // fetch the next group early
+            Jn = ld_list(col + (size_t)(q + 1) * C.stride);
+            if (cached) Gn = ld_list(gcol + (size_t)(q + 1) * C.stride);
         }
+        if (q + 1 + SPH_LIST_PREFETCH < nq) prefetch_list(col + (size_t)(q + 1 + SPH_LIST_PREFETCH) * C.stride);
         const uint32_t j[4] = {J.x, J.y, J.z, J.w};
         const float g[4] = {Gq.x, Gq.y, Gq.z, Gq.w};
         float4 pj[4];
@@ -171,10 +193,11 @@ k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, 
         const uint32_t n = min(L.cnt_f[i], C.cap_f);
         const uint32_t nq = (n + 3u) >> 2;
         const uint4* col = L.nbr_f + i;
-        uint4 J = nq ? __ldg(col) : make_uint4(i, i, i, i);
+        uint4 J = nq ? ld_list(col) : make_uint4(i, i, i, i);
         for (uint32_t q = 0; q < nq; ++q) {
             uint4 Jn = J;
-            if (q + 1 < nq) Jn = __ldg(col + (size_t)(q + 1) * C.stride);
+            if (q + 1 < nq) Jn = ld_list(col + (size_t)(q + 1) * C.stride);
+            if (q + 1 + SPH_LIST_PREFETCH < nq) prefetch_list(col + (size_t)(q + 1 + SPH_LIST_PREFETCH) * C.stride);
             const uint32_t j[4] = {J.x, J.y, J.z, J.w};
             float4 pj[4];
 #pragma unroll
@@ -226,11 +249,11 @@ __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, const float4* __restrict__ vs, cudaTextureObject_t tvs,
                     const float2* __restrict__ vyz, cudaTextureObject_t tvyz, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
                     float4* __restrict__ g_out, float* __restrict__ dens, float* __restrict__ alpha, float* __restrict__ divv, float* __restrict__ kappa,
-                    float4* __restrict__ pk4, float* __restrict__ partial, int* __restrict__ err) {
+                    float4* __restrict__ pk4, float* __restrict__ partial, int* __restrict__ err, Range rg) {
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < C.n_owned;
-    i += C.i_begin;
+    bool valid = i < rg.count;
+    i += rg.begin;
     float e = 0.f;
     uint32_t fi = 0;
     if (valid) {
@@ -251,10 +274,11 @@ k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, const 
         const uint32_t n = min(L.cnt_f[i], C.cap_f);
         const uint32_t nq = (n + 3u) >> 2;
         const uint4* col = L.nbr_f + i;
-        uint4 J = nq ? __ldg(col) : make_uint4(i, i, i, i);
+        uint4 J = nq ? ld_list(col) : make_uint4(i, i, i, i);
         for (uint32_t q = 0; q < nq; ++q) {
             uint4 Jn = J;
-            if (q + 1 < nq) Jn = __ldg(col + (size_t)(q + 1) * C.stride);
+            if (q + 1 < nq) Jn = ld_list(col + (size_t)(q + 1) * C.stride);
+            if (q + 1 + SPH_LIST_PREFETCH < nq) prefetch_list(col + (size_t)(q + 1 + SPH_LIST_PREFETCH) * C.stride);
             const uint32_t j[4] = {J.x, J.y, J.z, J.w};
             float4 pj[4];
             Vel3 vj[4];
@@ -326,12 +350,12 @@ __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_divergence(const float4* __restrict__ pos, const float4* __restrict__ vs, cudaTextureObject_t tvs, const float4* __restrict__ vel,
                  const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
                  const float* __restrict__ alpha, float* __restrict__ out, float* __restrict__ kappa, float* __restrict__ partial, float dt,
-                 int* __restrict__ err, const int* __restrict__ gate) {
+                 int* __restrict__ err, const int* __restrict__ gate, Range rg) {
     if (gate && !*gate) return;  // device-side loop control: this evaluation is past the break
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < C.n_owned;
-    i += C.i_begin;
+    bool valid = i < rg.count;
+    i += rg.begin;
     float e = 0.f;
     uint32_t fi = 0;
     if (valid) {
@@ -384,9 +408,11 @@ template <bool MULTI, bool BFORCE, bool PRESSURE, bool TEX>
 __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_update(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ kappa,
              cudaTextureObject_t tkappa, float4* __restrict__ vc, float4* __restrict__ vs, float* __restrict__ bforce, float inv_dt,
-             const int* __restrict__ gate) {
+             const int* __restrict__ gate, Range rg) {
     if (gate && !*gate) return;
-    SPH_OWNED_INDEX(i)
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rg.count) return;
+    i += rg.begin;
     float4 pi = pos[i];
     float4 v = vel[i];
     float rho0 = C.fluids[MULTI ? fid_of(v) : 0].density0;
@@ -430,12 +456,12 @@ __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, const float2* __restrict__ vyz, cudaTextureObject_t tvyz,
                    const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
                    const float* __restrict__ alpha, float* __restrict__ out, float4* __restrict__ pk4, float* __restrict__ partial, float dt,
-                   int* __restrict__ err, const int* __restrict__ gate) {
+                   int* __restrict__ err, const int* __restrict__ gate, Range rg) {
     if (gate && !*gate) return;
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < C.n_owned;
-    i += C.i_begin;
+    bool valid = i < rg.count;
+    i += rg.begin;
     float e = 0.f;
     if (valid) {
         const float4 a = pvx[i];
@@ -485,9 +511,11 @@ template <bool BFORCE, bool PRESSURE, bool POS_TEX>
 __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_update_u(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
                float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ pvx, float2* __restrict__ vyz, float* __restrict__ bforce,
-               float inv_dt, const int* __restrict__ gate) {
+               float inv_dt, const int* __restrict__ gate, Range rg) {
     if (gate && !*gate) return;
-    SPH_OWNED_INDEX(i)
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rg.count) return;
+    i += rg.begin;
     const float4 a = pk4[i];
     const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
     const float ki = a.w;

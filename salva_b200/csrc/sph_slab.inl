@@ -71,6 +71,11 @@ void slab_release(sph_world* w) {
     SlabState& S = w->slab;
     if (S.comm && S.own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S.comm);
     S.comm = nullptr;
+    if (S.comm_st) cudaStreamSynchronize(S.comm_st);
+    if (S.ev_ready) cudaEventDestroy(S.ev_ready);
+    if (S.ev_done) cudaEventDestroy(S.ev_done);
+    if (S.comm_st) cudaStreamDestroy(S.comm_st);
+    S.comm_st = nullptr; S.ev_ready = nullptr; S.ev_done = nullptr;
     S.d_cnt.release(); S.flag.release(); S.flag_o.release(); S.gid_l.release(); S.gid_r.release(); S.d_cnt64.release();
     for (int a = 0; a < 3; ++a) {
         S.out_l[a].release();
@@ -87,20 +92,21 @@ inline int slab_right(const sph_world* w) { return w->slab.rank + 1 < w->slab.nr
 
 // Per-iteration ghost refresh of up to 4 per-particle arrays in ONE NCCL group (elem = bytes per particle): my boundary
 // columns go to the neighbours, their boundary columns land in my ghost ranges.  Contiguous ranges, no packing.
-sph_status slab_refresh_n(sph_world* w, const SlabArray* arrays, int n_arrays) {
+sph_status slab_refresh_n(sph_world* w, const SlabArray* arrays, int n_arrays, cudaStream_t st) {
     if (!slab_on(w)) return SPH_OK;
     SlabState& S = w->slab;
+    if (!st) st = w->st;
     NC(g_nccl.GroupStart());
     for (int k = 0; k < n_arrays; ++k) {
         char* a = static_cast<char*>(arrays[k].p);
         const size_t elem = arrays[k].elem;
         if (slab_left(w) >= 0) {
-            if (S.sl_count) NC(g_nccl.Send(a + (size_t)S.sl_begin * elem, (size_t)S.sl_count * elem, NCCL_CHAR, slab_left(w), S.comm, w->st));
-            if (S.gl_count) NC(g_nccl.Recv(a, (size_t)S.gl_count * elem, NCCL_CHAR, slab_left(w), S.comm, w->st));
+            if (S.sl_count) NC(g_nccl.Send(a + (size_t)S.sl_begin * elem, (size_t)S.sl_count * elem, NCCL_CHAR, slab_left(w), S.comm, st));
+            if (S.gl_count) NC(g_nccl.Recv(a, (size_t)S.gl_count * elem, NCCL_CHAR, slab_left(w), S.comm, st));
         }
         if (slab_right(w) >= 0) {
-            if (S.sr_count) NC(g_nccl.Send(a + (size_t)S.sr_begin * elem, (size_t)S.sr_count * elem, NCCL_CHAR, slab_right(w), S.comm, w->st));
-            if (S.gr_count) NC(g_nccl.Recv(a + (size_t)S.gr_begin * elem, (size_t)S.gr_count * elem, NCCL_CHAR, slab_right(w), S.comm, w->st));
+            if (S.sr_count) NC(g_nccl.Send(a + (size_t)S.sr_begin * elem, (size_t)S.sr_count * elem, NCCL_CHAR, slab_right(w), S.comm, st));
+            if (S.gr_count) NC(g_nccl.Recv(a + (size_t)S.gr_begin * elem, (size_t)S.gr_count * elem, NCCL_CHAR, slab_right(w), S.comm, st));
         }
     }
     NC(g_nccl.GroupEnd());
