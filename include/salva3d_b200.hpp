@@ -1,0 +1,270 @@
+// salva3d_b200.hpp — header-only C++ host mirror of salva3d's solver-path API on top of the C ABI (include/sph.h).
+//
+// The reference's host language (Rust) has no toolchain in this build image, so the host side above the C ABI is
+// provided in C++ with the reference's type names, constructor arguments and error behaviour (reference panics /
+// assert! sites become exceptions).  Mirrors (paths under the reference's src/):
+//   LiquidWorld::{new, add_fluid, add_boundary, step, fluids, boundaries, h, particle_radius}  liquid_world.rs:39-208
+//   Fluid::{new, add_particles, delete_particle_at_next_timestep, num_particles, particle_mass}  object/fluid.rs:40-196
+//   Boundary::new                                                                              object/boundary.rs:28-46
+//   InteractionGroups::{default, test}                                                         object/interaction_groups.rs:64-79
+//   DFSPHSolver::new / IISPHSolver::new (public tunables)       solver/pressure/dfsph_solver.rs:54-70, iisph_solver.rs:48-64
+//   XSPHViscosity / ArtificialViscosity / Akinci2013SurfaceTension / Becker2009Elasticity ::new  solver/{viscosity,surface_tension,elasticity}/*.rs
+// Every call goes to libsalva_b200.so (CUDA); there is no CPU path.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "sph.h"
+
+namespace salva3d {
+
+using Real = float;  // lib.rs:199
+struct Vector3 {
+    Real x = 0, y = 0, z = 0;
+};
+using Point3 = Vector3;  // tightly packed xyz f32 triples == Vec<Point3<f32>> memory layout
+
+struct InteractionGroups {  // interaction_groups.rs:20-79
+    uint32_t memberships = 1u, filter = 0xFFFFFFFFu;
+    bool test(const InteractionGroups& rhs) const { return (memberships & rhs.filter) != 0 && (rhs.memberships & filter) != 0; }
+};
+
+struct NonPressureForce {  // solver/nonpressure_force.rs:10-30 (built-in forces carry a descriptor the engine executes)
+    virtual ~NonPressureForce() {}
+    virtual sph_force_desc descriptor() const = 0;
+};
+struct XSPHViscosity : NonPressureForce {  // xsph_viscosity.rs:12-26
+    Real boundary_viscosity_coefficient, fluid_viscosity_coefficient;
+    XSPHViscosity(Real fluid_viscosity_coefficient_, Real boundary_viscosity_coefficient_)
+        : boundary_viscosity_coefficient(boundary_viscosity_coefficient_), fluid_viscosity_coefficient(fluid_viscosity_coefficient_) {}
+    sph_force_desc descriptor() const override {
+        sph_force_desc d{SPH_FORCE_XSPH_VISCOSITY, {fluid_viscosity_coefficient, boundary_viscosity_coefficient}};
+        return d;
+    }
+};
+struct ArtificialViscosity : NonPressureForce {  // artificial_viscosity.rs:14-38
+    Real alpha = 1.0f, beta = 0.0f, speed_of_sound = 10.0f, fluid_viscosity_coefficient, boundary_viscosity_coefficient;
+    ArtificialViscosity(Real fluid_viscosity_coefficient_, Real boundary_viscosity_coefficient_)
+        : fluid_viscosity_coefficient(fluid_viscosity_coefficient_), boundary_viscosity_coefficient(boundary_viscosity_coefficient_) {}
+    sph_force_desc descriptor() const override {
+        sph_force_desc d{SPH_FORCE_ARTIFICIAL_VISCOSITY, {fluid_viscosity_coefficient, boundary_viscosity_coefficient, alpha, beta, speed_of_sound}};
+        return d;
+    }
+};
+struct Akinci2013SurfaceTension : NonPressureForce {  // akinci2013_surface_tension.rs:20-35
+    Real fluid_tension_coefficient, boundary_adhesion_coefficient;
+    Akinci2013SurfaceTension(Real fluid_tension_coefficient_, Real boundary_adhesion_coefficient_)
+        : fluid_tension_coefficient(fluid_tension_coefficient_), boundary_adhesion_coefficient(boundary_adhesion_coefficient_) {}
+    sph_force_desc descriptor() const override {
+        sph_force_desc d{SPH_FORCE_AKINCI2013_TENSION, {fluid_tension_coefficient, boundary_adhesion_coefficient}};
+        return d;
+    }
+};
+struct Becker2009Elasticity : NonPressureForce {  // becker2009_elasticity.rs:60-76
+    Real young_modulus, poisson_ratio;
+    bool nonlinear_strain;
+    Becker2009Elasticity(Real young_modulus_, Real poisson_ratio_, bool nonlinear_strain_)
+        : young_modulus(young_modulus_), poisson_ratio(poisson_ratio_), nonlinear_strain(nonlinear_strain_) {}
+    sph_force_desc descriptor() const override {
+        sph_force_desc d{SPH_FORCE_BECKER2009_ELASTICITY, {young_modulus, poisson_ratio, nonlinear_strain ? 1.0f : 0.0f}};
+        return d;
+    }
+};
+
+struct DFSPHSolver {  // dfsph_solver.rs:54-70
+    int kind = SPH_SOLVER_DFSPH;
+    uint32_t min_pressure_iter = 1, max_pressure_iter = 50;
+    Real max_density_error = 0.05f;
+    uint32_t min_divergence_iter = 1, max_divergence_iter = 50;
+    Real max_divergence_error = 0.1f;
+    Real omega = 0.5f;
+};
+struct IISPHSolver : DFSPHSolver {  // iisph_solver.rs:48-64
+    IISPHSolver() { kind = SPH_SOLVER_IISPH; }
+};
+
+class Fluid {  // object/fluid.rs:12-34
+public:
+    std::vector<std::shared_ptr<NonPressureForce>> nonpressure_forces;
+    std::vector<Point3> positions;
+    std::vector<Vector3> velocities;
+    std::vector<Real> volumes;
+    Real density0;
+    InteractionGroups interaction_groups;
+
+    Fluid(std::vector<Point3> particle_positions, Real particle_radius, Real density0_, InteractionGroups groups = InteractionGroups())
+        : positions(std::move(particle_positions)), density0(density0_), interaction_groups(groups), particle_radius_(particle_radius) {
+        velocities.assign(positions.size(), Vector3());
+        volumes.assign(positions.size(), default_particle_volume());
+        deleted_.assign(positions.size(), 0);
+    }
+    size_t num_particles() const { return positions.size(); }
+    Real particle_radius() const { return particle_radius_; }
+    Real default_particle_volume() const { return particle_radius_ * particle_radius_ * particle_radius_ * (Real)(8.0 * 0.8); }  // fluid.rs:110-120
+    Real particle_mass(size_t i) const { return volumes[i] * density0; }                                                           // fluid.rs:183-185
+    void add_particles(const std::vector<Point3>& pos, const std::vector<Vector3>* vel = nullptr) {                                // fluid.rs:126-150
+        if (vel && vel->size() != pos.size()) throw std::invalid_argument("The provided positions and velocities arrays must have the same length.");
+        appended_pos_.insert(appended_pos_.end(), pos.begin(), pos.end());
+        for (size_t i = 0; i < pos.size(); ++i) appended_vel_.push_back(vel ? (*vel)[i] : Vector3());
+        positions.insert(positions.end(), pos.begin(), pos.end());
+        for (size_t i = 0; i < pos.size(); ++i) velocities.push_back(vel ? (*vel)[i] : Vector3());
+        volumes.resize(positions.size(), default_particle_volume());
+        deleted_.resize(positions.size(), 0);
+    }
+    void delete_particle_at_next_timestep(size_t particle) {  // fluid.rs:71-76
+        if (!deleted_[particle]) {
+            deleted_[particle] = 1;
+            ++num_deleted_;
+        }
+    }
+    size_t num_deleted_particles() const { return num_deleted_; }
+
+private:
+    friend class LiquidWorld;
+    Real particle_radius_;
+    std::vector<uint8_t> deleted_;
+    size_t num_deleted_ = 0;
+    std::vector<Point3> appended_pos_;
+    std::vector<Vector3> appended_vel_;
+    uint32_t handle_ = 0;
+};
+
+class Boundary {  // object/boundary.rs:11-46
+public:
+    std::vector<Point3> positions;
+    std::vector<Vector3> velocities;
+    std::vector<Real> volumes;
+    std::vector<Vector3> forces;  // filled after each step when constructed with want_forces (boundary.rs:21)
+    InteractionGroups interaction_groups;
+    Boundary(std::vector<Point3> particle_positions, InteractionGroups groups = InteractionGroups(), bool want_forces = false)
+        : positions(std::move(particle_positions)), interaction_groups(groups), want_forces_(want_forces) {
+        velocities.assign(positions.size(), Vector3());
+        volumes.assign(positions.size(), 0.0f);
+        if (want_forces) forces.assign(positions.size(), Vector3());
+    }
+    size_t num_particles() const { return positions.size(); }
+
+private:
+    friend class LiquidWorld;
+    bool want_forces_;
+    uint32_t handle_ = 0;
+};
+
+using FluidHandle = size_t;
+using BoundaryHandle = size_t;
+
+class LiquidWorld {  // liquid_world.rs:17-158
+public:
+    template <class Solver>
+    LiquidWorld(const Solver& solver, Real particle_radius, Real smoothing_factor, int device = 0) {
+        sph_world_desc d;
+        sph_world_desc_default(&d);
+        d.solver = solver.kind;
+        d.particle_radius = particle_radius;
+        d.smoothing_factor = smoothing_factor;
+        d.min_pressure_iter = solver.min_pressure_iter;
+        d.max_pressure_iter = solver.max_pressure_iter;
+        d.max_density_error = solver.max_density_error;
+        d.min_divergence_iter = solver.min_divergence_iter;
+        d.max_divergence_iter = solver.max_divergence_iter;
+        d.max_divergence_error = solver.max_divergence_error;
+        d.omega = solver.omega;
+        d.device = device;
+        sph_status st = sph_world_create(&d, &raw_);
+        if (st != SPH_OK) throw std::runtime_error("sph_world_create failed (status " + std::to_string(st) + "): no CUDA device? there is no CPU fallback");
+    }
+    ~LiquidWorld() {
+        if (raw_) sph_world_destroy(raw_);
+    }
+    LiquidWorld(const LiquidWorld&) = delete;
+    LiquidWorld& operator=(const LiquidWorld&) = delete;
+
+    FluidHandle add_fluid(Fluid fluid) {  // liquid_world.rs:161
+        uint32_t h = 0;
+        check(sph_fluid_add(raw_, fp(fluid.positions), fp(fluid.velocities), fluid.volumes.data(), fluid.positions.size(), fluid.density0,
+                            fluid.interaction_groups.memberships, fluid.interaction_groups.filter, &h));
+        for (auto& f : fluid.nonpressure_forces) {
+            sph_force_desc d = f->descriptor();
+            check(sph_fluid_push_force(raw_, h, &d));
+        }
+        fluid.handle_ = h;
+        fluid.appended_pos_.clear();
+        fluid.appended_vel_.clear();
+        fluids_.push_back(std::move(fluid));
+        return fluids_.size() - 1;
+    }
+    BoundaryHandle add_boundary(Boundary boundary) {  // liquid_world.rs:166
+        uint32_t h = 0;
+        check(sph_boundary_add(raw_, fp(boundary.positions), fp(boundary.velocities), boundary.positions.size(), boundary.interaction_groups.memberships,
+                               boundary.interaction_groups.filter, boundary.want_forces_ ? 1 : 0, &h));
+        boundary.handle_ = h;
+        boundaries_.push_back(std::move(boundary));
+        return boundaries_.size() - 1;
+    }
+    std::vector<Fluid>& fluids_mut() { return fluids_; }  // liquid_world.rs:186-188: host edits are uploaded by the next step
+    const std::vector<Fluid>& fluids() const { return fluids_; }
+    std::vector<Boundary>& boundaries_mut() { return boundaries_; }
+    const std::vector<Boundary>& boundaries() const { return boundaries_; }
+    Real h() const { return sph_world_h(raw_); }
+    Real particle_radius() const { return sph_world_particle_radius(raw_); }
+
+    // Advances the simulation by dt seconds (liquid_world.rs:62-64).
+    void step(Real dt, const Vector3& gravity) {
+        for (Fluid& f : fluids_) {
+            size_t n_dev = f.positions.size() - f.appended_pos_.size();
+            if (n_dev) check(sph_fluid_write(raw_, f.handle_, fp(f.positions), fp(f.velocities), n_dev));  // host edits
+            if (!f.appended_pos_.empty()) {
+                check(sph_fluid_append(raw_, f.handle_, fp(f.appended_pos_), fp(f.appended_vel_), f.appended_pos_.size()));
+                f.appended_pos_.clear();
+                f.appended_vel_.clear();
+            }
+            if (f.num_deleted_) {
+                check(sph_fluid_delete(raw_, f.handle_, f.deleted_.data(), f.deleted_.size()));
+                f.num_deleted_ = 0;
+            }
+        }
+        for (Boundary& b : boundaries_)
+            if (b.num_particles()) check(sph_boundary_write(raw_, b.handle_, fp(b.positions), fp(b.velocities), b.num_particles()));
+        const float g[3] = {gravity.x, gravity.y, gravity.z};
+        check(sph_world_step(raw_, dt, g));  // == LiquidWorld::step
+        for (Fluid& f : fluids_) {
+            size_t n = 0;
+            check(sph_fluid_count(raw_, f.handle_, &n));
+            f.positions.resize(n);
+            f.velocities.resize(n);
+            f.volumes.resize(n, f.default_particle_volume());
+            f.deleted_.assign(n, 0);
+            if (n) check(sph_fluid_read(raw_, f.handle_, reinterpret_cast<float*>(f.positions.data()), reinterpret_cast<float*>(f.velocities.data()), n, &n));
+        }
+        for (Boundary& b : boundaries_) {
+            if (!b.num_particles()) continue;
+            check(sph_boundary_read_volumes(raw_, b.handle_, b.volumes.data(), b.volumes.size()));
+            if (b.want_forces_) check(sph_boundary_read_forces(raw_, b.handle_, reinterpret_cast<float*>(b.forces.data()), b.forces.size()));
+        }
+    }
+    sph_step_stats counters() const {  // world.counters (counters/mod.rs:17-30)
+        sph_step_stats s;
+        sph_world_stats(raw_, &s);
+        return s;
+    }
+    sph_world* raw() { return raw_; }
+
+private:
+    template <class V>
+    static const float* fp(const std::vector<V>& v) {
+        static_assert(sizeof(V) == 3 * sizeof(float), "packed xyz triples");
+        return v.empty() ? nullptr : reinterpret_cast<const float*>(v.data());
+    }
+    void check(sph_status st) const {  // reference assert!/panic sites surface as exceptions
+        if (st != SPH_OK) throw std::runtime_error(std::string("salva_b200: status ") + std::to_string((int)st) + ": " + sph_last_error(raw_));
+    }
+    sph_world* raw_ = nullptr;
+    std::vector<Fluid> fluids_;
+    std::vector<Boundary> boundaries_;
+};
+
+}  // namespace salva3d
