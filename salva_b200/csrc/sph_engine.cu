@@ -148,6 +148,7 @@ struct sph_world {
     std::vector<BoundaryRec> bounds;
     size_t N = 0, B = 0;   // N = fluid particles OWNED by this world
     size_t Ntot = 0;       // slots of the sorted arrays during a step: owned + ghost (== N on one GPU)
+    bool single_launch = true;
     int protect_buf = -1;    // double-buffer index ensure_fluid_buffers() must not reallocate (it is being read)
     uint32_t own_begin = 0;  // first owned slot (ghost columns of a slab world sit at both ends of the sorted arrays)
     SlabState slab;
@@ -197,6 +198,8 @@ struct sph_world {
     const void* tex_pvx_ptr = nullptr;
     const void* tex_vyz_ptr = nullptr;
     const void* tex_pk_ptr = nullptr;
+    DBuf<uint32_t> d_ticket;      // last-block ticket of the in-kernel error reduction (kept at 0 between launches)
+    bool errsum_ready = false;    // the last evaluation launch already reduced its partials into errsum
     DBuf<LoopCtl> d_ctl;          // device-side Jacobi loop control (sph_kernels.cuh LoopCtl)
     LoopCtl* h_ctl = nullptr;     // pinned host mirror
     bool device_loops = false;  // measured slower at C2 (gated no-op launches cost more than the syncs they save)
@@ -797,8 +800,11 @@ sph_status phase_neighbors(sph_world* w) {
 // mean-per-fluid -> max over fluids (dfsph_solver.rs:153-158, :347-352)
 sph_status read_error(sph_world* w, uint32_t nblk, float* out) {
     int nf = (int)w->fluids.size();
-    k_reduce_partials<<<nf, 256, 0, w->st>>>(w->partial.p, nblk, nf, w->errsum.p);
-    w->launches++;
+    if (!w->errsum_ready) {
+        k_reduce_partials<<<nf, 256, 0, w->st>>>(w->partial.p, nblk, nf, w->errsum.p);
+        w->launches++;
+    }
+    w->errsum_ready = false;
     TRY(slab_allreduce(w, w->errsum.p, nf));  // multi-GPU: the means are over ALL ranks' particles
     CU(cudaMemcpyAsync(w->h_pinned, w->errsum.p, nf * sizeof(float), cudaMemcpyDeviceToHost, w->st));
     CU(cudaStreamSynchronize(w->st));
@@ -940,6 +946,7 @@ sph_status run_parts(sph_world* w, const SlabArray* arrays, int n_arrays, uint32
     SlabState& S = w->slab;
     TRY(slab_wait(w));
     uint32_t off = 0;
+    w->single_launch = !(S.active && S.overlap && n_arrays != 0);  // one launch covers the pass -> in-kernel final reduction
     auto part = [&](uint32_t b, uint32_t cnt) -> sph_status {
         if (!cnt) return SPH_OK;
         TRY(fn(Range{b, cnt}, off));
@@ -974,19 +981,22 @@ sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
     else TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
     const size_t nf = std::max<size_t>(1, w->fluids.size());
     SlabArray a[2] = {{w->dens.p, sizeof(float)}, {w->unimass ? (void*)w->pk4.p : (void*)w->kappa.p, w->unimass ? sizeof(float4) : sizeof(float)}};
-    return run_parts(w, a, 2, nblk, [&](Range rg, uint32_t blk) -> sph_status {
+    sph_status rs = run_parts(w, a, 2, nblk, [&](Range rg, uint32_t blk) -> sph_status {
         float* partial = w->partial.p + (size_t)blk * nf;
+        uint32_t* tk = w->single_launch ? w->d_ticket.p : nullptr;
         if (w->unimass)
             LAUNCH_R((k_density_alpha_div<false, true>), rg, w->pvx4.p, w->vs.p, (cudaTextureObject_t)0, w->vyz2.p, w->tex_vyz, w->vel[c].p, w->bpos[bc].p, L,
-                     w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7);
+                     w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7, tk, w->errsum.p);
         else if (multi)
             LAUNCH_R((k_density_alpha_div<true, false>), rg, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p, w->bpos[bc].p,
-                     L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7);
+                     L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7, tk, w->errsum.p);
         else
             LAUNCH_R((k_density_alpha_div<false, false>), rg, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p, w->bpos[bc].p,
-                     L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7);
+                     L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7, tk, w->errsum.p);
         return SPH_OK;
     });
+    w->errsum_ready = w->single_launch;
+    return rs;
 }
 
 // compute_divergences (predict = false) / compute_predicted_densities (predict = true); returns #partials.
@@ -1001,6 +1011,7 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
         TDISPATCH2(k_tile_vel_divergence, multi, predict, 32, cap, w->pos[c].p, w->vs.p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, w->cstart.p, cap, L,
                    w->dens.p, w->alpha.p, predict ? w->pred.p : w->divv.p, w->kappa.p, w->partial.p, w->dt, w->d_scal.p + 7);
         *nblk = w->n_tiles;
+        w->errsum_ready = false;
         return SPH_OK;
     }
     Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
@@ -1014,27 +1025,30 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
     const size_t nf = std::max<size_t>(1, w->fluids.size());
     SlabArray a[1] = {{w->unimass ? (void*)w->pk4.p : (void*)w->kappa.p, w->unimass ? sizeof(float4) : sizeof(float)}};
     const int n_arrays = (w->slab.active && w->slab.overlap) ? 1 : 0;
-    return run_parts(w, a, n_arrays, nblk, [&](Range rg, uint32_t blk) -> sph_status {
+    sph_status rs = run_parts(w, a, n_arrays, nblk, [&](Range rg, uint32_t blk) -> sph_status {
         float* partial = w->partial.p + (size_t)blk * nf;
+        uint32_t* tk = (w->single_launch && !gate) ? w->d_ticket.p : nullptr;
         if (w->unimass) {
             const bool ptex = w->uni_eval_mode == 1;
             if (predict) {
                 if (ptex) LAUNCH_R((k_vel_divergence_u<true, true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                                   w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate);
+                                   w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
                 else LAUNCH_R((k_vel_divergence_u<true, false>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                              w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate);
+                              w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
             } else {
                 if (ptex) LAUNCH_R((k_vel_divergence_u<false, true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                                   w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate);
+                                   w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
                 else LAUNCH_R((k_vel_divergence_u<false, false>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
-                              w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate);
+                              w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
             }
         } else {
             BOOL3(k_vel_divergence, multi, predict, w->use_tex, rg, w->pos[c].p, w->vs.p, w->tex_vs, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p,
-                  w->alpha.p, out, w->kappa.p, partial, w->dt, w->d_scal.p + 7, gate);
+                  w->alpha.p, out, w->kappa.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
         }
         return SPH_OK;
     });
+    w->errsum_ready = w->single_launch && !gate;
+    return rs;
 }
 // compute_velocity_changes_for_divergence (pressure = false) / compute_velocity_changes (pressure = true)
 sph_status launch_vel_update(sph_world* w, bool pressure, const int* gate = nullptr) {
@@ -1438,6 +1452,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     ok = ok && cudaMallocHost(&w->h_pinned, 64 * sizeof(float)) == cudaSuccess;
     ok = ok && cudaMallocHost(&w->h_ctl, sizeof(LoopCtl)) == cudaSuccess && w->d_ctl.ensure(1) == cudaSuccess;
     ok = ok && w->d_scal.ensure(16) == cudaSuccess && w->d_cnt.ensure(2) == cudaSuccess;
+    ok = ok && w->d_ticket.ensure(4) == cudaSuccess && cudaMemset(w->d_ticket.p, 0, 4 * sizeof(uint32_t)) == cudaSuccess;
     if (!ok) {
         delete w;
         return SPH_ERR_CUDA;
@@ -1480,6 +1495,7 @@ void sph_world_destroy(sph_world* w) {
     if (w->h_pinned) cudaFreeHost(w->h_pinned);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     w->d_ctl.release();
+    w->d_ticket.release();
     for (auto& e : w->ev)
         if (e) cudaEventDestroy(e);
     if (w->st) cudaStreamDestroy(w->st);

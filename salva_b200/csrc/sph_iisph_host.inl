@@ -56,6 +56,7 @@ sph_status iisph_step(sph_world* w, float dt_total, const float g[3]) {
     LAUNCH(k_iisph_warm_start, N, 256, w->press[c].p, w->dens.p, S.prho);                                                        // :673-677
     uint32_t nblk = 0;
     TRY(launch_vel_divergence(w, true, &nblk));                                                                                  // :679-685
+    w->errsum_ready = false;  // IISPH ignores this evaluation's error (iisph_solver.rs:679: `let _ =`)
     DISPATCH1(k_iisph_aii, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, S.dii, S.aii, w->dt);       // :687-693
     // pressure_solve :422-456
     float *p_cur = w->press[c].p, *p_next = S.next_p, *pr_cur = S.prho, *pr_next = S.next_prho;

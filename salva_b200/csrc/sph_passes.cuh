@@ -164,15 +164,34 @@ __device__ __forceinline__ float fetch1(const float* __restrict__ a, cudaTexture
 }
 
 // Per-fluid deterministic error reduction: partial[block * n_fluids + f].
+// With a ticket counter the LAST block to finish also sums the partials of the whole launch in index order into
+// errsum[f] (saves a separate k_reduce_partials launch per evaluation; same fixed summation tree every run).
 template <bool MULTI>
-__device__ __forceinline__ void reduce_error(float e, uint32_t fi, bool valid, float* __restrict__ partial, float* sm) {
+__device__ __forceinline__ void reduce_error(float e, uint32_t fi, bool valid, float* __restrict__ partial, float* sm, uint32_t* __restrict__ ticket = nullptr,
+                                             float* __restrict__ errsum = nullptr) {
+    const int nf = MULTI ? C.n_fluids : 1;
     if (!MULTI) {
         float s = block_sum(valid ? e : 0.f, sm);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
     } else {
-        for (int f = 0; f < C.n_fluids; ++f) {
+        for (int f = 0; f < nf; ++f) {
             float s = block_sum((valid && fi == (uint32_t)f) ? e : 0.f, sm);
-            if (threadIdx.x == 0) partial[(size_t)blockIdx.x * C.n_fluids + f] = s;
+            if (threadIdx.x == 0) partial[(size_t)blockIdx.x * nf + f] = s;
+        }
+    }
+    if (ticket) {
+        __shared__ bool s_last;
+        __threadfence();
+        if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            for (int f = 0; f < nf; ++f) {
+                float s = 0.f;
+                for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(&partial[(size_t)b * nf + f]);
+                s = block_sum(s, sm);
+                if (threadIdx.x == 0) errsum[f] = s;
+            }
+            if (threadIdx.x == 0) *ticket = 0;
         }
     }
 }
@@ -249,7 +268,8 @@ __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, const float4* __restrict__ vs, cudaTextureObject_t tvs,
                     const float2* __restrict__ vyz, cudaTextureObject_t tvyz, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
                     float4* __restrict__ g_out, float* __restrict__ dens, float* __restrict__ alpha, float* __restrict__ divv, float* __restrict__ kappa,
-                    float4* __restrict__ pk4, float* __restrict__ partial, int* __restrict__ err, Range rg) {
+                    float4* __restrict__ pk4, float* __restrict__ partial, int* __restrict__ err, uint32_t* __restrict__ ticket,
+                    float* __restrict__ errsum, Range rg) {
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < rg.count;
@@ -336,7 +356,7 @@ k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, const 
         else kappa[i] = d * al;
         e = d / rho0;
     }
-    reduce_error<MULTI>(e, fi, valid, partial, sm);
+    reduce_error<MULTI>(e, fi, valid, partial, sm, ticket, errsum);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -350,7 +370,7 @@ __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_divergence(const float4* __restrict__ pos, const float4* __restrict__ vs, cudaTextureObject_t tvs, const float4* __restrict__ vel,
                  const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
                  const float* __restrict__ alpha, float* __restrict__ out, float* __restrict__ kappa, float* __restrict__ partial, float dt,
-                 int* __restrict__ err, const int* __restrict__ gate, Range rg) {
+                 int* __restrict__ err, const int* __restrict__ gate, uint32_t* __restrict__ ticket, float* __restrict__ errsum, Range rg) {
     if (gate && !*gate) return;  // device-side loop control: this evaluation is past the break
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,7 +415,7 @@ k_vel_divergence(const float4* __restrict__ pos, const float4* __restrict__ vs, 
             e = d / rho0;
         }
     }
-    reduce_error<MULTI>(e, fi, valid, partial, sm);
+    reduce_error<MULTI>(e, fi, valid, partial, sm, ticket, errsum);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -456,7 +476,7 @@ __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, const float2* __restrict__ vyz, cudaTextureObject_t tvyz,
                    const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
                    const float* __restrict__ alpha, float* __restrict__ out, float4* __restrict__ pk4, float* __restrict__ partial, float dt,
-                   int* __restrict__ err, const int* __restrict__ gate, Range rg) {
+                   int* __restrict__ err, const int* __restrict__ gate, uint32_t* __restrict__ ticket, float* __restrict__ errsum, Range rg) {
     if (gate && !*gate) return;
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,7 +524,7 @@ k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, con
         }
         pk4[i] = make_float4(a.x, a.y, a.z, kap);
     }
-    reduce_error<false>(e, 0u, valid, partial, sm);
+    reduce_error<false>(e, 0u, valid, partial, sm, ticket, errsum);
 }
 
 template <bool BFORCE, bool PRESSURE, bool POS_TEX>
