@@ -180,7 +180,7 @@ struct sph_world {
     DBuf<float> press[2];
     DBuf<float4> vs, acc, normals, dbg_acc;
     DBuf<float> dens, alpha, kappa, divv, pred, bvol, bforce;
-    DBuf<uint32_t> cid, rank, perm, cstart, bcid, brank, bperm, bstart, scan_aux[3];
+    DBuf<uint32_t> cid, rank, perm, cstart, bcid, brank, bperm, bstart, scan_aux[3], scan_aux_k[3];
     DBuf<uint32_t> nbr_f, nbr_b, cnt_f, cnt_b;
     DBuf<float4> g_f;  // cached gradient scalars, one float4 per group of 4 contacts (same layout as nbr_f)
     // gather_backend 1 (sph_tile.cuh): 16-bit tile-local fluid contact indices
@@ -328,6 +328,29 @@ sph_status scan_exclusive(sph_world* w, uint32_t* data, size_t n, int level = 0)
     w->launches++;
     TRY(scan_exclusive(w, w->scan_aux[level].p, nb, level + 1));
     k_scan_add<<<nb, SCAN_T, 0, w->st>>>(data, (uint32_t)n, w->scan_aux[level].p);
+    w->launches++;
+    return SPH_OK;
+}
+
+// K arrays of the same length scanned together (in place, exclusive); n <= 2048 * 2048 * 2048
+template <int K>
+sph_status scan_exclusive_k(sph_world* w, ScanSet<K> arrays, size_t n, int level = 0) {
+    if (n == 0) return SPH_OK;
+    uint32_t nb = cdiv(n, SCAN_B);
+    ScanSet<K> sums;
+    for (int a = 0; a < K; ++a) sums.a[a] = nullptr;
+    if (nb == 1) {
+        k_scanK_block<K><<<1, SCAN_T, 0, w->st>>>(arrays, (uint32_t)n, sums);
+        w->launches++;
+        return SPH_OK;
+    }
+    if (level >= 3) return w->fail(SPH_ERR_INVALID, "scan too deep");
+    CU(w->scan_aux_k[level].ensure((size_t)K * nb));
+    for (int a = 0; a < K; ++a) sums.a[a] = w->scan_aux_k[level].p + (size_t)a * nb;
+    k_scanK_block<K><<<nb, SCAN_T, 0, w->st>>>(arrays, (uint32_t)n, sums);
+    w->launches++;
+    TRY(scan_exclusive_k<K>(w, sums, nb, level + 1));
+    k_scanK_add<K><<<nb, SCAN_T, 0, w->st>>>(arrays, (uint32_t)n, sums);
     w->launches++;
     return SPH_OK;
 }
@@ -1476,6 +1499,7 @@ void sph_world_destroy(sph_world* w) {
     w->cid.release(); w->rank.release(); w->perm.release(); w->cstart.release(); w->bcid.release(); w->brank.release(); w->bperm.release();
     w->bstart.release();
     for (auto& a : w->scan_aux) a.release();
+    for (auto& a : w->scan_aux_k) a.release();
     w->nbr_f.release(); w->g_f.release(); w->nbr16.release(); w->nbr_b.release(); w->cnt_f.release(); w->cnt_b.release();
     w->partial.release(); w->errsum.release(); w->d_scal.release(); w->d_cnt.release();
     w->o_a.release(); w->o_b.release(); w->o_c.release(); w->o_mass.release(); w->o_fid.release();

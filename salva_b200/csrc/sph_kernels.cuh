@@ -299,6 +299,68 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_
     }
 }
 
+// K-way exclusive scan: the same 2048-item blocks, K independent arrays scanned by one launch (slab prologue: the five
+// classification flag arrays are compacted together instead of by five 3-kernel scans).
+template <int K>
+struct ScanSet {
+    uint32_t* a[K];
+};
+template <int K>
+__global__ void k_scanK_block(ScanSet<K> io, uint32_t n, ScanSet<K> block_sums) {
+    __shared__ uint32_t warp_tot[K][SCAN_T / 32];
+    const uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_I;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        uint32_t v[SCAN_I];
+        uint32_t tsum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_I; ++k) {
+            v[k] = (base + k < n) ? io.a[a][base + k] : 0u;
+            tsum += v[k];
+        }
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[a][wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = lane < SCAN_T / 32 ? warp_tot[a][lane] : 0u;
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            if (lane < SCAN_T / 32) warp_tot[a][lane] = wi - w;
+            if (lane == SCAN_T / 32 - 1 && block_sums.a[a]) block_sums.a[a][blockIdx.x] = wi;
+        }
+        __syncthreads();
+        uint32_t run = warp_tot[a][wid] + incl - tsum;
+#pragma unroll
+        for (int k = 0; k < SCAN_I; ++k) {
+            if (base + k < n) io.a[a][base + k] = run;
+            run += v[k];
+        }
+    }
+}
+template <int K>
+__global__ void k_scanK_add(ScanSet<K> io, uint32_t n, ScanSet<K> block_offsets) {
+    uint32_t i = blockIdx.x * SCAN_B + threadIdx.x;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        uint32_t off = block_offsets.a[a][blockIdx.x];
+#pragma unroll
+        for (int k = 0; k < SCAN_I; ++k) {
+            uint32_t j = i + k * SCAN_T;
+            if (j < n) io.a[a][j] += off;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: neighbour search (contacts.rs:154-400).  One thread per particle walks the 9 z-runs of its
 // 27-cell stencil and keeps the indices that pass the reference's exact `d^2 <= h*h` test.

@@ -171,7 +171,11 @@ sph_status slab_begin_step(sph_world* w) {
     uint32_t hc[16];
     CU(cudaMemcpyAsync(hc, S.d_cnt.p, sizeof hc, cudaMemcpyDeviceToHost, w->st));
     CU(cudaMemcpyAsync(sc[0], f[0], 5 * (size_t)n_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->st));
-    for (int a = 0; a < 5; ++a) TRY(scan_exclusive(w, sc[a], n_slots));
+    {
+        ScanSet<5> set;
+        for (int a = 0; a < 5; ++a) set.a[a] = sc[a];
+        TRY(scan_exclusive_k<5>(w, set, n_slots));  // one 3-launch scan for the five flag arrays
+    }
     TRY(scan_exclusive(w, S.flag_o.p, on));  // new original index of the kept particles (stable in the old order)
     CU(cudaStreamSynchronize(w->st));        // the only host sync of the prologue
     const uint32_t nk = hc[0], nl = hc[1], nr = hc[2], ncl = hc[3], ncr = hc[4];
