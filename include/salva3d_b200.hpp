@@ -37,6 +37,15 @@ struct NonPressureForce {  // solver/nonpressure_force.rs:10-30 (built-in forces
     virtual ~NonPressureForce() {}
     virtual sph_force_desc descriptor() const = 0;
 };
+// User-defined force: arbitrary host code, as a `dyn NonPressureForce` is in the reference (examples3d/custom_forces3.rs:66-90).
+struct CustomNonPressureForce : NonPressureForce {
+    virtual void solve(Real dt, Real inv_dt, Real kernel_radius, size_t n, const Point3* positions, const Vector3* velocities, const Real* densities,
+                       Vector3* accelerations) = 0;
+    sph_force_desc descriptor() const override {
+        sph_force_desc d{-1, {}};
+        return d;
+    }
+};
 struct XSPHViscosity : NonPressureForce {  // xsph_viscosity.rs:12-26
     Real boundary_viscosity_coefficient, fluid_viscosity_coefficient;
     XSPHViscosity(Real fluid_viscosity_coefficient_, Real boundary_viscosity_coefficient_)
@@ -188,6 +197,10 @@ public:
         check(sph_fluid_add(raw_, fp(fluid.positions), fp(fluid.velocities), fluid.volumes.data(), fluid.positions.size(), fluid.density0,
                             fluid.interaction_groups.memberships, fluid.interaction_groups.filter, &h));
         for (auto& f : fluid.nonpressure_forces) {
+            if (auto* custom = dynamic_cast<CustomNonPressureForce*>(f.get())) {  // host callback, kept alive by fluids_
+                check(sph_fluid_push_host_force(raw_, h, &LiquidWorld::host_force_trampoline, custom));
+                continue;
+            }
             sph_force_desc d = f->descriptor();
             check(sph_fluid_push_force(raw_, h, &d));
         }
@@ -254,6 +267,11 @@ public:
     sph_world* raw() { return raw_; }
 
 private:
+    static void host_force_trampoline(void* user, float dt, float inv_dt, float kernel_radius, size_t n, const float* pos, const float* vel,
+                                      const float* dens, float* acc) {
+        static_cast<CustomNonPressureForce*>(user)->solve(dt, inv_dt, kernel_radius, n, reinterpret_cast<const Point3*>(pos),
+                                                          reinterpret_cast<const Vector3*>(vel), dens, reinterpret_cast<Vector3*>(acc));
+    }
     template <class V>
     static const float* fp(const std::vector<V>& v) {
         static_assert(sizeof(V) == 3 * sizeof(float), "packed xyz triples");

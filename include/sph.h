@@ -132,6 +132,14 @@ sph_status sph_fluid_add(sph_world* w, const float* pos_xyz, const float* vel_xy
                          size_t n, float density0, uint32_t memberships, uint32_t filter, uint32_t* handle);
 /* fluid.nonpressure_forces.push(..)  fluid.rs:14; forces run in push order (dfsph_solver.rs:590). */
 sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid, const sph_force_desc* force);
+/* User-defined NonPressureForce plugins (trait solver/nonpressure_force.rs:10-30; e.g. examples3d/custom_forces3.rs:66-90):
+ * arbitrary HOST code that adds to fluid.accelerations.  At the force's slot in push order the library hands the
+ * callback the fluid's particles in ORIGINAL index order (host copies) and takes the accelerations back.  `dt` / `inv_dt`
+ * are the TimestepManager values the reference passes at that point (the previous step's: dfsph_solver.rs:693-702).
+ * Contact lists are not materialised for callbacks (pass-through of ParticlesContacts is a later row). */
+typedef void (*sph_host_force_fn)(void* user, float dt, float inv_dt, float kernel_radius, size_t n, const float* positions_xyz,
+                                  const float* velocities_xyz, const float* densities, float* accelerations_xyz);
+sph_status sph_fluid_push_host_force(sph_world* w, uint32_t fluid, sph_host_force_fn fn, void* user);
 /* Fluid::add_particles fluid.rs:126-150 */
 sph_status sph_fluid_append(sph_world* w, uint32_t fluid, const float* pos_xyz, const float* vel_xyz, size_t n);
 /* Fluid::delete_particle_at_next_timestep fluid.rs:71-76; applied at the next step (fluid.rs:88-98). */

@@ -146,7 +146,9 @@ struct ParticlesContacts {
     }
 };
 
-enum ForceKind { F_XSPH = 0, F_ARTIFICIAL = 1, F_AKINCI = 2, F_BECKER = 3 };
+enum ForceKind { F_XSPH = 0, F_ARTIFICIAL = 1, F_AKINCI = 2, F_BECKER = 3, F_HOST = 100 };
+typedef void (*host_force_fn)(void* user, float dt, float inv_dt, float kernel_radius, size_t n, const float* pos, const float* vel, const float* dens,
+                              float* acc);
 
 struct Mat3 {
     float m[3][3];  // m[row][col]
@@ -167,6 +169,8 @@ static inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - 
 struct Force {
     int kind;
     float p[8];
+    host_force_fn host_fn = nullptr;  // user-defined NonPressureForce::solve (nonpressure_force.rs:10-30)
+    void* host_user = nullptr;
     // Akinci2013: normals (akinci2013_surface_tension.rs:23)
     std::vector<V3> normals;
     // Becker2009 state (becker2009_elasticity.rs:48-58)
@@ -928,6 +932,12 @@ static void predict_advection(World& w, V3 gravity) {
                 case F_ARTIFICIAL: solve_artificial(w, f, fc); break;
                 case F_AKINCI: solve_akinci(w, f, fc); break;
                 case F_BECKER: solve_becker(w, f, fc); break;
+                case F_HOST: {
+                    Fluid& fl = w.fluids[f];
+                    fc.host_fn(fc.host_user, w.dt, w.inv_dt, w.h, fl.n(), &fl.positions[0].x, &fl.velocities[0].x, w.densities[f].data(),
+                               &fl.accelerations[0].x);
+                    break;
+                }
             }
         }
     w.dbg_acc.resize(w.fluids.size());
@@ -1326,6 +1336,17 @@ int orc_fluid_push_force(void* p, uint32_t fluid, int kind, const float* params)
     Force f;
     f.kind = kind;
     std::memcpy(f.p, params, sizeof f.p);
+    w.fluids[fluid].forces.push_back(std::move(f));
+    return 0;
+}
+int orc_fluid_push_host_force(void* p, uint32_t fluid, host_force_fn fn, void* user) {
+    World& w = *(World*)p;
+    if (fluid >= w.fluids.size() || !fn) return 1;
+    Force f;
+    f.kind = F_HOST;
+    std::memset(f.p, 0, sizeof f.p);
+    f.host_fn = fn;
+    f.host_user = user;
     w.fluids[fluid].forces.push_back(std::move(f));
     return 0;
 }

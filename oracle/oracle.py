@@ -33,6 +33,10 @@ class OrcStats(C.Structure):
                 ("n_contacts", C.c_uint64), ("threads", C.c_int32)]
 
 
+HOST_FORCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                            C.POINTER(C.c_float), C.POINTER(C.c_float))
+
+
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
     src = os.path.join(_HERE, "oracle.cpp")
@@ -52,6 +56,7 @@ def lib():
         L.orc_fluid_add.argtypes = [vp, fp, fp, fp, C.c_size_t, C.c_float, C.c_uint32, C.c_uint32]
         L.orc_fluid_push_force.argtypes = [vp, C.c_uint32, C.c_int, fp]
         L.orc_fluid_append.argtypes = [vp, C.c_uint32, fp, fp, C.c_size_t]
+        L.orc_fluid_push_host_force.argtypes = [vp, C.c_uint32, HOST_FORCE_FN, vp]
         L.orc_fluid_delete.argtypes = [vp, C.c_uint32, u8p, C.c_size_t]
         L.orc_fluid_write.argtypes = [vp, C.c_uint32, fp, fp, C.c_size_t]
         L.orc_fluid_count.restype = C.c_size_t
@@ -124,6 +129,16 @@ class OracleWorld:
         pr = np.zeros(8, np.float32)
         pr[:len(params)] = params
         assert self._L.orc_fluid_push_force(self._w, fluid, kind, _fp(pr)) == 0
+
+    def push_host_force(self, fluid, solve):
+        def tramp(_user, dt, inv_dt, h, n, pos, vel, dens, acc):
+            solve(dt, inv_dt, h, np.ctypeslib.as_array(pos, (n, 3)), np.ctypeslib.as_array(vel, (n, 3)),
+                  np.ctypeslib.as_array(dens, (n,)), np.ctypeslib.as_array(acc, (n, 3)))
+        cb = HOST_FORCE_FN(tramp)
+        if not hasattr(self, "_callbacks"):
+            self._callbacks = []
+        self._callbacks.append(cb)
+        assert self._L.orc_fluid_push_host_force(self._w, fluid, cb, None) == 0
 
     def append_particles(self, fluid, positions, velocities=None):
         p = _f32(positions, (-1, 3))

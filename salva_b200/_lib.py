@@ -40,8 +40,11 @@ class StepStats(C.Structure):
                 ("reserved_", C.c_uint32)]
 
 
-# every symbol include/sph.h declares: name -> (restype, argtypes)
 _fp, _u8p, _vp = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.c_void_p
+HOST_FORCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                            C.POINTER(C.c_float), C.POINTER(C.c_float))
+
+# every symbol include/sph.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "sph_world_desc_default": (None, [C.POINTER(WorldDesc)]),
     "sph_world_create": (C.c_int, [C.POINTER(WorldDesc), C.POINTER(_vp)]),
@@ -49,6 +52,7 @@ SYMBOLS = {
     "sph_fluid_add": (C.c_int, [_vp, _fp, _fp, _fp, C.c_size_t, C.c_float, C.c_uint32, C.c_uint32,
                                 C.POINTER(C.c_uint32)]),
     "sph_fluid_push_force": (C.c_int, [_vp, C.c_uint32, C.POINTER(ForceDesc)]),
+    "sph_fluid_push_host_force": (C.c_int, [_vp, C.c_uint32, HOST_FORCE_FN, _vp]),
     "sph_fluid_append": (C.c_int, [_vp, C.c_uint32, _fp, _fp, C.c_size_t]),
     "sph_fluid_delete": (C.c_int, [_vp, C.c_uint32, _u8p, C.c_size_t]),
     "sph_fluid_write": (C.c_int, [_vp, C.c_uint32, _fp, _fp, C.c_size_t]),

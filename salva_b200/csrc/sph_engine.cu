@@ -70,8 +70,11 @@ struct ForceRec;
 }  // namespace
 struct sph_world;
 namespace {
+constexpr int FORCE_HOST_CALLBACK = 100;  // internal kind of sph_fluid_push_host_force entries
 struct ForceRec {
     sph_force_desc d;
+    sph_host_force_fn host_fn = nullptr;
+    void* host_user = nullptr;
     ElasticityState* elastic = nullptr;  // Becker2009 rest-pose state (sph_elasticity.cuh)
 };
 struct FluidRec {
@@ -1162,6 +1165,31 @@ sph_status phase_forces(sph_world* w) {
                 case SPH_FORCE_BECKER2009_ELASTICITY:
                     TRY(elasticity_solve(w, (uint32_t)f, fr));
                     break;
+                case FORCE_HOST_CALLBACK: {  // user-defined NonPressureForce::solve on the host (nonpressure_force.rs:10-30)
+                    FluidRec& fl = w->fluids[f];
+                    if (fl.n == 0) break;
+                    const uint32_t ob = w->own_begin;
+                    const size_t Nf = fl.n;
+                    CU(w->o_a.ensure(3 * N));
+                    CU(w->o_b.ensure(3 * N));
+                    CU(w->o_c.ensure(3 * std::max(N, w->B)));
+                    CU(w->o_mass.ensure(N));
+                    LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p + ob, w->pos[c].p + ob, w->o_a.p);
+                    LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p + ob, w->vel[c].p + ob, w->o_b.p);
+                    LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p + ob, w->acc.p + ob, w->o_c.p);
+                    LAUNCH(k_export1, N, 256, (uint32_t)N, w->orig[c].p + ob, w->dens.p + ob, w->o_mass.p);
+                    std::vector<float> hp(3 * Nf), hv(3 * Nf), ha(3 * Nf), hd(Nf);
+                    CU(cudaMemcpyAsync(hp.data(), w->o_a.p + 3 * fl.offset, 3 * Nf * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+                    CU(cudaMemcpyAsync(hv.data(), w->o_b.p + 3 * fl.offset, 3 * Nf * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+                    CU(cudaMemcpyAsync(ha.data(), w->o_c.p + 3 * fl.offset, 3 * Nf * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+                    CU(cudaMemcpyAsync(hd.data(), w->o_mass.p + fl.offset, Nf * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+                    CU(cudaStreamSynchronize(w->st));
+                    fr.host_fn(fr.host_user, w->dt, w->inv_dt, w->h, Nf, hp.data(), hv.data(), hd.data(), ha.data());
+                    CU(cudaMemcpyAsync(w->o_c.p + 3 * fl.offset, ha.data(), 3 * Nf * sizeof(float), cudaMemcpyHostToDevice, w->st));
+                    LAUNCH(k_import_acc, N, 256, (uint32_t)N, w->orig[c].p + ob, w->o_c.p, (uint32_t)fl.offset, (uint32_t)(fl.offset + Nf), w->acc.p + ob);
+                    CU(cudaStreamSynchronize(w->st));  // host vectors go out of scope
+                    break;
+                }
                 default:
                     return w->fail(SPH_ERR_INVALID, "unknown force kind %d", fr.d.kind);
             }
@@ -1565,6 +1593,19 @@ sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid, const sph_force_de
     if (force->kind < 0 || force->kind > SPH_FORCE_BECKER2009_ELASTICITY) return w->fail(SPH_ERR_INVALID, "unknown force kind %d", force->kind);
     ForceRec fr;
     fr.d = *force;
+    w->fluids[fluid].forces.push_back(fr);
+    return SPH_OK;
+}
+
+sph_status sph_fluid_push_host_force(sph_world* w, uint32_t fluid, sph_host_force_fn fn, void* user) {
+    if (!w || !fn) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    ForceRec fr;
+    memset(&fr.d, 0, sizeof fr.d);
+    fr.d.kind = FORCE_HOST_CALLBACK;
+    fr.host_fn = fn;
+    fr.host_user = user;
     w->fluids[fluid].forces.push_back(fr);
     return SPH_OK;
 }

@@ -667,6 +667,14 @@ __global__ void k_export1u(uint32_t n, const uint32_t* __restrict__ orig, const 
     if (s >= n) return;
     dst[orig[s]] = (float)src[s];
 }
+// accelerations back from a host force callback: acc[s].xyz = src[orig[s]] for the particles of one fluid
+__global__ void k_import_acc(uint32_t n, const uint32_t* __restrict__ orig, const float* __restrict__ src, uint32_t lo, uint32_t hi, float4* __restrict__ acc) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t g = orig[s];
+    if (g < lo || g >= hi) return;
+    acc[s] = make_float4(src[3 * (size_t)g], src[3 * (size_t)g + 1], src[3 * (size_t)g + 2], 0.f);
+}
 __global__ void k_import1(uint32_t n, const uint32_t* __restrict__ orig, const float* __restrict__ src, float* __restrict__ dst) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;

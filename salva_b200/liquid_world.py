@@ -157,6 +157,7 @@ class LiquidWorld:
             self._w = None
             raise SphError(st, "sph_world_create failed (no CUDA device?); there is no CPU fallback")
         self._nb = {}
+        self._callbacks = []
 
     def close(self):
         if getattr(self, "_w", None):
@@ -205,6 +206,17 @@ class LiquidWorld:
         for i, x in enumerate(params):
             d.p[i] = x
         self._ck(self._L.sph_fluid_push_force(self._w, fluid, C.byref(d)))
+
+    def push_host_force(self, fluid, solve):
+        """User-defined NonPressureForce (nonpressure_force.rs:10-30): solve(dt, inv_dt, kernel_radius, positions,
+        velocities, densities, accelerations) is called on the host with numpy views in ORIGINAL index order and adds
+        to `accelerations` in place (examples3d/custom_forces3.rs:66-90)."""
+        def tramp(_user, dt, inv_dt, h, n, pos, vel, dens, acc):
+            solve(dt, inv_dt, h, np.ctypeslib.as_array(pos, (n, 3)), np.ctypeslib.as_array(vel, (n, 3)),
+                  np.ctypeslib.as_array(dens, (n,)), np.ctypeslib.as_array(acc, (n, 3)))
+        cb = _lib.HOST_FORCE_FN(tramp)
+        self._callbacks.append(cb)  # keep the trampoline alive as long as the world
+        self._ck(self._L.sph_fluid_push_host_force(self._w, fluid, cb, None))
 
     def add_boundary(self, boundary_or_positions, velocities=None, memberships=1, filter=0xFFFFFFFF,
                      want_forces=False):

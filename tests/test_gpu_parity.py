@@ -282,6 +282,34 @@ def test_boundary_rewrite_between_steps():
     assert gpu.stats()["n_contacts"] == cpu.stats()["n_contacts"]
 
 
+def test_user_defined_host_force_plugin():
+    """NonPressureForce trait objects with arbitrary host code (nonpressure_force.rs:10-30): the custom force field of
+    examples3d/custom_forces3.rs:66-90 (acc += dir / dist towards an origin), pushed BETWEEN two built-in forces."""
+    origin = np.array([0.3, 0.6, 0.2], np.float32)
+
+    def solve(dt, inv_dt, h, pos, vel, dens, acc):
+        d = origin - pos
+        sq = (d * d).sum(axis=1)
+        ok = sq > 0.1 * 0.1
+        dist = np.sqrt(sq[ok])
+        acc[ok] += (d[ok] / dist[:, None]) / dist[:, None]
+
+    sc = _small_scene(seed=37)
+    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    for w, f in ((gpu, fg[0]), (cpu, fc[0])):
+        w.push_force(f, *scenes.xsph_viscosity(0.5, 0.0))
+        w.push_host_force(f, solve)
+        w.push_force(f, *scenes.artificial_viscosity(1.0, 0.0))
+        w.force_iterations(1, 2)
+    for _ in range(4):
+        gpu.step(0.005)
+        cpu.step(0.005)
+    pg, vg = gpu.read_fluid(fg[0])
+    pc, vc = cpu.read_fluid(fc[0])
+    assert _rel(gpu.debug(fg[0], "acceleration"), cpu.debug(fc[0], "acceleration")) <= 1e-3
+    assert np.abs(pg - pc).max() <= 1e-3 * float(gpu.h)
+
+
 def test_deterministic_mode_is_bit_reproducible():
     sc = _small_scene(seed=21)
     outs = []

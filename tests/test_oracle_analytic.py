@@ -88,3 +88,22 @@ def test_first_step_has_zero_inv_dt():
     a.step(0.005)
     b.step(0.005)
     assert not np.array_equal(a.debug(fa, "acceleration"), b.debug(fb, "acceleration"))
+
+
+def test_host_force_callback_adds_to_accelerations():
+    """User-defined NonPressureForce (nonpressure_force.rs:10-30) on the oracle: a callback that cancels gravity leaves an
+    isolated particle at rest."""
+    w = OracleWorld(0.05, 2.0)
+    f = w.add_fluid(np.array([[0.0, 1.0, 0.0], [5.0, 1.0, 0.0]], np.float32))
+    seen = []
+
+    def solve(dt, inv_dt, h, pos, vel, dens, acc):
+        seen.append((dt, len(pos)))
+        acc[:, 1] += 9.81
+
+    w.push_host_force(f, solve)
+    for _ in range(3):
+        w.step(0.01)
+    p, v = w.read_fluid(f)
+    assert len(seen) == 3 and seen[0] == (0.0, 2) and seen[1][0] == pytest.approx(0.01)   # dt lags one step (dfsph_solver.rs:702)
+    assert np.abs(p - np.array([[0.0, 1.0, 0.0], [5.0, 1.0, 0.0]])).max() < 1e-6
