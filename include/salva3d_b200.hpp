@@ -73,6 +73,24 @@ struct Akinci2013SurfaceTension : NonPressureForce {  // akinci2013_surface_tens
         return d;
     }
 };
+struct He2014SurfaceTension : NonPressureForce {  // he2014_surface_tension.rs:12-29
+    Real fluid_tension_coefficient, boundary_tension_coefficient;
+    He2014SurfaceTension(Real fluid_tension_coefficient_, Real boundary_tension_coefficient_)
+        : fluid_tension_coefficient(fluid_tension_coefficient_), boundary_tension_coefficient(boundary_tension_coefficient_) {}
+    sph_force_desc descriptor() const override {
+        sph_force_desc d{SPH_FORCE_HE2014_TENSION, {fluid_tension_coefficient, boundary_tension_coefficient}};
+        return d;
+    }
+};
+struct WCSPHSurfaceTension : NonPressureForce {  // wcsph_surface_tension.rs:15-27 (boundary coefficient must be 0, see sph.h)
+    Real fluid_tension_coefficient, boundary_tension_coefficient;
+    WCSPHSurfaceTension(Real fluid_tension_coefficient_, Real boundary_tension_coefficient_)
+        : fluid_tension_coefficient(fluid_tension_coefficient_), boundary_tension_coefficient(boundary_tension_coefficient_) {}
+    sph_force_desc descriptor() const override {
+        sph_force_desc d{SPH_FORCE_WCSPH_TENSION, {fluid_tension_coefficient, boundary_tension_coefficient}};
+        return d;
+    }
+};
 struct Becker2009Elasticity : NonPressureForce {  // becker2009_elasticity.rs:60-76
     Real young_modulus, poisson_ratio;
     bool nonlinear_strain;
@@ -258,6 +276,24 @@ public:
             check(sph_boundary_read_volumes(raw_, b.handle_, b.volumes.data(), b.volumes.size()));
             if (b.want_forces_) check(sph_boundary_read_forces(raw_, b.handle_, reinterpret_cast<float*>(b.forces.data()), b.forces.size()));
         }
+    }
+    // liquid_world.rs:211-243 (ParticleId::FluidParticle(handle, i) / BoundaryParticle(handle, i)), sorted.
+    struct ParticleId {
+        bool is_boundary;
+        uint32_t handle, index;
+    };
+    std::vector<ParticleId> particles_intersecting_aabb(const Point3& mins, const Point3& maxs) {
+        const float lo[3] = {mins.x, mins.y, mins.z}, hi[3] = {maxs.x, maxs.y, maxs.z};
+        std::vector<uint32_t> k(256), h(256), i(256);
+        size_t n = 0;
+        for (;;) {
+            check(sph_world_particles_in_aabb(raw_, lo, hi, k.data(), h.data(), i.data(), k.size(), &n));
+            if (n <= k.size()) break;
+            k.resize(n); h.resize(n); i.resize(n);
+        }
+        std::vector<ParticleId> out(n);
+        for (size_t t = 0; t < n; ++t) out[t] = ParticleId{k[t] != 0, h[t], i[t]};
+        return out;
     }
     sph_step_stats counters() const {  // world.counters (counters/mod.rs:17-30)
         sph_step_stats s;

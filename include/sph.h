@@ -50,7 +50,13 @@ enum { SPH_FORCE_XSPH_VISCOSITY = 0,        /* p[0]=fluid coeff, p[1]=boundary c
        SPH_FORCE_ARTIFICIAL_VISCOSITY = 1,  /* p[0]=fluid coeff, p[1]=boundary coeff, p[2]=alpha, p[3]=beta,
                                                p[4]=speed_of_sound                      artificial_viscosity.rs:27-38 */
        SPH_FORCE_AKINCI2013_TENSION = 2,    /* p[0]=tension coeff, p[1]=adhesion coeff akinci2013_surface_tension.rs:27-35 */
-       SPH_FORCE_BECKER2009_ELASTICITY = 3  /* p[0]=young, p[1]=poisson, p[2]=nonlinear becker2009_elasticity.rs:60-76 */ };
+       SPH_FORCE_BECKER2009_ELASTICITY = 3, /* p[0]=young, p[1]=poisson, p[2]=nonlinear becker2009_elasticity.rs:60-76 */
+       SPH_FORCE_HE2014_TENSION = 4,        /* p[0]=fluid tension coeff, p[1]=boundary tension coeff
+                                               he2014_surface_tension.rs:21-29 */
+       SPH_FORCE_WCSPH_TENSION = 5          /* p[0]=fluid tension coeff, p[1]=boundary tension coeff (must be 0: the
+                                               reference's boundary loop walks the FLUID contact list and indexes
+                                               boundaries with it, wcsph_surface_tension.rs:66-83)
+                                               wcsph_surface_tension.rs:21-27 */ };
 
 typedef struct {
     int32_t  solver;                 /* SPH_SOLVER_* */
@@ -160,6 +166,15 @@ sph_status sph_boundary_write(sph_world* w, uint32_t boundary, const float* pos_
 sph_status sph_boundary_read_forces(sph_world* w, uint32_t boundary, float* f_xyz, size_t cap);
 /* boundary.volumes after compute_boundary_volumes (dfsph_solver.rs:72-96). */
 sph_status sph_boundary_read_volumes(sph_world* w, uint32_t boundary, float* volumes, size_t cap);
+
+/* LiquidWorld::particles_intersecting_aabb  liquid_world.rs:211-243: the particles of the cells [key(mins), key(maxs)]
+ * of the grid built by the LAST step (hgrid.rs:122-133) whose CURRENT position is closer than particle_radius to the
+ * box.  Entry k is (kinds[k] = 0 fluid / 1 boundary, handles[k], indices[k] = index inside that object), sorted by
+ * (kind, handle, index) — the reference's order is hash-map order.  *n = number found (may exceed cap; only cap
+ * entries are written).  Empty before the first step, like the reference's empty grid.  SPH_ERR_INVALID while host
+ * edits (write/append/delete) are pending: the cell grid of the last step no longer describes those particles. */
+sph_status sph_world_particles_in_aabb(sph_world* w, const float mins[3], const float maxs[3], uint32_t* kinds, uint32_t* handles,
+                                       uint32_t* indices, size_t cap, size_t* n);
 
 /* LiquidWorld::step  liquid_world.rs:62-158 */
 sph_status sph_world_step(sph_world* w, float dt, const float gravity[3]);

@@ -251,6 +251,77 @@ class NumpyDFSPH:
                                       np.maximum(-F(4) * r * r / h + F(6) * r - F(2) * h, F(0)) ** F(0.25), F(0)).astype(F)
                         av = np.where((ok & self.Mfb & sel[:, None])[..., None], dirs * ak[..., None], F(0)).astype(F)
                         acc = (acc - (av * (adh * self.mb)[..., None]).sum(axis=1, dtype=F)).astype(F)
+                elif kind == 4:  # He 2014 (he2014_surface_tension.rs:40-178)
+                    cf, cb = F(p[0]), F(p[1])
+                    mfb = self.Mfb & sel[:, None]
+                    colors = (np.where(sm, self.Wff * self.mass[None, :] / self.dens[None, :], F(0)).sum(axis=1, dtype=F)
+                              + np.where(mfb, self.Wfb * self.bvol[None, :], F(0)).sum(axis=1, dtype=F)).astype(F)
+                    cj = np.where(sm, colors[None, :] * self.mass[None, :] / self.dens[None, :], F(0)).astype(F)
+                    gradc = (self.Gff * cj[..., None]).sum(axis=1, dtype=F)
+                    q = (gradc / np.where(sel, colors, F(1))[:, None]).astype(F)
+                    gc = np.where(sel, (q * q).sum(axis=1, dtype=F), F(0)).astype(F)
+                    mi = self.mass
+                    if cf != 0:
+                        c = np.where(sm, mi[:, None] / self.dens[:, None] * self.mass[None, :] / self.dens[None, :]
+                                     * (gc[:, None] + gc[None, :]) / F(2), F(0)).astype(F)
+                        a = (self.Gff * c[..., None]).sum(axis=1, dtype=F) * (cf / (F(2) * mi))[:, None]
+                        acc = (acc + np.where(sel[:, None], a, F(0))).astype(F)
+                    if cb != 0 and len(self.BP):
+                        c = np.where(mfb, mi[:, None] / self.dens[:, None] * self.mb / self.rho0[:, None] * gc[:, None] * cb * F(0.25),
+                                     F(0)).astype(F)
+                        a = (self.Gfb * c[..., None]).sum(axis=1, dtype=F) / mi[:, None]
+                        acc = (acc + np.where(sel[:, None], a, F(0))).astype(F)
+                elif kind == 5:  # WCSPH fluid term (wcsph_surface_tension.rs:45-63)
+                    cf = F(p[0])
+                    c = np.where(sm, -cf * self.Wff * self.mass[None, :] / self.mass[:, None], F(0)).astype(F)
+                    acc = (acc + (self.Dff * c[..., None]).sum(axis=1, dtype=F)).astype(F)
+                elif kind == 6:  # DFSPHViscosity (dfsph_viscosity.rs:133-324), dense restatement with LAPACK inverses
+                    visc, min_it, max_it, max_err = F(p[0]), int(p[1]), int(p[2]), F(p[3])
+                    idx = np.nonzero(sel)[0]
+                    G = self.Gff
+                    Z = np.zeros_like(G[..., 0])
+                    mat = np.stack([np.stack([G[..., 0] * 2, Z, Z], -1), np.stack([Z, G[..., 1] * 2, Z], -1),
+                                    np.stack([Z, Z, G[..., 2] * 2], -1), np.stack([G[..., 1], G[..., 0], Z], -1),
+                                    np.stack([G[..., 2], Z, G[..., 0]], -1), np.stack([Z, G[..., 2], G[..., 1]], -1)], -2).astype(F)  # N,N,6,3
+                    sc = np.where(sm, self.mass[None, :] / (F(2) * self.dens[:, None]), F(0)).astype(F)
+                    gi = (mat * sc[..., None, None]).astype(F)
+                    sq = (np.einsum("ijrk,ijck->ijrc", gi, gi).astype(F) / self.dens[:, None, None, None]).sum(axis=1, dtype=F)
+                    gs = gi.sum(axis=1, dtype=F)
+                    den = (sq + np.einsum("irk,ick->irc", gs, gs).astype(F) / self.dens[:, None, None]).astype(F)
+                    betas = np.zeros((len(self.P), 6, 6), F)
+                    for i in idx:
+                        d = den[i].copy()
+                        dg = np.diag(d).copy()
+                        inv_diag = np.where(np.abs(dg) < F(1e-6), F(1), F(1) / np.where(dg == 0, F(1), dg)).astype(F)
+                        d[:, :3] *= inv_diag[:, None]
+                        if abs(np.linalg.det(d.astype(np.float64))) >= 1e-6:
+                            b = np.linalg.inv(d.astype(np.float64)).astype(F)
+                            b[:, :3] *= inv_diag[None, :3]
+                            betas[i] = b
+                    dtl = self.dt
+
+                    def rates(a):
+                        vv = (self.V + a * dtl).astype(F)
+                        vji = (vv[None, :, :] - vv[:, None, :]).astype(F)
+                        r6 = np.stack([F(2) * vji[..., 0] * G[..., 0], F(2) * vji[..., 1] * G[..., 1], F(2) * vji[..., 2] * G[..., 2],
+                                       vji[..., 0] * G[..., 1] + vji[..., 1] * G[..., 0], vji[..., 0] * G[..., 2] + vji[..., 2] * G[..., 0],
+                                       vji[..., 1] * G[..., 2] + vji[..., 2] * G[..., 1]], -1).astype(F)
+                        return (r6 * sc[..., None]).sum(axis=1, dtype=F)
+
+                    target = (rates(acc) * (F(1) - visc)).astype(F)
+                    self.visc_iters = 0
+                    for it in range(max_it):
+                        err6 = (rates(acc) - target).astype(F)
+                        avg = F(np.abs(err6[idx]).sum(axis=1, dtype=F).sum(dtype=F) / F(6) / F(max(len(idx), 1)))
+                        self.visc_err = avg
+                        if avg <= max_err and it >= min_it:
+                            break
+                        u = (np.einsum("irk,ik->ir", betas, err6).astype(F) / (self.dens * self.dens)[:, None]).astype(F)
+                        co = np.where(sm[..., None], (u[:, None, :] + u[None, :, :]) * (self.mass[None, :, None] / F(2)), F(0)).astype(F)
+                        t = np.einsum("ijrk,ijr->ijk", mat, co).astype(F)
+                        a = t.sum(axis=1, dtype=F) * (self.mass * self.inv_dt)[:, None]
+                        acc = (acc + np.where(sel[:, None], a, F(0))).astype(F)
+                        self.visc_iters += 1
                 else:
                     raise NotImplementedError(kind)
         return acc

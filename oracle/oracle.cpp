@@ -21,6 +21,7 @@
 // contraction is disabled because rustc never fuses a*b+c).
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -42,6 +43,7 @@ struct V3 {
 static inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 static inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 static inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+static inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
 static inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
 static inline V3& operator+=(V3& a, V3 b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
 static inline V3& operator-=(V3& a, V3 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; return a; }
@@ -146,7 +148,7 @@ struct ParticlesContacts {
     }
 };
 
-enum ForceKind { F_XSPH = 0, F_ARTIFICIAL = 1, F_AKINCI = 2, F_BECKER = 3, F_HOST = 100 };
+enum ForceKind { F_XSPH = 0, F_ARTIFICIAL = 1, F_AKINCI = 2, F_BECKER = 3, F_HE2014 = 4, F_WCSPH = 5, F_DFSPH_VISC = 6, F_HOST = 100 };
 typedef void (*host_force_fn)(void* user, float dt, float inv_dt, float kernel_radius, size_t n, const float* pos, const float* vel, const float* dens,
                               float* acc);
 
@@ -173,6 +175,13 @@ struct Force {
     void* host_user = nullptr;
     // Akinci2013: normals (akinci2013_surface_tension.rs:23)
     std::vector<V3> normals;
+    // He2014: colors, squared colour-gradient norms (he2014_surface_tension.rs:16-17)
+    std::vector<float> colors, gradcs;
+    // DFSPHViscosity: betas (6x6 row-major), strain-rate targets / errors (dfsph_viscosity.rs:99-100)
+    std::vector<std::array<float, 36>> betas;
+    std::vector<std::array<float, 6>> sr_target, sr_error;
+    uint32_t visc_iters = 0;
+    float visc_err = 0.f;
     // Becker2009 state (becker2009_elasticity.rs:48-58)
     float d0 = 0, d1 = 0, d2 = 0;
     std::vector<float> volumes0;
@@ -747,6 +756,297 @@ static void solve_akinci(World& w, size_t f, Force& fc) {
     }
 }
 
+// ---- surface_tension/he2014_surface_tension.rs:31-180 --------------------------------------------
+static void solve_he2014(World& w, size_t f, Force& fc) {
+    Fluid& fl = w.fluids[f];
+    const float cf = fc.p[0], cb = fc.p[1];
+    const std::vector<float>& dens = w.densities[f];
+    if (fc.gradcs.size() != fl.n()) {  // init :31-38
+        fc.gradcs.resize(fl.n(), 0.f);
+        fc.colors.resize(fl.n(), 0.f);
+    }
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)fl.n(); ++i) {  // compute_colors :40-75
+        float color = 0.f;
+        for (const Contact& c : w.ff[f].lists[i])
+            if (c.i_model == c.j_model) color += c.weight * fl.mass(c.j) / dens[c.j];
+        for (const Contact& c : w.fb[f].lists[i]) color += c.weight * w.boundaries[c.j_model].volumes[c.j];
+        fc.colors[i] = color;
+    }
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)fl.n(); ++i) {  // compute_gradc :77-105
+        V3 gradc = ZERO3;
+        for (const Contact& c : w.ff[f].lists[i])
+            if (c.i_model == c.j_model) gradc += c.gradient * fc.colors[c.j] * fl.mass(c.j) / dens[c.j];
+        V3 q = gradc / fc.colors[i];
+        fc.gradcs[i] = norm2(q);
+    }
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)fl.n(); ++i) {  // forces :131-178
+        V3 acc = fl.accelerations[i];
+        const float mi = fl.volumes[i] * fl.density0;
+        if (cf != 0.f)
+            for (const Contact& c : w.ff[f].lists[i])
+                if (c.i_model == c.j_model) {
+                    float mj = fl.volumes[c.j] * fl.density0;
+                    float gradsum = fc.gradcs[c.i] + fc.gradcs[c.j];
+                    V3 fo = c.gradient * (mi / dens[c.i] * mj / dens[c.j] * gradsum / 2.0f);
+                    acc += fo * (cf / (2.0f * mi));
+                }
+        if (cb != 0.f)
+            for (const Contact& c : w.fb[f].lists[i]) {
+                Boundary& b = w.boundaries[c.j_model];
+                float mj = b.volumes[c.j] * fl.density0;
+                float gradsum = fc.gradcs[c.i];
+                V3 fo = c.gradient * (mi / dens[c.i] * mj / fl.density0 * gradsum * cb * 0.25f);
+                acc += fo / mi;
+                b.apply_force(c.j, fo * -1.0f);
+            }
+        fl.accelerations[i] = acc;
+    }
+}
+
+// ---- nalgebra 0.33 (crates.io dependency, build/salva3d/Cargo.toml:42; not vendored): linalg/lu.rs ------------------
+// LU::new — partial pivoting (icamax = FIRST largest |.| of the column), multipliers scaled by the RECIPROCAL of the
+// pivot (`coeffs *= inv_diag`), trailing update `down[:,k] = (-pivot_row[k]) * coeffs + down[:,k]` (axpy, no FMA);
+// determinant = product of the diagonal times the permutation sign; try_inverse = permute identity, forward
+// substitution with unit diagonal (column axpy form), back substitution (`coeff = b[i] / diag`), None on a zero pivot.
+struct LU6 {
+    float a[6][6];
+    int swaps[6][2];
+    int nswaps = 0;
+};
+static void lu6_new(const float m[6][6], LU6& lu) {
+    std::memcpy(lu.a, m, sizeof lu.a);
+    lu.nswaps = 0;
+    for (int i = 0; i < 6; ++i) {
+        int piv = i;
+        float best = std::fabs(lu.a[i][i]);
+        for (int r = i + 1; r < 6; ++r)
+            if (std::fabs(lu.a[r][i]) > best) {
+                best = std::fabs(lu.a[r][i]);
+                piv = r;
+            }
+        float diag = lu.a[piv][i];
+        if (diag == 0.f) continue;
+        if (piv != i) {
+            lu.swaps[lu.nswaps][0] = i;
+            lu.swaps[lu.nswaps][1] = piv;
+            lu.nswaps++;
+            for (int c = 0; c < 6; ++c) std::swap(lu.a[i][c], lu.a[piv][c]);
+        }
+        float inv_diag = 1.0f / diag;
+        for (int r = i + 1; r < 6; ++r) lu.a[r][i] *= inv_diag;
+        for (int k = i + 1; k < 6; ++k) {
+            float mp = -lu.a[i][k];
+            for (int r = i + 1; r < 6; ++r) lu.a[r][k] = mp * lu.a[r][i] + lu.a[r][k];
+        }
+    }
+}
+static float lu6_determinant(const LU6& lu) {
+    float res = 1.f;
+    for (int i = 0; i < 6; ++i) res *= lu.a[i][i];
+    return (lu.nswaps & 1) ? res * -1.f : res * 1.f;
+}
+static bool lu6_try_inverse(const LU6& lu, float out[6][6]) {
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) out[r][c] = r == c ? 1.f : 0.f;
+    for (int sidx = 0; sidx < lu.nswaps; ++sidx)
+        for (int c = 0; c < 6; ++c) std::swap(out[lu.swaps[sidx][0]][c], out[lu.swaps[sidx][1]][c]);
+    for (int k = 0; k < 6; ++k) {  // solve_lower_triangular_with_diag_mut(b, 1)
+        for (int i = 0; i < 5; ++i) {
+            float coeff = out[i][k] / 1.0f;
+            for (int r = i + 1; r < 6; ++r) out[r][k] = (-coeff) * lu.a[r][i] + out[r][k];
+        }
+    }
+    for (int k = 0; k < 6; ++k) {  // solve_upper_triangular_mut
+        for (int i = 5; i >= 0; --i) {
+            float diag = lu.a[i][i];
+            if (diag == 0.f) return false;
+            float coeff = out[i][k] / diag;
+            out[i][k] = coeff;
+            for (int r = 0; r < i; ++r) out[r][k] = (-coeff) * lu.a[r][i] + out[r][k];
+        }
+    }
+    return true;
+}
+
+// ---- viscosity/dfsph_viscosity.rs -----------------------------------------------------------------
+// compute_gradient_matrix :59-82 (6x3, dim3)
+static inline void visc_gradient_matrix(V3 g, float m[6][3]) {
+    const float r[6][3] = {{g.x * 2.f, 0.f, 0.f}, {0.f, g.y * 2.f, 0.f}, {0.f, 0.f, g.z * 2.f}, {g.y, g.x, 0.f}, {g.z, 0.f, g.x}, {0.f, g.z, g.y}};
+    std::memcpy(m, r, sizeof r);
+}
+// compute_strain_rate :38-57
+static inline void visc_strain_rate(V3 g, V3 v, float out[6]) {
+    out[0] = 2.f * v.x * g.x;
+    out[1] = 2.f * v.y * g.y;
+    out[2] = 2.f * v.z * g.z;
+    out[3] = v.x * g.y + v.y * g.x;
+    out[4] = v.x * g.z + v.z * g.x;
+    out[5] = v.y * g.z + v.z * g.y;
+}
+// compute_betas :133-201
+static void visc_compute_betas(World& w, size_t f, Force& fc) {
+    Fluid& fl = w.fluids[f];
+    const std::vector<float>& dens = w.densities[f];
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)fl.n(); ++i) {
+        float grad_sum[6][3] = {}, sq[6][6] = {};
+        for (const Contact& c : w.ff[f].lists[i])
+            if (c.i_model == c.j_model) {
+                float mat[6][3], gi[6][3];
+                visc_gradient_matrix(c.gradient, mat);
+                const float s = fl.mass(c.j) / (2.0f * dens[c.i]);
+                for (int r = 0; r < 6; ++r)
+                    for (int k = 0; k < 3; ++k) gi[r][k] = mat[r][k] * s;
+                for (int r = 0; r < 6; ++r)
+                    for (int cc = 0; cc < 6; ++cc) {
+                        float e = gi[r][0] * gi[cc][0];
+                        e += gi[r][1] * gi[cc][1];
+                        e += gi[r][2] * gi[cc][2];
+                        sq[r][cc] += e / dens[c.i];
+                    }
+                for (int r = 0; r < 6; ++r)
+                    for (int k = 0; k < 3; ++k) grad_sum[r][k] += gi[r][k];
+            }
+        float den[6][6];
+        for (int r = 0; r < 6; ++r)
+            for (int cc = 0; cc < 6; ++cc) {
+                float e = grad_sum[r][0] * grad_sum[cc][0];
+                e += grad_sum[r][1] * grad_sum[cc][1];
+                e += grad_sum[r][2] * grad_sum[cc][2];
+                den[r][cc] = sq[r][cc] + e / dens[i];
+            }
+        float inv_diag[6];  // "Preconditionner" :162-174 (only the first SPATIAL_DIM columns are scaled)
+        for (int k = 0; k < 6; ++k) inv_diag[k] = std::fabs(den[k][k]) < 1.0e-6f ? 1.f : 1.f / den[k][k];
+        for (int cc = 0; cc < 3; ++cc)
+            for (int r = 0; r < 6; ++r) den[r][cc] *= inv_diag[r];
+        LU6 lu;  // :185-191 (the dim3 block :176-184 is overwritten by this one)
+        lu6_new(den, lu);
+        float inv[6][6];
+        std::array<float, 36>& beta = fc.betas[i];
+        if (std::fabs(lu6_determinant(lu)) < 1.0e-6f || !lu6_try_inverse(lu, inv)) {
+            beta.fill(0.f);
+        } else {
+            for (int r = 0; r < 6; ++r)
+                for (int cc = 0; cc < 6; ++cc) beta[r * 6 + cc] = inv[r][cc];
+        }
+        for (int cc = 0; cc < 3; ++cc)  // :193-196
+            for (int r = 0; r < 6; ++r) beta[r * 6 + cc] *= inv_diag[cc];
+    }
+}
+// compute_strain_rates :203-252
+static float visc_compute_strain_rates(World& w, size_t f, Force& fc, bool compute_error) {
+    Fluid& fl = w.fluids[f];
+    const std::vector<float>& dens = w.densities[f];
+    const float visc = fc.p[0];
+    double total = 0.0;
+    std::vector<float> per(fl.n(), 0.f);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)fl.n(); ++i) {
+        float rate[6] = {};
+        for (const Contact& c : w.ff[f].lists[i])
+            if (c.i_model == c.j_model) {
+                V3 v_i = fl.velocities[c.i] + fl.accelerations[c.i] * w.dt;
+                V3 v_j = fl.velocities[c.j] + fl.accelerations[c.j] * w.dt;
+                float r6[6];
+                visc_strain_rate(c.gradient, v_j - v_i, r6);
+                const float s = fl.mass(c.j) / (2.0f * dens[c.i]);
+                for (int k = 0; k < 6; ++k) rate[k] += r6[k] * s;
+            }
+        if (compute_error) {
+            float l1 = 0.f;
+            for (int k = 0; k < 6; ++k) {
+                fc.sr_error[i][k] = rate[k] - fc.sr_target[i][k];
+                l1 += std::fabs(fc.sr_error[i][k]);
+            }
+            per[i] = l1 / 6.0f;
+        } else {
+            for (int k = 0; k < 6; ++k) fc.sr_target[i][k] = rate[k] * (1.0f - visc);
+        }
+    }
+    float err = 0.f;  // par_reduce_sum: f32 sum (order unspecified in the reference)
+    for (size_t i = 0; i < fl.n(); ++i) err += per[i];
+    (void)total;
+    return fl.n() ? std::max(0.f, err / (float)fl.n()) : 0.f;
+}
+// compute_accelerations :254-289
+static void visc_compute_accelerations(World& w, size_t f, Force& fc) {
+    Fluid& fl = w.fluids[f];
+    const std::vector<float>& dens = w.densities[f];
+    std::vector<std::array<float, 6>> u(fl.n());
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)fl.n(); ++i) {  // u = betas * error / rho^2 (per particle; the reference recomputes it per contact)
+        const std::array<float, 36>& b = fc.betas[i];
+        for (int r = 0; r < 6; ++r) {
+            float e = b[r * 6 + 0] * fc.sr_error[i][0];
+            for (int k = 1; k < 6; ++k) e += b[r * 6 + k] * fc.sr_error[i][k];
+            u[i][r] = e / (dens[i] * dens[i]);
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)fl.n(); ++i) {
+        V3 acc = fl.accelerations[i];
+        for (const Contact& c : w.ff[f].lists[i])
+            if (c.i_model == c.j_model) {
+                float co[6];
+                const float hm = fl.volumes[c.j] * fl.density0 / 2.0f;
+                for (int k = 0; k < 6; ++k) co[k] = (u[c.i][k] + u[c.j][k]) * hm;
+                const V3 g = c.gradient;  // gradient.tr_mul(&coeff): sequential dot products over the 6 rows
+                V3 t = {(g.x * 2.f) * co[0] + g.y * co[3] + g.z * co[4], (g.y * 2.f) * co[1] + g.x * co[3] + g.z * co[5],
+                        (g.z * 2.f) * co[2] + g.x * co[4] + g.y * co[5]};
+                acc += t * (fl.volumes[c.i] * fl.density0 * w.inv_dt);
+            }
+        fl.accelerations[i] = acc;
+    }
+}
+// DFSPHViscosity::solve :292-324 (p[0] = viscosity coefficient, p[1] = min iter, p[2] = max iter, p[3] = max error)
+static void solve_dfsph_viscosity(World& w, size_t f, Force& fc) {
+    Fluid& fl = w.fluids[f];
+    if (fc.betas.size() != fl.n()) {  // init :126-131
+        std::array<float, 36> z36;
+        z36.fill(0.f);
+        std::array<float, 6> z6;
+        z6.fill(0.f);
+        fc.betas.resize(fl.n(), z36);
+        fc.sr_target.resize(fl.n(), z6);
+        fc.sr_error.resize(fl.n(), z6);
+    }
+    const uint32_t min_iter = (uint32_t)fc.p[1], max_iter = (uint32_t)fc.p[2];
+    const float max_error = fc.p[3];
+    visc_compute_betas(w, f, fc);
+    visc_compute_strain_rates(w, f, fc, false);
+    fc.visc_iters = 0;
+    for (uint32_t i = 0; i < max_iter; ++i) {
+        float avg_err = visc_compute_strain_rates(w, f, fc, true);
+        fc.visc_err = avg_err;
+        if (avg_err <= max_error && i >= min_iter) break;
+        visc_compute_accelerations(w, f, fc);
+        fc.visc_iters++;
+    }
+}
+
+// ---- surface_tension/wcsph_surface_tension.rs:29-86 ---------------------------------------------
+// Only the fluid term: the reference's boundary loop (:66-83) iterates fluid_fluid_contacts and indexes
+// `boundaries[c.j_model].positions[c.j]` with FLUID ids (out-of-bounds panic or garbage), so a non-zero boundary
+// coefficient is rejected at push time by both this restatement and the CUDA path.
+static void solve_wcsph(World& w, size_t f, Force& fc) {
+    Fluid& fl = w.fluids[f];
+    const float cf = fc.p[0];
+    if (cf == 0.f) return;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)fl.n(); ++i) {
+        V3 acc = fl.accelerations[i];
+        for (const Contact& c : w.ff[f].lists[i])
+            if (c.i_model == c.j_model) {
+                V3 dpos = fl.positions[c.i] - fl.positions[c.j];
+                acc += dpos * (-cf * c.weight * fl.volumes[c.j] * fl.density0 / (fl.volumes[c.i] * fl.density0));
+            }
+        fl.accelerations[i] = acc;
+    }
+}
+
 // ---- geometry/contacts.rs:403-446 + hgrid.rs:93-103 (27-cell stencil, self included) -----------
 static void compute_self_contacts(float h, const Fluid& fl, ParticlesContacts& pc) {
     pc.reset(fl.n());
@@ -932,6 +1232,9 @@ static void predict_advection(World& w, V3 gravity) {
                 case F_ARTIFICIAL: solve_artificial(w, f, fc); break;
                 case F_AKINCI: solve_akinci(w, f, fc); break;
                 case F_BECKER: solve_becker(w, f, fc); break;
+                case F_HE2014: solve_he2014(w, f, fc); break;
+                case F_WCSPH: solve_wcsph(w, f, fc); break;
+                case F_DFSPH_VISC: solve_dfsph_viscosity(w, f, fc); break;
                 case F_HOST: {
                     Fluid& fl = w.fluids[f];
                     fc.host_fn(fc.host_user, w.dt, w.inv_dt, w.h, fl.n(), &fl.positions[0].x, &fl.velocities[0].x, w.densities[f].data(),
@@ -1333,11 +1636,50 @@ int orc_fluid_add(void* p, const float* pos, const float* vel, const float* volu
 int orc_fluid_push_force(void* p, uint32_t fluid, int kind, const float* params) {
     World& w = *(World*)p;
     if (fluid >= w.fluids.size()) return 1;
+    if (kind == F_WCSPH && params[1] != 0.f) return 1;  // see solve_wcsph
     Force f;
     f.kind = kind;
     std::memcpy(f.p, params, sizeof f.p);
     w.fluids[fluid].forces.push_back(std::move(f));
     return 0;
+}
+// LiquidWorld::particles_intersecting_aabb liquid_world.rs:211-243 over hgrid.rs:122-133 (cells key(mins)..=key(maxs) of the
+// grid of the last step; distance of the CURRENT position to the box < particle_radius).  Output sorted by
+// (kind, handle, index); returns the number found.
+size_t orc_particles_in_aabb(void* p, const float* mins, const float* maxs, uint32_t* kinds, uint32_t* handles, uint32_t* indices, size_t cap) {
+    World& w = *(World*)p;
+    CellKey a = cell_key({mins[0], mins[1], mins[2]}, w.h), b = cell_key({maxs[0], maxs[1], maxs[2]}, w.h);
+    struct Hit {
+        uint32_t kind, handle, index;
+        bool operator<(const Hit& o) const { return kind != o.kind ? kind < o.kind : handle != o.handle ? handle < o.handle : index < o.index; }
+    };
+    std::vector<Hit> hits;
+    auto dist_ok = [&](V3 pt) {  // Aabb::distance_to_point(solid = true): norm of the per-axis excess
+        float dx = std::max(std::max(mins[0] - pt.x, pt.x - maxs[0]), 0.f);
+        float dy = std::max(std::max(mins[1] - pt.y, pt.y - maxs[1]), 0.f);
+        float dz = std::max(std::max(mins[2] - pt.z, pt.z - maxs[2]), 0.f);
+        return std::sqrt((dx * dx + dy * dy) + dz * dz) < w.particle_radius;
+    };
+    for (const auto& kv : w.grid) {
+        const CellKey& k = kv.first;
+        if (k.x < a.x || k.x > b.x || k.y < a.y || k.y > b.y || k.z < a.z || k.z > b.z) continue;
+        for (const GridEntry& e : kv.second) {
+            if (e.is_boundary) {
+                if (e.model < w.boundaries.size() && e.particle < w.boundaries[e.model].n() && dist_ok(w.boundaries[e.model].positions[e.particle]))
+                    hits.push_back({1u, e.model, e.particle});
+            } else {
+                if (e.model < w.fluids.size() && e.particle < w.fluids[e.model].n() && dist_ok(w.fluids[e.model].positions[e.particle]))
+                    hits.push_back({0u, e.model, e.particle});
+            }
+        }
+    }
+    std::sort(hits.begin(), hits.end());
+    for (size_t k = 0; k < hits.size() && k < cap; ++k) {
+        kinds[k] = hits[k].kind;
+        handles[k] = hits[k].handle;
+        indices[k] = hits[k].index;
+    }
+    return hits.size();
 }
 int orc_fluid_push_host_force(void* p, uint32_t fluid, host_force_fn fn, void* user) {
     World& w = *(World*)p;

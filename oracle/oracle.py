@@ -55,6 +55,9 @@ def lib():
         L.orc_world_destroy.argtypes = [vp]
         L.orc_fluid_add.argtypes = [vp, fp, fp, fp, C.c_size_t, C.c_float, C.c_uint32, C.c_uint32]
         L.orc_fluid_push_force.argtypes = [vp, C.c_uint32, C.c_int, fp]
+        u32p = C.POINTER(C.c_uint32)
+        L.orc_particles_in_aabb.argtypes = [vp, fp, fp, u32p, u32p, u32p, C.c_size_t]
+        L.orc_particles_in_aabb.restype = C.c_size_t
         L.orc_fluid_append.argtypes = [vp, C.c_uint32, fp, fp, C.c_size_t]
         L.orc_fluid_push_host_force.argtypes = [vp, C.c_uint32, HOST_FORCE_FN, vp]
         L.orc_fluid_delete.argtypes = [vp, C.c_uint32, u8p, C.c_size_t]
@@ -129,6 +132,21 @@ class OracleWorld:
         pr = np.zeros(8, np.float32)
         pr[:len(params)] = params
         assert self._L.orc_fluid_push_force(self._w, fluid, kind, _fp(pr)) == 0
+
+    def particles_intersecting_aabb(self, mins, maxs):
+        lo = np.ascontiguousarray(mins, np.float32)
+        hi = np.ascontiguousarray(maxs, np.float32)
+        u32p = C.POINTER(C.c_uint32)
+        cap = 1024
+        while True:
+            k = np.empty(cap, np.uint32)
+            h = np.empty(cap, np.uint32)
+            i = np.empty(cap, np.uint32)
+            n = self._L.orc_particles_in_aabb(self._w, _fp(lo), _fp(hi), k.ctypes.data_as(u32p), h.ctypes.data_as(u32p),
+                                              i.ctypes.data_as(u32p), cap)
+            if n <= cap:
+                return k[:n], h[:n], i[:n]
+            cap = n
 
     def push_host_force(self, fluid, solve):
         def tramp(_user, dt, inv_dt, h, n, pos, vel, dens, acc):

@@ -52,6 +52,8 @@ SYMBOLS = {
     "sph_fluid_add": (C.c_int, [_vp, _fp, _fp, _fp, C.c_size_t, C.c_float, C.c_uint32, C.c_uint32,
                                 C.POINTER(C.c_uint32)]),
     "sph_fluid_push_force": (C.c_int, [_vp, C.c_uint32, C.POINTER(ForceDesc)]),
+    "sph_world_particles_in_aabb": (C.c_int, [_vp, _fp, _fp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                              C.c_size_t, C.POINTER(C.c_size_t)]),
     "sph_fluid_push_host_force": (C.c_int, [_vp, C.c_uint32, HOST_FORCE_FN, _vp]),
     "sph_fluid_append": (C.c_int, [_vp, C.c_uint32, _fp, _fp, C.c_size_t]),
     "sph_fluid_delete": (C.c_int, [_vp, C.c_uint32, _u8p, C.c_size_t]),

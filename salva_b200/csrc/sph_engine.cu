@@ -201,6 +201,8 @@ struct sph_world {
     const void* tex_pvx_ptr = nullptr;
     const void* tex_vyz_ptr = nullptr;
     const void* tex_pk_ptr = nullptr;
+    DBuf<float> he_colors, he_gradc;  // He2014 colours / squared colour-gradient norms (he2014_surface_tension.rs:16-17)
+    DBuf<uint32_t> q_out, q_count;     // particles_intersecting_aabb results
     DBuf<uint32_t> d_ticket;      // last-block ticket of the in-kernel error reduction (kept at 0 between launches)
     bool errsum_ready = false;    // the last evaluation launch already reduced its partials into errsum
     DBuf<LoopCtl> d_ctl;          // device-side Jacobi loop control (sph_kernels.cuh LoopCtl)
@@ -228,6 +230,8 @@ struct sph_world {
 
     uint32_t cap_f = 64, cap_b = 32, stride = 0;
     bool lists_valid = false;
+    bool grid_ready = false;    // cstart/bstart + sorted arrays describe the last step's cell grid (AABB queries)
+    bool ever_stepped = false;
     sph_step_stats stats;
     uint64_t launches = 0;
 
@@ -390,6 +394,7 @@ sph_status stage_down(sph_world* w) {
     }
     w->staged = true;
     w->lists_valid = false;
+    w->grid_ready = false;
     return SPH_OK;
 }
 
@@ -1165,6 +1170,22 @@ sph_status phase_forces(sph_world* w) {
                 case SPH_FORCE_BECKER2009_ELASTICITY:
                     TRY(elasticity_solve(w, (uint32_t)f, fr));
                     break;
+                case SPH_FORCE_HE2014_TENSION: {
+                    if (w->tile) return w->fail(SPH_ERR_INVALID, "He2014SurfaceTension is not implemented by gather_backend 1");
+                    CU(w->he_colors.ensure(std::max(w->Ntot, w->N)));
+                    CU(w->he_gradc.ensure(std::max(w->Ntot, w->N)));
+                    DISPATCH1(k_he2014_colors, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->he_colors.p, (uint32_t)f);
+                    TRY(slab_refresh(w, w->he_colors.p, sizeof(float)));
+                    DISPATCH1(k_he2014_gradc, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->dens.p, w->he_colors.p, w->he_gradc.p, (uint32_t)f);
+                    TRY(slab_refresh(w, w->he_gradc.p, sizeof(float)));
+                    DISPATCH2(k_he2014_force, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->he_gradc.p, w->acc.p,
+                              w->bforce.p, (uint32_t)f, p[0], p[1]);
+                    break;
+                }
+                case SPH_FORCE_WCSPH_TENSION:
+                    if (w->tile) return w->fail(SPH_ERR_INVALID, "WCSPHSurfaceTension is not implemented by gather_backend 1");
+                    if (p[0] != 0.f) DISPATCH1(k_wcsph_force, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->acc.p, (uint32_t)f, p[0]);
+                    break;
                 case FORCE_HOST_CALLBACK: {  // user-defined NonPressureForce::solve on the host (nonpressure_force.rs:10-30)
                     FluidRec& fl = w->fluids[f];
                     if (fl.n == 0) break;
@@ -1375,6 +1396,8 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
     }
     if (w->Ntot + w->B == 0) return SPH_OK;
     TRY(phase_grid(w));
+    w->grid_ready = true;
+    w->ever_stepped = true;
     CU(cudaEventRecord(w->ev[EV_GRID], w->st));
     TRY(phase_neighbors(w));
     CU(cudaEventRecord(w->ev[EV_NBR], w->st));
@@ -1548,6 +1571,7 @@ void sph_world_destroy(sph_world* w) {
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     w->d_ctl.release();
     w->d_ticket.release();
+    w->he_colors.release(); w->he_gradc.release(); w->q_out.release(); w->q_count.release();
     for (auto& e : w->ev)
         if (e) cudaEventDestroy(e);
     if (w->st) cudaStreamDestroy(w->st);
@@ -1590,7 +1614,11 @@ sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid, const sph_force_de
     if (!w || !force) return SPH_ERR_INVALID;
     std::lock_guard<std::mutex> lock(g_mutex);
     if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
-    if (force->kind < 0 || force->kind > SPH_FORCE_BECKER2009_ELASTICITY) return w->fail(SPH_ERR_INVALID, "unknown force kind %d", force->kind);
+    if (force->kind < 0 || force->kind > SPH_FORCE_WCSPH_TENSION) return w->fail(SPH_ERR_INVALID, "unknown force kind %d", force->kind);
+    if (force->kind == SPH_FORCE_WCSPH_TENSION && force->p[1] != 0.f)
+        return w->fail(SPH_ERR_INVALID,
+                       "WCSPHSurfaceTension: boundary coefficient must be 0 (the reference's boundary loop indexes boundaries with fluid "
+                       "contacts, wcsph_surface_tension.rs:66-83)");
     ForceRec fr;
     fr.d = *force;
     w->fluids[fluid].forces.push_back(fr);
@@ -1791,6 +1819,78 @@ sph_status sph_boundary_read_volumes(sph_world* w, uint32_t boundary, float* vol
     if (!w || !volumes) return SPH_ERR_INVALID;
     std::lock_guard<std::mutex> lock(g_mutex);
     return boundary_export(w, boundary, volumes, cap, false);
+}
+
+// LiquidWorld::particles_intersecting_aabb liquid_world.rs:211-243
+sph_status sph_world_particles_in_aabb(sph_world* w, const float mins[3], const float maxs[3], uint32_t* kinds, uint32_t* handles, uint32_t* indices,
+                                       size_t cap, size_t* n) {
+    if (!w || !mins || !maxs || !n || (cap && (!kinds || !handles || !indices))) return SPH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    *n = 0;
+    if (!w->grid_ready) {
+        if (!w->ever_stepped) return SPH_OK;  // no step yet: the reference's grid is empty
+        return w->fail(SPH_ERR_INVALID, "particles_in_aabb: host edits are pending; the last step's cell grid no longer describes the particles");
+    }
+    if (w->b_dirty) return w->fail(SPH_ERR_INVALID, "particles_in_aabb: a boundary rewrite is pending; step first");
+    TRY(enter(w));
+    const Consts& hc = w->hc;
+    int lo[3], hi[3];
+    const int go[3] = {hc.ox, hc.oy, hc.oz}, gn[3] = {hc.nx, hc.ny, hc.nz};
+    for (int a = 0; a < 3; ++a) {  // hgrid.rs:41-52 keys, clipped to the dense grid (cells outside hold nothing)
+        lo[a] = std::max((int)std::floor(mins[a] / w->h), go[a]);
+        hi[a] = std::min((int)std::floor(maxs[a] / w->h), go[a] + gn[a] - 1);
+        if (hi[a] < lo[a]) return SPH_OK;
+    }
+    AabbQuery q;
+    q.lx = lo[0]; q.ly = lo[1]; q.lz = lo[2];
+    q.dx = hi[0] - lo[0] + 1; q.dy = hi[1] - lo[1] + 1; q.dz = hi[2] - lo[2] + 1;
+    for (int a = 0; a < 3; ++a) { q.mins[a] = mins[a]; q.maxs[a] = maxs[a]; }
+    q.radius = w->desc.particle_radius;
+    q.slot_lo = w->own_begin;
+    q.slot_hi = w->own_begin + (uint32_t)w->N;
+    const size_t cells = (size_t)q.dx * q.dy * q.dz;
+    int c = w->cur, bc = w->bcur;
+    CU(w->q_count.ensure(1));
+    size_t qcap = std::max<size_t>(w->q_out.cap / 2, 4096);
+    uint32_t found = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CU(w->q_out.ensure(2 * qcap));
+        CU(cudaMemsetAsync(w->q_count.p, 0, sizeof(uint32_t), w->st));
+        LAUNCH(k_aabb_query, cells, 128, q, w->N ? w->pos[c].p : nullptr, w->cstart.p, w->orig[c].p, w->B ? w->bpos[bc].p : nullptr, w->bstart.p,
+               w->borig[bc].p, w->q_out.p, (uint32_t)qcap, w->q_count.p);
+        CU(cudaMemcpyAsync(&found, w->q_count.p, sizeof found, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaStreamSynchronize(w->st));
+        if (found <= qcap) break;
+        qcap = found;
+    }
+    std::vector<uint32_t> raw(2 * (size_t)found);
+    if (found) CU(cudaMemcpy(raw.data(), w->q_out.p, raw.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    struct Hit {
+        uint32_t kind, handle, index;
+    };
+    std::vector<Hit> hits(found);
+    for (uint32_t k = 0; k < found; ++k) {
+        uint32_t kind = raw[2 * (size_t)k], g = raw[2 * (size_t)k + 1];
+        Hit h{kind, 0u, g};
+        if (kind == 0) {
+            for (size_t f = 0; f < w->fluids.size(); ++f)
+                if (g >= w->fluids[f].offset && g < w->fluids[f].offset + w->fluids[f].n) { h.handle = (uint32_t)f; h.index = g - (uint32_t)w->fluids[f].offset; }
+        } else {
+            for (size_t b = 0; b < w->bounds.size(); ++b)
+                if (g >= w->bounds[b].offset && g < w->bounds[b].offset + w->bounds[b].n) { h.handle = (uint32_t)b; h.index = g - (uint32_t)w->bounds[b].offset; }
+        }
+        hits[k] = h;
+    }
+    std::sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) {
+        return a.kind != b.kind ? a.kind < b.kind : a.handle != b.handle ? a.handle < b.handle : a.index < b.index;
+    });
+    *n = found;
+    for (size_t k = 0; k < hits.size() && k < cap; ++k) {
+        kinds[k] = hits[k].kind;
+        handles[k] = hits[k].handle;
+        indices[k] = hits[k].index;
+    }
+    return SPH_OK;
 }
 
 sph_status sph_world_step(sph_world* w, float dt, const float gravity[3]) {

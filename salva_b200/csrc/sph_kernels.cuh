@@ -770,6 +770,53 @@ __global__ void k_import_u32(uint32_t n, const uint32_t* __restrict__ orig, cons
     if (s < n) dst[s] = src[orig[s]];
 }
 
+// LiquidWorld::particles_intersecting_aabb liquid_world.rs:211-243 over HGrid::cells_intersecting_aabb hgrid.rs:122-133.
+// One thread per cell of the (clipped) cell box [key(mins), key(maxs)] of the grid built by the last step; the CURRENT
+// positions are tested (Aabb::distance_to_point, solid: norm of the per-axis excess) against particle_radius.
+// out[2k] = kind (0 fluid, 1 boundary), out[2k+1] = original index; order is whatever the atomics give (host sorts).
+struct AabbQuery {
+    int lx, ly, lz, dx, dy, dz;  // first cell and extent (cells) of the box
+    float mins[3], maxs[3], radius;
+    uint32_t slot_lo, slot_hi;   // owned fluid slots (ghost copies of a slab world are skipped)
+};
+__device__ __forceinline__ bool aabb_near(const AabbQuery& q, const float4& p) {
+    float ex = fmaxf(fmaxf(q.mins[0] - p.x, p.x - q.maxs[0]), 0.f);
+    float ey = fmaxf(fmaxf(q.mins[1] - p.y, p.y - q.maxs[1]), 0.f);
+    float ez = fmaxf(fmaxf(q.mins[2] - p.z, p.z - q.maxs[2]), 0.f);
+    return __fsqrt_rn(dist2_exact(ex, ey, ez)) < q.radius;
+}
+__global__ void k_aabb_query(AabbQuery q, const float4* __restrict__ pos, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ orig,
+                             const float4* __restrict__ bpos, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ borig,
+                             uint32_t* __restrict__ out, uint32_t cap, uint32_t* __restrict__ count) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)(q.dx * q.dy * q.dz)) return;
+    int cz = q.lz + (int)(t % (uint32_t)q.dz);
+    int cy = q.ly + (int)((t / (uint32_t)q.dz) % (uint32_t)q.dy);
+    int cx = q.lx + (int)(t / (uint32_t)(q.dz * q.dy));
+    int c = cell_id(cx, cy, cz);
+    if (pos) {
+        uint32_t s = max(cstart[c], q.slot_lo), e = min(cstart[c + 1], q.slot_hi);
+        for (uint32_t j = s; j < e; ++j)
+            if (aabb_near(q, pos[j])) {
+                uint32_t k = atomicAdd(count, 1u);
+                if (k < cap) {
+                    out[2 * (size_t)k] = 0u;
+                    out[2 * (size_t)k + 1] = orig[j];
+                }
+            }
+    }
+    if (bpos) {
+        for (uint32_t j = bstart[c]; j < bstart[c + 1]; ++j)
+            if (aabb_near(q, bpos[j])) {
+                uint32_t k = atomicAdd(count, 1u);
+                if (k < cap) {
+                    out[2 * (size_t)k] = 1u;
+                    out[2 * (size_t)k + 1] = borig[j];
+                }
+            }
+    }
+}
+
 __global__ void k_sum_u32(uint32_t n, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, unsigned long long* __restrict__ out) {
     unsigned long long s = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)a[i] + b[i];

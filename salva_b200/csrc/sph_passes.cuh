@@ -735,4 +735,109 @@ k_akinci_force(const float4* __restrict__ pos, const float4* __restrict__ vel, c
     acc[i] = a;
 }
 
+// ------------------------------------------------------------------------------------------------
+// He2014SurfaceTension (surface_tension/he2014_surface_tension.rs): colours -> squared colour-gradient norms -> forces.
+// ------------------------------------------------------------------------------------------------
+// pass 1: compute_colors :40-75
+template <bool MULTI>
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
+k_he2014_colors(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens,
+                float* __restrict__ colors, uint32_t which) {
+    SPH_OWNED_INDEX(i)
+    if (MULTI && fid_of(vel[i]) != which) return;
+    float4 pi = pos[i];
+    float color = 0.f;
+    for_fluid_contacts<true, false>(
+        i, pi, L, pos, [&](uint32_t j) { return FidRho{MULTI ? fid_of(__ldg(&vel[j])) : 0u, __ldg(&dens[j])}; },
+        [&](uint32_t, const Pair& p, const float4& pj, const FidRho& a) {
+            if (MULTI && a.fid != which) return;
+            color += p.w * pj.w / a.rho;  // c.weight * m_j / rho_j
+        });
+    for_boundary_contacts<true, false>(i, pi, L, bpos, [&](uint32_t, const Pair& p, const float4& pj) { color += p.w * pj.w; });  // W * vol_b
+    colors[i] = color;
+}
+
+struct FidRhoVal {
+    uint32_t fid;
+    float rho, val;
+};
+// pass 2: compute_gradc :77-105 -> |sum_j grad W_ij c_j m_j / rho_j / c_i|^2
+template <bool MULTI>
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
+k_he2014_gradc(const float4* __restrict__ pos, const float4* __restrict__ vel, Lists L, const float* __restrict__ dens, const float* __restrict__ colors,
+               float* __restrict__ gradc, uint32_t which) {
+    SPH_OWNED_INDEX(i)
+    if (MULTI && fid_of(vel[i]) != which) return;
+    float4 pi = pos[i];
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for_fluid_grads_pos<false>(
+        i, pi, L, pos, [&](uint32_t j) { return FidRhoVal{MULTI ? fid_of(__ldg(&vel[j])) : 0u, __ldg(&dens[j]), __ldg(&colors[j])}; },
+        [&](uint32_t, const Pair& p, const float4& pj, const FidRhoVal& a) {
+            if (MULTI && a.fid != which) return;
+            float c = p.g * a.val * pj.w / a.rho;
+            gx = fmaf(c, p.dx, gx); gy = fmaf(c, p.dy, gy); gz = fmaf(c, p.dz, gz);
+        });
+    float ci = colors[i];
+    float qx = gx / ci, qy = gy / ci, qz = gz / ci;
+    gradc[i] = (qx * qx + qy * qy) + qz * qz;
+}
+
+// pass 3: forces :131-178
+template <bool MULTI, bool BFORCE>
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
+k_he2014_force(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens,
+               const float* __restrict__ gradc, float4* __restrict__ acc, float* __restrict__ bforce, uint32_t which, float cf, float cb) {
+    SPH_OWNED_INDEX(i)
+    if (MULTI && fid_of(vel[i]) != which) return;
+    float4 pi = pos[i];
+    const float rho0 = C.fluids[which].density0;
+    const float mi = pi.w, rho_i = dens[i], gi = gradc[i];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (cf != 0.f) {
+        const float k = cf / (2.0f * mi);
+        for_fluid_grads_pos<false>(
+            i, pi, L, pos, [&](uint32_t j) { return FidRhoVal{MULTI ? fid_of(__ldg(&vel[j])) : 0u, __ldg(&dens[j]), __ldg(&gradc[j])}; },
+            [&](uint32_t, const Pair& p, const float4& pj, const FidRhoVal& a) {
+                if (MULTI && a.fid != which) return;
+                float s = p.g * (mi / rho_i * pj.w / a.rho * (gi + a.val) / 2.0f);
+                ax += s * p.dx * k; ay += s * p.dy * k; az += s * p.dz * k;
+            });
+    }
+    if (cb != 0.f)
+        for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+            float mj = pj.w * rho0;
+            float s = p.g * (mi / rho_i * mj / rho0 * gi * cb * 0.25f);
+            float fx = s * p.dx, fy = s * p.dy, fz = s * p.dz;
+            ax += fx / mi; ay += fy / mi; az += fz / mi;
+            if (BFORCE) {  // apply_force(c.j, -f) :175
+                atomicAdd(&bforce[3 * (size_t)j + 0], -fx);
+                atomicAdd(&bforce[3 * (size_t)j + 1], -fy);
+                atomicAdd(&bforce[3 * (size_t)j + 2], -fz);
+            }
+        });
+    float4 a = acc[i];
+    a.x += ax; a.y += ay; a.z += az;
+    acc[i] = a;
+}
+
+// WCSPHSurfaceTension fluid term (surface_tension/wcsph_surface_tension.rs:45-63): a_i -= k W_ij m_j / m_i x_ij
+template <bool MULTI>
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
+k_wcsph_force(const float4* __restrict__ pos, const float4* __restrict__ vel, Lists L, float4* __restrict__ acc, uint32_t which, float cf) {
+    SPH_OWNED_INDEX(i)
+    if (MULTI && fid_of(vel[i]) != which) return;
+    float4 pi = pos[i];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for_fluid_contacts<true, false>(
+        i, pi, L, pos, [&](uint32_t j) { return MULTI ? fid_of(__ldg(&vel[j])) : 0u; },
+        [&](uint32_t, const Pair& p, const float4& pj, uint32_t fj) {
+            if (MULTI && fj != which) return;
+            float c = -cf * p.w * pj.w / pi.w;
+            ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
+        });
+    float4 a = acc[i];
+    a.x += ax; a.y += ay; a.z += az;
+    acc[i] = a;
+}
+
 }  // namespace sphk

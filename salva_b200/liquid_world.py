@@ -84,6 +84,22 @@ class Becker2009Elasticity:
         self.params = [young_modulus, poisson_ratio, 1.0 if nonlinear_strain else 0.0]
 
 
+class He2014SurfaceTension:
+    """he2014_surface_tension.rs:21-29"""
+    kind = 4
+
+    def __init__(self, fluid_tension_coefficient, boundary_tension_coefficient):
+        self.params = [fluid_tension_coefficient, boundary_tension_coefficient]
+
+
+class WCSPHSurfaceTension:
+    """wcsph_surface_tension.rs:21-27; a non-zero boundary coefficient is rejected (include/sph.h SPH_FORCE_WCSPH_TENSION)"""
+    kind = 5
+
+    def __init__(self, fluid_tension_coefficient, boundary_tension_coefficient):
+        self.params = [fluid_tension_coefficient, boundary_tension_coefficient]
+
+
 class Fluid:
     """fluid.rs:12-68: host description handed to LiquidWorld.add_fluid."""
 
@@ -280,6 +296,24 @@ class LiquidWorld:
         self._ck(self._L.sph_boundary_read_volumes(self._w, b, _fp(vol), n))
         self._ck(self._L.sph_boundary_read_forces(self._w, b, _fp(f), n))
         return vol, f
+
+    def particles_intersecting_aabb(self, mins, maxs):
+        """liquid_world.rs:211-243 -> (kinds, handles, indices) uint32 arrays sorted by (kind, handle, index);
+        kind 0 = fluid particle, 1 = boundary particle."""
+        lo = np.ascontiguousarray(mins, np.float32)
+        hi = np.ascontiguousarray(maxs, np.float32)
+        n = C.c_size_t(0)
+        u32p = C.POINTER(C.c_uint32)
+        cap = 1024
+        while True:
+            k = np.empty(cap, np.uint32)
+            h = np.empty(cap, np.uint32)
+            i = np.empty(cap, np.uint32)
+            self._ck(self._L.sph_world_particles_in_aabb(self._w, _fp(lo), _fp(hi), k.ctypes.data_as(u32p), h.ctypes.data_as(u32p),
+                                                         i.ctypes.data_as(u32p), cap, C.byref(n)))
+            if n.value <= cap:
+                return k[:n.value], h[:n.value], i[:n.value]
+            cap = n.value
 
     # -- particle ids and multi-GPU slabs (include/sph.h "Multi-GPU") --------------------------------------
     def set_ids(self, fluid, ids):

@@ -16,7 +16,7 @@ F32 = np.float32
 GRAVITY = (0.0, -9.81, 0.0)
 
 # force kinds (include/sph.h SPH_FORCE_*)
-XSPH, ARTIFICIAL, AKINCI2013, BECKER2009 = 0, 1, 2, 3
+XSPH, ARTIFICIAL, AKINCI2013, BECKER2009, HE2014, WCSPH, DFSPH_VISCOSITY = 0, 1, 2, 3, 4, 5, 6
 DFSPH, IISPH = 0, 1
 
 
@@ -38,6 +38,21 @@ def akinci2013_surface_tension(tension, adhesion=0.0):
 def becker2009_elasticity(young, poisson, nonlinear=True):
     """Becker2009Elasticity::new(E, nu, nonlinear)  becker2009_elasticity.rs:60-76"""
     return (BECKER2009, [young, poisson, 1.0 if nonlinear else 0.0])
+
+
+def he2014_surface_tension(fluid_tension, boundary_tension=0.0):
+    """He2014SurfaceTension::new(fluid, boundary)  he2014_surface_tension.rs:21-29"""
+    return (HE2014, [fluid_tension, boundary_tension])
+
+
+def wcsph_surface_tension(fluid_tension, boundary_tension=0.0):
+    """WCSPHSurfaceTension::new(fluid, boundary)  wcsph_surface_tension.rs:21-27 (boundary term: see include/sph.h)"""
+    return (WCSPH, [fluid_tension, boundary_tension])
+
+
+def dfsph_viscosity(viscosity_coefficient, min_viscosity_iter=1, max_viscosity_iter=50, max_viscosity_error=0.01):
+    """DFSPHViscosity::new(coefficient) + public tunables  dfsph_viscosity.rs:86-124"""
+    return (DFSPH_VISCOSITY, [viscosity_coefficient, float(min_viscosity_iter), float(max_viscosity_iter), max_viscosity_error])
 
 
 def cube_fluid(ni, nj, nk, particle_rad):

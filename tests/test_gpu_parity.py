@@ -84,6 +84,75 @@ def test_trajectory_forced_iterations(forces, backend):
     assert np.abs(vg - vc).max() <= 1e-3 * h / dt
 
 
+@pytest.mark.parametrize("two_fluids", [False, True], ids=["one-fluid", "two-fluids"])
+@pytest.mark.parametrize("forces", [(scenes.he2014_surface_tension(40.0, 30.0),), (scenes.wcsph_surface_tension(2.0),)],
+                         ids=["he2014", "wcsph"])
+def test_surface_tension_rows_next(forces, two_fluids):
+    """He2014SurfaceTension (he2014_surface_tension.rs) and the fluid term of WCSPHSurfaceTension
+    (wcsph_surface_tension.rs:45-63), incl. the He2014 boundary reaction written through Boundary::apply_force."""
+    sc = _small_scene(seed=23, forces=forces, two_fluids=two_fluids, want_forces=True)
+    gpu, cpu, fg, fc, bg, bc = _pair(sc)
+    dt = 0.004
+    for w in (gpu, cpu):
+        w.force_iterations(2, 3)
+    for _ in range(6):
+        gpu.step(dt)
+        cpu.step(dt)
+    h = float(gpu.h)
+    for a, b in zip(fg, fc):
+        ag, ac = gpu.debug(a, "acceleration"), cpu.debug(b, "acceleration")
+        assert np.abs(ac - np.array([0, -9.81, 0], np.float32)).max() > 1.0      # the force is actually acting
+        assert _rel(ag, ac) <= 1e-3
+        pg, vg = gpu.read_fluid(a)
+        pc, vc = cpu.read_fluid(b)
+        assert np.abs(pg - pc).max() <= 1e-3 * h
+        assert np.abs(vg - vc).max() <= 1e-3 * h / dt
+    _, fgp = gpu.read_boundary(bg[0])
+    _, fcp = cpu.read_boundary(bc[0])
+    assert _rel(fgp, fcp) <= 1e-3
+
+
+def test_wcsph_boundary_coefficient_is_rejected():
+    from salva_b200 import SphError
+    gpu = LiquidWorld(particle_radius=0.05)
+    f = gpu.add_fluid(np.zeros((4, 3), np.float32) + np.arange(4, dtype=np.float32)[:, None] * 0.1)
+    with pytest.raises(SphError):
+        gpu.push_force(f, *scenes.wcsph_surface_tension(1.0, 0.5))
+
+
+def test_particles_intersecting_aabb_matches_oracle():
+    """liquid_world.rs:211-243: cells of the LAST step's grid, current positions, distance < particle_radius."""
+    from salva_b200 import SphError
+    sc = _small_scene(seed=29, vel_sigma=0.6)
+    gpu, cpu, fg, fc, bg, bc = _pair(sc)
+    boxes = [((0.13, -0.2, 0.11), (0.47, 0.33, 0.38)), ((-5.0, -5.0, -5.0), (5.0, 5.0, 5.0)), ((0.31, 0.2, 0.3), (0.32, 0.21, 0.31)),
+             ((7.0, 7.0, 7.0), (8.0, 8.0, 8.0))]
+    k, _, _ = gpu.particles_intersecting_aabb(*boxes[0])
+    assert len(k) == 0                                   # before the first step the reference's grid is empty
+    for w in (gpu, cpu):
+        w.force_iterations(1, 2)
+    for step in range(3):
+        gpu.step(0.004)
+        cpu.step(0.004)
+        for mins, maxs in boxes:
+            g = gpu.particles_intersecting_aabb(mins, maxs)
+            c = cpu.particles_intersecting_aabb(mins, maxs)
+            assert all(np.array_equal(a, b) for a, b in zip(g, c)), (step, mins)
+    assert len(gpu.particles_intersecting_aabb(*boxes[1])[0]) > 1000
+    # a host edit of positions keeps the stale cells but tests the new positions, exactly like the reference
+    p, v = cpu.read_fluid(fc[0])
+    p2 = (p + np.float32(0.03)).astype(np.float32)
+    gpu.write_fluid(fg[0], p2, v)
+    cpu.write_fluid(fc[0], p2, v)
+    for mins, maxs in boxes[:3]:
+        g = gpu.particles_intersecting_aabb(mins, maxs)
+        c = cpu.particles_intersecting_aabb(mins, maxs)
+        assert all(np.array_equal(a, b) for a, b in zip(g, c))
+    gpu.append_particles(fg[0], np.array([[0.2, 0.5, 0.2]], np.float32))
+    with pytest.raises(SphError):                        # structural edit pending: the old grid no longer applies
+        gpu.particles_intersecting_aabb(*boxes[0])
+
+
 @pytest.mark.parametrize("backend", [0, 1], ids=["l1-gather", "tile-tma"])
 def test_two_fluids_with_groups_and_free_running_iterations(backend):
     sc = _small_scene(seed=9, forces=(scenes.xsph_viscosity(0.5, 0.0),), two_fluids=True)

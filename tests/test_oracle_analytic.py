@@ -107,3 +107,39 @@ def test_host_force_callback_adds_to_accelerations():
     p, v = w.read_fluid(f)
     assert len(seen) == 3 and seen[0] == (0.0, 2) and seen[1][0] == pytest.approx(0.01)   # dt lags one step (dfsph_solver.rs:702)
     assert np.abs(p - np.array([[0.0, 1.0, 0.0], [5.0, 1.0, 0.0]])).max() < 1e-6
+
+
+def _aabb_brute_force(h, r, mins, maxs, groups):
+    """liquid_world.rs:211-243 restated densely: groups = [(kind, handle, positions_at_last_grid_build, positions_now)]."""
+    f32 = np.float32
+    lo = np.floor(np.asarray(mins, f32) / f32(h))
+    hi = np.floor(np.asarray(maxs, f32) / f32(h))
+    out = []
+    for kind, handle, p_grid, p_now in groups:
+        cell = np.floor(p_grid.astype(f32) / f32(h))
+        in_cells = np.all((cell >= lo) & (cell <= hi), axis=1)
+        ex = np.maximum(np.maximum(np.asarray(mins, f32) - p_now, p_now - np.asarray(maxs, f32)), f32(0))
+        near = np.sqrt((ex.astype(f32) ** 2).sum(axis=1, dtype=f32)) < f32(r)
+        out += [(kind, handle, int(i)) for i in np.nonzero(in_cells & near)[0]]
+    return sorted(out)
+
+
+def test_particles_intersecting_aabb_matches_brute_force():
+    r = 0.05
+    w = OracleWorld(r, 2.0)
+    pts = scenes.jitter(scenes.block_lattice(8, 7, 6, r), r, 4, amplitude=0.3)
+    floor = scenes.open_tank((-r, -r, -r), (8 * 2 * r + r, 0.4, 6 * 2 * r + r), r)
+    f = w.add_fluid(pts, velocities=np.full_like(pts, 0.8))
+    b = w.add_boundary(floor)
+    mins, maxs = (0.13, -0.2, 0.11), (0.47, 0.33, 0.38)
+    k, hd, ix = w.particles_intersecting_aabb(mins, maxs)
+    assert len(k) == 0                                  # no step yet: the grid is empty (liquid_world.rs:90-117)
+    w.step(0.004)
+    before, _ = w.read_fluid(f)
+    w.step(0.004)                                       # grid holds `before`, positions have moved on
+    now, _ = w.read_fluid(f)
+    k, hd, ix = w.particles_intersecting_aabb(mins, maxs)
+    got = sorted(zip(k.tolist(), hd.tolist(), ix.tolist()))
+    want = _aabb_brute_force(w.h, r, mins, maxs, [(0, f, before, now), (1, b, floor, floor)])
+    assert got == want
+    assert 20 < sum(1 for e in got if e[0] == 0) < len(pts) and any(e[0] == 1 for e in got)

@@ -36,7 +36,9 @@ def _run(world, scene, nsteps, n_div, n_press, dt=0.005):
 
 
 @pytest.mark.parametrize("forces", [(), (scenes.xsph_viscosity(0.5, 0.3),), (scenes.artificial_viscosity(1.0, 0.5),),
-                                    (scenes.akinci2013_surface_tension(1.0, 0.7),)])
+                                    (scenes.akinci2013_surface_tension(1.0, 0.7),),
+                                    (scenes.he2014_surface_tension(40.0, 30.0),), (scenes.wcsph_surface_tension(2.0),)],
+                         ids=["none", "xsph", "artificial", "akinci2013", "he2014", "wcsph"])
 def test_single_fluid_steps_match(forces):
     sc = _scene(5, forces=forces)
     o = OracleWorld(sc["particle_radius"], 2.0)
