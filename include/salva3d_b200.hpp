@@ -73,6 +73,18 @@ struct Akinci2013SurfaceTension : NonPressureForce {  // akinci2013_surface_tens
         return d;
     }
 };
+struct DFSPHViscosity : NonPressureForce {  // dfsph_viscosity.rs:86-124
+    size_t min_viscosity_iter = 1, max_viscosity_iter = 50;
+    Real max_viscosity_error = 0.01f, viscosity_coefficient;
+    explicit DFSPHViscosity(Real viscosity_coefficient_) : viscosity_coefficient(viscosity_coefficient_) {
+        if (!(viscosity_coefficient >= 0.0f && viscosity_coefficient <= 1.0f))
+            throw std::invalid_argument("The viscosity coefficient must be between 0.0 and 1.0.");  // assert! :106-110
+    }
+    sph_force_desc descriptor() const override {
+        sph_force_desc d{SPH_FORCE_DFSPH_VISCOSITY, {viscosity_coefficient, (Real)min_viscosity_iter, (Real)max_viscosity_iter, max_viscosity_error}};
+        return d;
+    }
+};
 struct He2014SurfaceTension : NonPressureForce {  // he2014_surface_tension.rs:12-29
     Real fluid_tension_coefficient, boundary_tension_coefficient;
     He2014SurfaceTension(Real fluid_tension_coefficient_, Real boundary_tension_coefficient_)

@@ -53,10 +53,13 @@ enum { SPH_FORCE_XSPH_VISCOSITY = 0,        /* p[0]=fluid coeff, p[1]=boundary c
        SPH_FORCE_BECKER2009_ELASTICITY = 3, /* p[0]=young, p[1]=poisson, p[2]=nonlinear becker2009_elasticity.rs:60-76 */
        SPH_FORCE_HE2014_TENSION = 4,        /* p[0]=fluid tension coeff, p[1]=boundary tension coeff
                                                he2014_surface_tension.rs:21-29 */
-       SPH_FORCE_WCSPH_TENSION = 5          /* p[0]=fluid tension coeff, p[1]=boundary tension coeff (must be 0: the
+       SPH_FORCE_WCSPH_TENSION = 5,         /* p[0]=fluid tension coeff, p[1]=boundary tension coeff (must be 0: the
                                                reference's boundary loop walks the FLUID contact list and indexes
                                                boundaries with it, wcsph_surface_tension.rs:66-83)
-                                               wcsph_surface_tension.rs:21-27 */ };
+                                               wcsph_surface_tension.rs:21-27 */
+       SPH_FORCE_DFSPH_VISCOSITY = 6        /* p[0]=viscosity coeff in [0,1], p[1]=min_viscosity_iter (1),
+                                               p[2]=max_viscosity_iter (50), p[3]=max_viscosity_error (0.01)
+                                               dfsph_viscosity.rs:86-124 */ };
 
 typedef struct {
     int32_t  solver;                 /* SPH_SOLVER_* */

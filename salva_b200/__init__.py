@@ -4,5 +4,5 @@ Product code only: CUDA kernels + C ABI (csrc/, include/sph.h) and the host mirr
 interface (liquid_world.py).  Nothing here imports the CPU oracle.
 """
 from .liquid_world import (Akinci2013SurfaceTension, ArtificialViscosity, Becker2009Elasticity, Boundary,  # noqa: F401
-                           DFSPHSolver, Fluid, He2014SurfaceTension, IISPHSolver, InteractionGroups, LiquidWorld, SphError,
+                           DFSPHSolver, DFSPHViscosity, Fluid, He2014SurfaceTension, IISPHSolver, InteractionGroups, LiquidWorld, SphError,
                            WCSPHSurfaceTension, XSPHViscosity)

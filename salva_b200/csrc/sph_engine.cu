@@ -23,6 +23,7 @@
 #include "sph_tile.cuh"
 #include "sph_iisph.cuh"
 #include "sph_elasticity.cuh"
+#include "sph_viscosity.cuh"
 
 using namespace sphk;
 
@@ -76,6 +77,8 @@ struct ForceRec {
     sph_host_force_fn host_fn = nullptr;
     void* host_user = nullptr;
     ElasticityState* elastic = nullptr;  // Becker2009 rest-pose state (sph_elasticity.cuh)
+    uint32_t visc_iters = 0;             // DFSPHViscosity: acceleration updates of the last solve
+    float visc_err = 0.f;                // ... and its last strain-rate error
 };
 struct FluidRec {
     size_t n = 0, offset = 0;
@@ -108,6 +111,8 @@ void slab_release(sph_world* w);
 const float* iisph_pred(sph_world* w);
 sph_status elasticity_solve(sph_world* w, uint32_t fluid, ForceRec& fr);
 void elasticity_release(ForceRec& fr);
+sph_status viscosity_solve(sph_world* w, uint32_t fluid, ForceRec& fr);
+void viscosity_release(sph_world* w);
 inline float __uint_as_float_host(uint32_t u) {
     float f;
     memcpy(&f, &u, sizeof f);
@@ -221,6 +226,7 @@ struct sph_world {
     DBuf<float> o_a, o_b, o_c, o_mass;  // staging, original order
     DBuf<uint32_t> o_fid;
     IisphState iisph;
+    ViscosityState visc;
     float* h_pinned = nullptr;  // 64 floats of pinned host memory for small read-backs
 
     // fine-grained kernel timers: (slot, begin, end) event pairs accumulated into stats at step end
@@ -1182,6 +1188,9 @@ sph_status phase_forces(sph_world* w) {
                               w->bforce.p, (uint32_t)f, p[0], p[1]);
                     break;
                 }
+                case SPH_FORCE_DFSPH_VISCOSITY:
+                    TRY(viscosity_solve(w, (uint32_t)f, fr));
+                    break;
                 case SPH_FORCE_WCSPH_TENSION:
                     if (w->tile) return w->fail(SPH_ERR_INVALID, "WCSPHSurfaceTension is not implemented by gather_backend 1");
                     if (p[0] != 0.f) DISPATCH1(k_wcsph_force, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->acc.p, (uint32_t)f, p[0]);
@@ -1472,6 +1481,7 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
 #include "sph_slab.inl"
 #include "sph_iisph_host.inl"
 #include "sph_elasticity_host.inl"
+#include "sph_viscosity_host.inl"
 
 // ===================================================================================================
 // extern "C" boundary
@@ -1555,6 +1565,7 @@ void sph_world_destroy(sph_world* w) {
     w->partial.release(); w->errsum.release(); w->d_scal.release(); w->d_cnt.release();
     w->o_a.release(); w->o_b.release(); w->o_c.release(); w->o_mass.release(); w->o_fid.release();
     iisph_release(w);
+    viscosity_release(w);
     slab_release(w);
     for (auto& f : w->fluids)
         for (auto& fr : f.forces) elasticity_release(fr);
@@ -1614,11 +1625,13 @@ sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid, const sph_force_de
     if (!w || !force) return SPH_ERR_INVALID;
     std::lock_guard<std::mutex> lock(g_mutex);
     if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
-    if (force->kind < 0 || force->kind > SPH_FORCE_WCSPH_TENSION) return w->fail(SPH_ERR_INVALID, "unknown force kind %d", force->kind);
+    if (force->kind < 0 || force->kind > SPH_FORCE_DFSPH_VISCOSITY) return w->fail(SPH_ERR_INVALID, "unknown force kind %d", force->kind);
     if (force->kind == SPH_FORCE_WCSPH_TENSION && force->p[1] != 0.f)
         return w->fail(SPH_ERR_INVALID,
                        "WCSPHSurfaceTension: boundary coefficient must be 0 (the reference's boundary loop indexes boundaries with fluid "
                        "contacts, wcsph_surface_tension.rs:66-83)");
+    if (force->kind == SPH_FORCE_DFSPH_VISCOSITY && !(force->p[0] >= 0.f && force->p[0] <= 1.f))
+        return w->fail(SPH_ERR_INVALID, "The viscosity coefficient must be between 0.0 and 1.0. (dfsph_viscosity.rs:106-110)");
     ForceRec fr;
     fr.d = *force;
     w->fluids[fluid].forces.push_back(fr);

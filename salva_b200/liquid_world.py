@@ -84,6 +84,23 @@ class Becker2009Elasticity:
         self.params = [young_modulus, poisson_ratio, 1.0 if nonlinear_strain else 0.0]
 
 
+class DFSPHViscosity:
+    """dfsph_viscosity.rs:86-124 (public tunables min/max_viscosity_iter, max_viscosity_error)"""
+    kind = 6
+
+    def __init__(self, viscosity_coefficient, min_viscosity_iter=1, max_viscosity_iter=50, max_viscosity_error=0.01):
+        if not 0.0 <= viscosity_coefficient <= 1.0:
+            raise ValueError("The viscosity coefficient must be between 0.0 and 1.0.")
+        self.viscosity_coefficient = viscosity_coefficient
+        self.min_viscosity_iter = min_viscosity_iter
+        self.max_viscosity_iter = max_viscosity_iter
+        self.max_viscosity_error = max_viscosity_error
+
+    @property
+    def params(self):
+        return [self.viscosity_coefficient, float(self.min_viscosity_iter), float(self.max_viscosity_iter), self.max_viscosity_error]
+
+
 class He2014SurfaceTension:
     """he2014_surface_tension.rs:21-29"""
     kind = 4
