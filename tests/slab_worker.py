@@ -25,7 +25,8 @@ def make_scene(kind):
     vel[:, 0] += np.where(pts[:, 0] < pts[:, 0].mean(), 1.5, -1.5).astype(np.float32)  # push particles across the planes
     tank = scenes.open_tank((-r, -r, -r), (nx * 2 * r + r, 1.2, nz * 2 * r + r), r)
     forces = {"xsph": [scenes.xsph_viscosity(0.5, 0.2)], "akinci": [scenes.akinci2013_surface_tension(1.0, 0.3)],
-              "artificial": [scenes.artificial_viscosity(1.0, 0.0)]}[kind]
+              "artificial": [scenes.artificial_viscosity(1.0, 0.0)], "he2014": [scenes.he2014_surface_tension(40.0, 30.0)],
+              "wcsph": [scenes.wcsph_surface_tension(2.0)]}[kind]
     return dict(particle_radius=r, smoothing_factor=2.0, dt=0.004,
                 fluids=[dict(positions=pts, velocities=vel, density0=1000.0, forces=forces)], boundaries=[dict(positions=tank)])
 

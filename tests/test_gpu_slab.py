@@ -28,7 +28,7 @@ def _run(nproc, kind, steps, tmp_path, mode="forced"):
     return json.load(open(out))
 
 
-@pytest.mark.parametrize("kind", ["xsph", "akinci", "artificial"])
+@pytest.mark.parametrize("kind", ["xsph", "akinci", "artificial", "he2014", "wcsph"])
 def test_two_slabs_match_one_gpu(kind, tmp_path):
     res = _run(2, kind, 12, tmp_path)
     assert res["n_total"] == res["n_expected"] and res["ids_unique"]
