@@ -364,7 +364,30 @@ __global__ void k_scanK_add(ScanSet<K> io, uint32_t n, ScanSet<K> block_offsets)
 // ------------------------------------------------------------------------------------------------
 // K2: neighbour search (contacts.rs:154-400).  One thread per particle walks the 9 z-runs of its
 // 27-cell stencil and keeps the indices that pass the reference's exact `d^2 <= h*h` test.
+// Only ~15 % of the candidates pass, but in a warp SOME lane passes for nearly every candidate, so a store inside the
+// candidate loop is executed (predicated off) by the whole warp almost every iteration.  The candidate loop therefore
+// only records hits in a 32-bit mask per chunk of 32 candidates; the (short) emit loop then walks the set bits in
+// ascending order, which keeps every list in the same order as a plain scan.
 // ------------------------------------------------------------------------------------------------
+template <class Accept, class Emit>
+__device__ __forceinline__ void scan_run(const float4& pi, const float4* __restrict__ P, uint32_t s, uint32_t e, Accept accept, Emit emit) {
+    for (uint32_t base = s; base < e; base += 32u) {
+        const uint32_t n = min(32u, e - base);
+        uint32_t m = 0u;
+#pragma unroll 4
+        for (uint32_t t = 0; t < n; ++t) {
+            const float4 pj = __ldg(&P[base + t]);
+            const float d2 = dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+            m |= (d2 <= C.h2 ? 1u : 0u) << t;
+        }
+        while (m) {
+            const uint32_t j = base + (uint32_t)__ffs((int)m) - 1u;
+            m &= m - 1u;
+            if (accept(j)) emit(j);
+        }
+    }
+}
+
 template <bool MULTI>
 __global__ void __launch_bounds__(128)
 k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, const uint32_t* __restrict__ cstart,
@@ -382,37 +405,28 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
         for (int ax = -1; ax <= 1; ++ax)
             for (int ay = -1; ay <= 1; ++ay) {
                 int base = cell_id(cx + ax, cy + ay, cz);
-                uint32_t s = cstart[base - 1], e = cstart[base + 2];
-                for (uint32_t j = s; j < e; ++j) {
-                    float4 pj = __ldg(&pos[j]);
-                    float d2 = dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-                    bool ok = d2 <= C.h2;
-                    if (MULTI && ok) {  // contacts.rs:355-362: different fluids need the groups test
-                        uint32_t fj = fid_of(__ldg(&vel[j]));
-                        ok = fi == fj || groups_test(C.fluids[fi].memberships, C.fluids[fi].filter, C.fluids[fj].memberships,
-                                                     C.fluids[fj].filter);
-                    }
-                    if (ok) {
+                scan_run(
+                    pi, pos, cstart[base - 1], cstart[base + 2],
+                    [&](uint32_t j) {
+                        if (!MULTI) return true;
+                        uint32_t fj = fid_of(__ldg(&vel[j]));  // contacts.rs:355-362: different fluids need the groups test
+                        return fi == fj || groups_test(C.fluids[fi].memberships, C.fluids[fi].filter, C.fluids[fj].memberships, C.fluids[fj].filter);
+                    },
+                    [&](uint32_t j) {
                         if (nf < C.cap_f) nbr_f[((size_t)(nf >> 2) * C.stride + i) * 4 + (nf & 3)] = j;
                         ++nf;
-                    }
-                }
-                if (C.n_bound) {
-                    uint32_t sb = bstart[base - 1], eb = bstart[base + 2];
-                    for (uint32_t j = sb; j < eb; ++j) {
-                        float4 pj = __ldg(&bpos[j]);
-                        float d2 = dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-                        bool ok = d2 <= C.h2;
-                        if (ok) {  // contacts.rs:347-352
+                    });
+                if (C.n_bound)
+                    scan_run(
+                        pi, bpos, bstart[base - 1], bstart[base + 2],
+                        [&](uint32_t j) {  // contacts.rs:347-352
                             uint32_t bj = fid_of(__ldg(&bvel[j]));
-                            ok = groups_test(C.fluids[fi].memberships, C.fluids[fi].filter, C.bounds[bj].memberships, C.bounds[bj].filter);
-                        }
-                        if (ok) {
+                            return groups_test(C.fluids[fi].memberships, C.fluids[fi].filter, C.bounds[bj].memberships, C.bounds[bj].filter);
+                        },
+                        [&](uint32_t j) {
                             if (nb < C.cap_b) nbr_b[(size_t)nb * C.stride + i] = j;
                             ++nb;
-                        }
-                    }
-                }
+                        });
             }
         for (uint32_t t = nf; t < ((nf + 3u) & ~3u) && t < C.cap_f; ++t) nbr_f[((size_t)(t >> 2) * C.stride + i) * 4 + (t & 3)] = i;  // pad the last group
         cnt_f[i] = nf;
