@@ -1320,6 +1320,10 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
         w->stats.n_divergence_eval++;
         if (w->force_div >= 0) {
             if ((int)i >= w->force_div) break;
+        } else if (i < w->desc.min_divergence_iter && i + 1 < maxit) {
+            // the break needs `i >= min_iter` (:486): this evaluation's error cannot end the loop and the next
+            // evaluation reports a fresher one, so neither the read-back (a host sync) nor the allreduce is needed
+            w->errsum_ready = false;
         } else {
             float avg;
             TRY(read_error(w, nblk, &avg));
@@ -1360,6 +1364,8 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
         w->stats.n_pressure_eval++;
         if (w->force_press >= 0) {
             if ((int)i >= w->force_press) break;
+        } else if (i < w->desc.min_pressure_iter && i + 1 < maxit) {
+            w->errsum_ready = false;  // cannot break yet (:450): skip the read-back, as in the divergence loop
         } else {
             float avg;
             TRY(read_error(w, nblk, &avg));

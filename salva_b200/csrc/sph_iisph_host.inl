@@ -78,7 +78,9 @@ sph_status iisph_step(sph_world* w, float dt_total, const float g[3]) {
         std::swap(pr_cur, pr_next);
         w->stats.n_pressure_iter++;
         w->stats.n_pressure_eval++;
-        if (w->force_press < 0) {
+        if (w->force_press < 0 && i < w->desc.min_pressure_iter && i + 1 < maxit) {
+            w->errsum_ready = false;  // `i >= min_pressure_iter` is required to break (iisph_solver.rs:446-454): no read-back needed
+        } else if (w->force_press < 0) {
             float avg;
             TRY(read_error(w, cdiv(N, PASS_T), &avg));
             w->stats.last_density_error = avg;

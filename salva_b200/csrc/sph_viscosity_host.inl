@@ -49,10 +49,12 @@ sph_status viscosity_solve(sph_world* w, uint32_t f, ForceRec& fr) {
         if (multi) LAUNCH((k_visc_rates<true, true>), N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->dens.p, V.vv, V.target, V.beta, V.u4, V.u2, w->partial.p, f, visc);
         else LAUNCH((k_visc_rates<false, true>), N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->dens.p, V.vv, V.target, V.beta, V.u4, V.u2, w->partial.p, f, visc);
         w->errsum_ready = false;
-        float avg = 0.f;
-        TRY(read_error(w, cdiv(N, PASS_T), &avg));
-        fr.visc_err = avg;
-        if (avg <= max_err && i >= min_iter) break;
+        if (!(i < min_iter && i + 1 < max_iter)) {  // an evaluation that cannot break the loop needs no read-back
+            float avg = 0.f;
+            TRY(read_error(w, cdiv(N, PASS_T), &avg));
+            fr.visc_err = avg;
+            if (avg <= max_err && i >= min_iter) break;
+        }
         DISPATCH1(k_visc_accel, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, L, V.u4, V.u2, w->acc.p, f, w->inv_dt);
         fr.visc_iters++;
     }
