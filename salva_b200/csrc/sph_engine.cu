@@ -149,6 +149,7 @@ struct sph_world {
     float h = 0.f;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
+    cudaEvent_t ev_lists = nullptr;  // list-capacity read-back of phase_neighbors
     std::string err;
     Consts hc;
 
@@ -764,7 +765,10 @@ cudaError_t tile_prepare(K kern) {
         }                                                                                                 \
     } while (0)
 
-sph_status phase_neighbors(sph_world* w) {
+// `speculative` (optional) enqueues the work that follows the neighbour search and only writes scratch (the density
+// pass): it is launched BEFORE the host learns whether the lists overflowed, so the GPU is busy during that round trip;
+// on overflow the lists are rebuilt with a larger capacity and the speculative work is simply enqueued again.
+sph_status phase_neighbors(sph_world* w, sph_status (*speculative)(sph_world*) = nullptr) {
     size_t N = w->N, B = w->B;
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1;
@@ -795,9 +799,15 @@ sph_status phase_neighbors(sph_world* w) {
             LAUNCH((k_neighbors<false>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
                    w->cnt_f.p, w->cnt_b.p, maxcnt);
         }
-        int hs[4];
-        CU(cudaMemcpyAsync(hs, w->d_scal.p + 7, sizeof hs, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaStreamSynchronize(w->st));
+        int* hs = reinterpret_cast<int*>(w->h_pinned + 32);  // pinned: the copy is truly asynchronous
+        CU(cudaMemcpyAsync(hs, w->d_scal.p + 7, 4 * sizeof(int), cudaMemcpyDeviceToHost, w->st));
+        CU(cudaEventRecord(w->ev_lists, w->st));
+        CU(cudaEventRecord(w->ev[EV_NBR], w->st));
+        // (not in slab worlds: the density pass ends with a ghost exchange, and a rank that has to repeat it alone would
+        //  leave its neighbours waiting in a collective they never enter)
+        const bool early = speculative && !w->slab.active && !w->tile;  // (tile launches need this read-back's slot count)
+        if (early) TRY(speculative(w));
+        CU(cudaEventSynchronize(w->ev_lists));
         if (hs[0]) return w->fail(SPH_ERR_ZERO_DENSITY, "zero boundary-volume denominator (reference assert dfsph_solver.rs:92)");
         if (w->tile) {
             if ((uint32_t)hs[3] > 65535u)
@@ -814,7 +824,11 @@ sph_status phase_neighbors(sph_world* w) {
             w->cap_b = ((uint32_t)hs[2] + 15) / 16 * 16;
             grow = true;
         }
-        if (!grow) break;
+        if (!grow) {
+            if (speculative && !early) TRY(speculative(w));
+            break;
+        }
+        if (early) CU(cudaMemsetAsync(w->d_scal.p + 7, 0, sizeof(int), w->st));  // error flag of the discarded speculative pass
         if (w->tile) CU(w->nbr16.ensure((size_t)w->cap_f * w->stride));
         else {
             CU(w->nbr_f.ensure((size_t)w->cap_f * w->stride));
@@ -823,6 +837,10 @@ sph_status phase_neighbors(sph_world* w) {
         CU(w->nbr_b.ensure((size_t)w->cap_b * w->stride));
         fill_static_consts(w);
         TRY(upload_consts(w));
+    }
+    if (!N) {  // boundaries only
+        CU(cudaEventRecord(w->ev[EV_NBR], w->st));
+        if (speculative) TRY(speculative(w));
     }
     if (N) {
         k_sum_u32<<<std::min<uint32_t>(cdiv(N, 256), 1184), 256, 0, w->st>>>((uint32_t)N, w->cnt_f.p + w->own_begin, w->cnt_b.p + w->own_begin,
@@ -1414,21 +1432,20 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
     w->grid_ready = true;
     w->ever_stepped = true;
     CU(cudaEventRecord(w->ev[EV_GRID], w->st));
-    TRY(phase_neighbors(w));
-    CU(cudaEventRecord(w->ev[EV_NBR], w->st));
-    int c = w->cur, bc = w->bcur;
-    const bool multi = w->fluids.size() > 1;
-    (void)c; (void)bc; (void)multi;
-    // evaluate_kernels + compute_densities (liquid_world.rs:123-134) + compute_alphas (dfsph_solver.rs:679-684)
-    w->fused_first_div = false;
-    if (N) {
-        if (w->desc.solver == SPH_SOLVER_DFSPH && !w->tile && w->fuse_div) {
-            TRY(launch_density_alpha_div(w, &w->fused_nblk));
-            w->fused_first_div = true;
-        } else {
-            TRY(launch_density_alpha(w));
+    // evaluate_kernels + compute_densities (liquid_world.rs:123-134) + compute_alphas (dfsph_solver.rs:679-684), enqueued
+    // speculatively by the neighbour phase (EV_NBR is recorded there, between the two)
+    TRY(phase_neighbors(w, [](sph_world* w) -> sph_status {
+        w->fused_first_div = false;
+        if (w->N) {
+            if (w->desc.solver == SPH_SOLVER_DFSPH && !w->tile && w->fuse_div) {
+                TRY(launch_density_alpha_div(w, &w->fused_nblk));
+                w->fused_first_div = true;
+            } else {
+                TRY(launch_density_alpha(w));
+            }
         }
-    }
+        return SPH_OK;
+    }));
     CU(cudaEventRecord(w->ev[EV_DENS], w->st));
     if (N) {
         if (w->desc.solver == SPH_SOLVER_DFSPH) TRY(dfsph_step(w, dt, g));
@@ -1539,6 +1556,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     memset(&w->stats, 0, sizeof w->stats);
     bool ok = cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < EV_COUNT; ++i) ok = cudaEventCreate(&w->ev[i]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&w->ev_lists, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&w->h_pinned, 64 * sizeof(float)) == cudaSuccess;
     ok = ok && cudaMallocHost(&w->h_ctl, sizeof(LoopCtl)) == cudaSuccess && w->d_ctl.ensure(1) == cudaSuccess;
     ok = ok && w->d_scal.ensure(16) == cudaSuccess && w->d_cnt.ensure(2) == cudaSuccess;
@@ -1591,6 +1609,7 @@ void sph_world_destroy(sph_world* w) {
     w->he_colors.release(); w->he_gradc.release(); w->q_out.release(); w->q_count.release();
     for (auto& e : w->ev)
         if (e) cudaEventDestroy(e);
+    if (w->ev_lists) cudaEventDestroy(w->ev_lists);
     if (w->st) cudaStreamDestroy(w->st);
     if (g_const_owner == w) g_const_owner = nullptr;
     delete w;

@@ -63,6 +63,28 @@ def test_single_pass_quantities_match_oracle():
     assert sg["n_contacts"] == so["n_contacts"]
 
 
+def test_list_capacity_regrows_behind_speculative_density_pass():
+    """A crowded cell overflows the initial contact-list capacity: the neighbour phase must rebuild the lists (the density
+    pass it had already enqueued speculatively is discarded and repeated) and still match the oracle."""
+    r = 0.05
+    h = 4 * r
+    rng = np.random.default_rng(11)
+    blob = (rng.random((400, 3)) * 0.9 * h + 0.05 * h).astype(np.float32)          # 400 particles in ONE cell
+    rest = scenes.jitter(scenes.block_lattice(6, 6, 6, r, origin=(2.0, 0.0, 0.0)), r, 5, amplitude=0.2)
+    pts = np.concatenate([blob, rest]).astype(np.float32)
+    sc = dict(particle_radius=r, fluids=[dict(positions=pts, velocities=np.zeros_like(pts), density0=1000.0, forces=[])],
+              boundaries=[])
+    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    for w in (gpu, cpu):
+        w.force_iterations(1, 1)
+        w.step(1e-5)
+    assert gpu.stats()["max_neighbors"] >= 400
+    assert np.array_equal(gpu.debug(fg[0], "num_fluid_contacts"), cpu.debug(fc[0], "num_fluid_contacts"))
+    assert _rel(gpu.debug(fg[0], "density"), cpu.debug(fc[0], "density")) <= 2e-5
+    assert _rel(gpu.debug(fg[0], "alpha"), cpu.debug(fc[0], "alpha")) <= 1e-4
+    assert _rel(gpu.debug(fg[0], "divergence"), cpu.debug(fc[0], "divergence")) <= 1e-3 or np.abs(cpu.debug(fc[0], "divergence")).max() == 0
+
+
 @pytest.mark.parametrize("forces", [(), (scenes.xsph_viscosity(0.5, 0.3),), (scenes.artificial_viscosity(1.0, 0.5),),
                                     (scenes.akinci2013_surface_tension(1.0, 0.7),)],
                          ids=["none", "xsph", "artificial", "akinci2013"])
