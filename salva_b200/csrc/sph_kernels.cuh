@@ -373,16 +373,21 @@ template <class Accept, class Emit>
 __device__ __forceinline__ void scan_run(const float4& pi, const float4* __restrict__ P, uint32_t s, uint32_t e, Accept accept, Emit emit) {
     for (uint32_t base = s; base < e; base += 32u) {
         const uint32_t n = min(32u, e - base);
-        uint32_t m = 0u;
+        const float4* __restrict__ q = P + base;
+        uint32_t rej = 0u;  // candidate t of the chunk ends up in bit n - 1 - t; set = rejected
 #pragma unroll 4
         for (uint32_t t = 0; t < n; ++t) {
-            const float4 pj = __ldg(&P[base + t]);
+            const float4 pj = __ldg(&q[t]);
             const float d2 = dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-            m |= (d2 <= C.h2 ? 1u : 0u) << t;
+            // d2 <= h*h  <=>  the sign bit of (h*h - d2) is clear (a float difference is zero only for equal operands;
+            // NaN positions never get here, k_bounds rejects them): shift that bit into the mask with one funnel shift
+            rej = __funnelshift_l(__float_as_uint(__fsub_rn(C.h2, d2)), rej, 1);
         }
+        uint32_t m = ~rej & (n == 32u ? 0xffffffffu : (1u << n) - 1u);
         while (m) {
-            const uint32_t j = base + (uint32_t)__ffs((int)m) - 1u;
-            m &= m - 1u;
+            const uint32_t b = 31u - (uint32_t)__clz((int)m);  // highest set bit = earliest candidate
+            m &= ~(1u << b);
+            const uint32_t j = base + (n - 1u - b);
             if (accept(j)) emit(j);
         }
     }
