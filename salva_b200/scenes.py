@@ -192,6 +192,18 @@ def scene_c1():
                 boundaries=bounds)
 
 
+def scene_tension_small():
+    """Not a reference config: a small jittered, slightly compressed block in an open tank with the two surface-tension
+    rows added in §8(f).3 (He2014 incl. its boundary reaction, WCSPH fluid term) — used for a committed golden fixture."""
+    r = 0.05
+    nx, ny, nz = 10, 8, 7
+    pts = jitter(block_lattice(nx, ny, nz, r * 0.95), r, 71, amplitude=0.3)
+    tank = open_tank((-r, -r, -r), (nx * 2 * r + r, 1.0, nz * 2 * r + r), r)
+    return dict(name="tension-small", particle_radius=r, smoothing_factor=2.0, dt=0.004, gravity=GRAVITY, solver=DFSPH,
+                fluids=[dict(positions=pts, density0=1000.0, forces=[he2014_surface_tension(40.0, 30.0), wcsph_surface_tension(2.0)])],
+                boundaries=[dict(positions=tank, want_forces=True)])
+
+
 def scene_c2(n=100):
     """1M-particle cube dam-break, DFSPH + XSPHViscosity(0.5, 0), r=0.025, dt=1/1000."""
     return _dam_break(n, n, n, 0.025, 1.0 / 1000.0, [xsph_viscosity(0.5, 0.0)], name="C2-dam-%d" % (n ** 3))

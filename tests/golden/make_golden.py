@@ -38,6 +38,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "c1_basic3_dfsph_5steps.npz"), **run(c1, 0, 5, 1, 2))
     c5 = scenes.scene_c5(6)
     np.savez_compressed(os.path.join(HERE, "c5_small_iisph_4steps.npz"), **run(c5, 1, 4, -1, 3))
+    ts = scenes.scene_tension_small()
+    np.savez_compressed(os.path.join(HERE, "tension_small_dfsph_5steps.npz"), **run(ts, 0, 5, 2, 3))
     print("written")
 
 
