@@ -941,7 +941,6 @@ static float visc_compute_strain_rates(World& w, size_t f, Force& fc, bool compu
     Fluid& fl = w.fluids[f];
     const std::vector<float>& dens = w.densities[f];
     const float visc = fc.p[0];
-    double total = 0.0;
     std::vector<float> per(fl.n(), 0.f);
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < (long)fl.n(); ++i) {
@@ -968,7 +967,6 @@ static float visc_compute_strain_rates(World& w, size_t f, Force& fc, bool compu
     }
     float err = 0.f;  // par_reduce_sum: f32 sum (order unspecified in the reference)
     for (size_t i = 0; i < fl.n(); ++i) err += per[i];
-    (void)total;
     return fl.n() ? std::max(0.f, err / (float)fl.n()) : 0.f;
 }
 // compute_accelerations :254-289
