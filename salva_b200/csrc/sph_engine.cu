@@ -216,6 +216,9 @@ struct sph_world {
     bool device_loops = false;  // measured slower at C2 (gated no-op launches cost more than the syncs they save)
     int use_gcache = 0;
     bool fuse_div = true, fused_first_div = false;  // first compute_divergences evaluation rides with the density pass
+    bool fuse_xsph = true;    // XSPH sums ride with the stand-alone divergence evaluations (k_vel_divergence_xsph_u)
+    bool xs_valid = false;    // ... and the last evaluation of this step produced them
+    DBuf<float4> xs;
     uint32_t fused_nblk = 0;
     bool use_tex = false;
     cudaTextureObject_t tex_vs = 0, tex_kappa = 0;
@@ -1057,9 +1060,20 @@ sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
 // compute_divergences (predict = false) / compute_predicted_densities (predict = true); returns #partials.
 // In a slab world with overlap the kappa ghosts are exchanged speculatively (the evaluation may turn out to be the
 // loop's last one) behind the interior launch; otherwise refresh_kappa() does it only when an update follows.
+// The fluid term of the FIRST force of a single-fluid DFSPH world can ride with the divergence evaluations when it is an
+// XSPHViscosity without a boundary term (see k_vel_divergence_xsph_u).
+bool xsph_fusable(const sph_world* w) {
+    if (!w->fuse_xsph || w->desc.solver != SPH_SOLVER_DFSPH || w->tile || !w->unimass || w->use_gcache || w->slab.active) return false;
+    if (w->fluids.size() != 1 || w->fluids[0].forces.empty()) return false;
+    const sph_force_desc& d = w->fluids[0].forces[0].d;
+    return d.kind == SPH_FORCE_XSPH_VISCOSITY && d.p[0] != 0.f && (d.p[1] == 0.f || w->B == 0);
+}
+
 sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, const int* gate = nullptr) {
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1;
+    const bool xsf = !predict && !gate && xsph_fusable(w);
+    if (xsf) CU(w->xs.ensure(std::max(w->Ntot, w->N)));
     if (w->tile) {
         TileLists L{w->nbr16.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
         uint32_t cap = tile_cap(w, 32);
@@ -1090,6 +1104,13 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
                                    w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
                 else LAUNCH_R((k_vel_divergence_u<true, false>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
                               w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
+            } else if (xsf) {
+                const float cf = w->fluids[0].forces[0].d.p[0];
+                if (ptex) LAUNCH_R((k_vel_divergence_xsph_u<true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, L, w->dens.p,
+                                   w->alpha.p, out, w->pk4.p, partial, tk, w->errsum.p, w->xs.p, cf);
+                else LAUNCH_R((k_vel_divergence_xsph_u<false>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, L, w->dens.p,
+                              w->alpha.p, out, w->pk4.p, partial, tk, w->errsum.p, w->xs.p, cf);
+                w->xs_valid = true;
             } else {
                 if (ptex) LAUNCH_R((k_vel_divergence_u<false, true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
                                    w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
@@ -1151,6 +1172,7 @@ sph_status phase_forces(sph_world* w) {
             const float* p = fr.d.p;
             switch (fr.d.kind) {
                 case SPH_FORCE_XSPH_VISCOSITY:
+                    if (w->xs_valid && f == 0 && &fr == &w->fluids[0].forces[0]) break;  // already folded in by k_fold_velocities
                     if (w->tile) {
                         uint32_t cap = tile_cap(w, 36);
                         TDISPATCH2(k_tile_xsph, multi, bf, 36, cap, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, w->bvel[bc].p, w->cstart.p, cap, TL,
@@ -1320,6 +1342,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     (void)bc; (void)multi; (void)bf;
     // divergence_solve :466-503 (uses the PREVIOUS step's inv_dt; 0 on the first step)
     w->stats.n_divergence_iter = w->stats.n_divergence_eval = 0;
+    w->xs_valid = false;
     uint32_t maxit = w->force_div >= 0 ? (uint32_t)w->force_div + 1 : w->desc.max_divergence_iter;
     const bool dev_loops = w->device_loops && !w->tile;
     if (dev_loops && w->force_div < 0) {
@@ -1353,12 +1376,14 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
         TRY(span_begin(w, SP_DIV_UPD));
         TRY(launch_vel_update(w, false));
         TRY(span_end(w));
+        w->xs_valid = false;  // v* moved on: XSPH sums of the evaluation above are stale unless another evaluation follows
         w->stats.n_divergence_iter++;
     }
     CU(cudaEventRecord(w->ev[EV_DIV], w->st));
     // update_velocities :422-430, zero vc :689-691, acc += gravity :574-578
     TRY(slab_wait(w));
-    LAUNCH(k_fold_velocities, w->Ntot, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2]);  // ghosts too (vel = v*)
+    LAUNCH(k_fold_velocities, w->Ntot, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2],  // ghosts too (vel = v*)
+           w->xs_valid ? (const float4*)w->xs.p : (const float4*)nullptr, w->inv_dt);
     CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
     TRY(phase_forces(w));
     CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
@@ -1546,6 +1571,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     if (const char* t = getenv("SALVA_B200_DEVICE_LOOPS")) w->device_loops = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_GCACHE")) w->use_gcache = atoi(t);
     if (const char* t = getenv("SALVA_B200_FUSE_DIV")) w->fuse_div = atoi(t) != 0;
+    if (const char* t = getenv("SALVA_B200_FUSE_XSPH")) w->fuse_xsph = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_UNI_EVAL")) w->uni_eval_mode = atoi(t);
     if (const char* t = getenv("SALVA_B200_UNI_UPD")) w->uni_upd_mode = atoi(t);
     {
@@ -1606,7 +1632,7 @@ void sph_world_destroy(sph_world* w) {
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     w->d_ctl.release();
     w->d_ticket.release();
-    w->he_colors.release(); w->he_gradc.release(); w->q_out.release(); w->q_count.release();
+    w->xs.release(); w->he_colors.release(); w->he_gradc.release(); w->q_out.release(); w->q_count.release();
     for (auto& e : w->ev)
         if (e) cudaEventDestroy(e);
     if (w->ev_lists) cudaEventDestroy(w->ev_lists);

@@ -568,14 +568,23 @@ __global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __res
 // a10: update_velocities dfsph_solver.rs:422-430 + zero vc :689-691 + acc = gravity (predict_advection :574-578).
 // vel += vc is written as vel = v*: v* was materialised as vel + vc by the producer, so the result is bitwise the
 // same for owned particles, and ghost particles (multi-GPU) only carry an up-to-date v*.
+// xs (optional): XSPH sums of the divergence loop's last evaluation (k_vel_divergence_xsph_u): acc = g + xs * inv_dt,
+// rounded like k_force_xsph's `acc += f * inv_dt` on top of the gravity written here.
 __global__ void k_fold_velocities(float4* __restrict__ vel, float4* __restrict__ vc, const float4* __restrict__ vs, float4* __restrict__ acc, float gx, float gy,
-                                  float gz) {
+                                  float gz, const float4* __restrict__ xs, float inv_dt) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C.n_fluid) return;
     float4 v = vel[i], s = vs[i];
     vel[i] = make_float4(s.x, s.y, s.z, v.w);
     vc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc[i] = make_float4(gx, gy, gz, 0.f);
+    float ax = gx, ay = gy, az = gz;
+    if (xs) {
+        float4 f = xs[i];
+        ax = __fadd_rn(gx, __fmul_rn(f.x, inv_dt));
+        ay = __fadd_rn(gy, __fmul_rn(f.y, inv_dt));
+        az = __fadd_rn(gz, __fmul_rn(f.z, inv_dt));
+    }
+    acc[i] = make_float4(ax, ay, az, 0.f);
 }
 // IISPH variant: accelerations += gravity only (vc is already zero, velocities untouched).
 __global__ void k_set_gravity(const float4* __restrict__ vel, float4* __restrict__ vs, float4* __restrict__ acc, float gx, float gy, float gz) {

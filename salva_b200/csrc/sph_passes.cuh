@@ -87,7 +87,7 @@ __device__ __forceinline__ void for_fluid_contacts_g(uint32_t i, const float4& p
 // k_density_alpha (fewer instructions, +4 B/contact of traffic; measured neutral at 1M, slower at 10M where the list
 // traffic already puts DRAM at ~50 %) or recomputed from the positions (default).
 // No tail masking: padded slots are (j = i, g = 0) and a self contact has zero gradient either way.
-template <bool NEED_D2, class LP, class LD, class FF>
+template <bool NEED_D2, bool NEED_W = false, class LP, class LD, class FF>
 __device__ __forceinline__ void for_fluid_grads(uint32_t i, const float4& pi, const Lists& L, LP ldpos, LD ld, FF ff) {
     const uint32_t n = min(L.cnt_f[i], C.cap_f);
     const uint32_t nq = (n + 3u) >> 2;
@@ -123,7 +123,7 @@ __device__ __forceinline__ void for_fluid_grads(uint32_t i, const float4& pi, co
                 p.g = g[u];
                 if (NEED_D2) p.d2 = fmaf(p.dz, p.dz, fmaf(p.dy, p.dy, p.dx * p.dx));
             } else {
-                p = make_pair<false, true>(pi, pj[u]);
+                p = make_pair<NEED_W, true>(pi, pj[u]);
             }
             ff(j[u], p, pj[u], aux[u]);
         }
@@ -523,6 +523,61 @@ k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, con
             e = d / rho0;
         }
         pk4[i] = make_float4(a.x, a.y, a.z, kap);
+    }
+    reduce_error<false>(e, 0u, valid, partial, sm, ticket, errsum);
+}
+
+// compute_divergences (a7) + the fluid term of XSPHViscosity::solve (a12, xsph_viscosity.rs:52-69) in ONE sweep.
+// XSPH is evaluated on `fluid.velocities` right after update_velocities folded vc into them (dfsph_solver.rs:688-697),
+// i.e. on exactly the v* the divergence loop's LAST evaluation gathers; so every stand-alone evaluation also accumulates
+// the XSPH sums (one extra 4-byte gather of rho_j and the kernel value per contact) and the last one's are used:
+// k_fold_velocities adds xs * inv_dt to the gravity it writes and the separate XSPH pass is skipped.  Same per-contact
+// arithmetic and summation order as k_force_xsph; padded self slots contribute c * (v_i - v_i) = 0.
+struct VyzRho {
+    float2 v;
+    float rho;
+};
+template <bool POS_TEX>
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)  // 64 registers: the extra sums spill at 56
+k_vel_divergence_xsph_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, const float2* __restrict__ vyz, cudaTextureObject_t tvyz,
+                        const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens, const float* __restrict__ alpha,
+                        float* __restrict__ out, float4* __restrict__ pk4, float* __restrict__ partial, uint32_t* __restrict__ ticket,
+                        float* __restrict__ errsum, float4* __restrict__ xs, float cf, Range rg) {
+    __shared__ float sm[32];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < rg.count;
+    i += rg.begin;
+    float e = 0.f;
+    if (valid) {
+        const float4 a = pvx[i];
+        const float2 b = vyz[i];
+        const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
+        const float vix = a.w, viy = b.x, viz = b.y;
+        const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
+        const bool gated = L.cnt_f[i] + L.cnt_b[i] < 20u;  // dfsph_solver.rs:301-314
+        float d = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
+        for_fluid_grads<false, true>(
+            i, pi, L, [&](uint32_t j) { return POS_TEX ? tex1Dfetch<float4>(tpvx, (int)j) : __ldg(&pvx[j]); },
+            [&](uint32_t j) { return VyzRho{POS_TEX ? __ldg(&vyz[j]) : tex1Dfetch<float2>(tvyz, (int)j), __ldg(&dens[j])}; },
+            [&](uint32_t, const Pair& p, const float4& pj, const VyzRho& wj) {
+                float dv = (vix - pj.w) * p.dx + (viy - wj.v.x) * p.dy + (viz - wj.v.y) * p.dz;
+                d = fmaf(dv * p.g, mass, d);
+                float c = cf * p.w * mass / wj.rho;  // coeff * W * (vol_j * rho0) / rho_j
+                fx = fmaf(c, pj.w - vix, fx); fy = fmaf(c, wj.v.x - viy, fy); fz = fmaf(c, wj.v.y - viz, fz);
+            });
+        if (gated) {
+            d = 0.f;
+        } else {
+            for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t, const Pair& p, const float4& pj) {
+                float dv = vix * p.dx + viy * p.dy + viz * p.dz;
+                d = fmaf(dv * p.g, pj.w * rho0, d);
+            });
+        }
+        d = fmaxf(d, 0.f);
+        out[i] = d;
+        e = d / rho0;
+        pk4[i] = make_float4(a.x, a.y, a.z, d * alpha[i]);
+        xs[i] = make_float4(fx, fy, fz, 0.f);
     }
     reduce_error<false>(e, 0u, valid, partial, sm, ticket, errsum);
 }

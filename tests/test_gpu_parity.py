@@ -166,6 +166,56 @@ def test_dfsph_viscosity_coefficient_range_is_checked():
         gpu.push_force(f, *scenes.dfsph_viscosity(1.5))
 
 
+def test_xsph_fusion_falls_back_when_the_loop_ends_with_an_update(monkeypatch):
+    """divergence_solve that runs out of iterations ends with an UPDATE (dfsph_solver.rs:474-502): the XSPH sums of its
+    last evaluation are stale, so the separate XSPH pass must run."""
+    monkeypatch.setenv("SALVA_B200_FUSE_XSPH", "1")
+    sc = _small_scene(seed=41, forces=(scenes.xsph_viscosity(0.5, 0.0),))
+    solver = DFSPHSolver()
+    solver.max_divergence_iter, solver.max_divergence_error = 2, 1e-9      # never converges: exactly 2 updates
+    gpu = LiquidWorld(solver, particle_radius=sc["particle_radius"], smoothing_factor=2.0)
+    cpu = OracleWorld(sc["particle_radius"], 2.0, max_divergence_iter=2, max_divergence_error=1e-9)
+    fg, _ = scenes.populate(gpu, sc)
+    fc, _ = scenes.populate(cpu, sc)
+    dt = 0.005
+    for _ in range(6):
+        gpu.step(dt)
+        cpu.step(dt)
+    assert gpu.stats()["n_divergence_iter"] == 2 and gpu.stats()["n_divergence_eval"] == 2
+    pg, vg = gpu.read_fluid(fg[0])
+    pc, vc = cpu.read_fluid(fc[0])
+    h = float(gpu.h)
+    assert _rel(gpu.debug(fg[0], "acceleration"), cpu.debug(fc[0], "acceleration")) <= 1e-3
+    assert np.abs(pg - pc).max() <= 1e-3 * h
+    assert np.abs(vg - vc).max() <= 1e-3 * h / dt
+
+
+@pytest.mark.parametrize("mode", ["forced", "free", "boundary-term-fallback"])
+def test_xsph_fused_with_divergence_evaluation(mode, monkeypatch):
+    """SALVA_B200_FUSE_XSPH=1: the XSPH sums ride with the divergence loop's stand-alone evaluations
+    (k_vel_divergence_xsph_u) and k_fold_velocities applies the last ones; with a boundary coefficient the engine must
+    fall back to the separate pass.  Same tolerances as the plain trajectory test."""
+    monkeypatch.setenv("SALVA_B200_FUSE_XSPH", "1")
+    forces = (scenes.xsph_viscosity(0.5, 0.3 if mode == "boundary-term-fallback" else 0.0),)
+    sc = _small_scene(seed=37, forces=forces)
+    gpu, cpu, fg, fc, _, _ = _pair(sc)
+    dt = 0.005
+    if mode != "free":
+        for w in (gpu, cpu):
+            w.force_iterations(2, 3)
+    for _ in range(8):
+        gpu.step(dt)
+        cpu.step(dt)
+    pg, vg = gpu.read_fluid(fg[0])
+    pc, vc = cpu.read_fluid(fc[0])
+    h = float(gpu.h)
+    ac = cpu.debug(fc[0], "acceleration")
+    assert np.abs(ac - np.array([0, -9.81, 0], np.float32)).max() > 0.5     # XSPH is acting
+    assert _rel(gpu.debug(fg[0], "acceleration"), ac) <= 1e-3
+    assert np.abs(pg - pc).max() <= 1e-3 * h
+    assert np.abs(vg - vc).max() <= 1e-3 * h / dt
+
+
 def test_wcsph_boundary_coefficient_is_rejected():
     from salva_b200 import SphError
     gpu = LiquidWorld(particle_radius=0.05)
