@@ -11,9 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
-def _build(tmp_path):
-    exe = str(tmp_path / "basic3")
-    r = subprocess.run([GXX, "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "basic3.cpp"),
+def _build(tmp_path, name="basic3"):
+    exe = str(tmp_path / name)
+    r = subprocess.run([GXX, "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", name + ".cpp"),
                         "-L" + os.path.join(ROOT, "salva_b200"), "-lsalva_b200", "-Wl,-rpath," + os.path.join(ROOT, "salva_b200"), "-o", exe],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -27,6 +27,18 @@ def test_cpp_mirror_builds_and_fails_loudly_without_cuda(tmp_path):
         pytest.skip("CUDA present")
     r = subprocess.run([exe, "1"], capture_output=True, text=True)
     assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_cpp_custom_force_example_builds(tmp_path):
+    """examples/custom_forces3.cpp (examples3d/custom_forces3.rs): user NonPressureForce plugins as C++ trait objects."""
+    import torch
+    exe = _build(tmp_path, "custom_forces3")
+    if torch.cuda.is_available():
+        r = subprocess.run([exe, "3"], capture_output=True, text=True)
+        assert r.returncode == 0 and "custom_forces3: 1000 particles" in r.stdout, r.stderr
+    else:
+        r = subprocess.run([exe, "1"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
 
 
 @pytest.mark.gpu
