@@ -200,8 +200,10 @@ class NumpyDFSPH:
         for fi, fl in enumerate(self.fl):
             sel = self.fid == fi
             sm = self.Mff & self.same & sel[:, None]
-            for kind, p in fl["forces"]:
-                if kind == 0:  # XSPH
+            for force_index, (kind, p) in enumerate(fl["forces"]):
+                if kind == 3:  # Becker 2009 (becker2009_elasticity.rs:84-334); rotations by SVD polar decomposition
+                    acc = self._becker(acc, fi, force_index, p, sel)
+                elif kind == 0:  # XSPH
                     cf, cb = p[0], p[1]
                     dv = (self.V[None, :, :] - self.V[:, None, :]).astype(F)
                     c = np.where(sm, cf * self.Wff * self.vol[None, :] * self.rho0[:, None] / self.dens[None, :], F(0)).astype(F)
@@ -325,6 +327,87 @@ class NumpyDFSPH:
                 else:
                     raise NotImplementedError(kind)
         return acc
+
+    def _becker(self, acc, fi, force_index, p, sel):
+        """Dense restatement of Becker2009Elasticity::solve.  The reference extracts the rotation of A_pq with nalgebra's
+        iterative `from_matrix_eps` (warm-started, <= 20 iterations); here it is the orthogonal polar factor from an f64
+        SVD — a different algorithm that agrees with the converged iteration, so it independently checks the oracle's
+        restatement of that third-party routine."""
+        h = self.h
+        young, poisson, nonlinear = F(p[0]), F(p[1]), p[2] != 0
+        one, two = F(1), F(2)
+        d0 = (young * (one - poisson)) / ((one + poisson) * (one - two * poisson))     # elasticity_coefficients :15-26
+        d1 = (young * poisson) / ((one + poisson) * (one - two * poisson))
+        d2 = (young * (one - two * poisson)) / (two * (one + poisson) * (one - two * poisson))
+        idx = np.nonzero(sel)[0]
+        n = len(idx)
+        P = self.P[idx]
+        mass = self.mass[idx]
+        st = self.__dict__.setdefault("_becker_state", {}).get((fi, force_index))
+        if st is None or len(st["pos0"]) != n:                                           # init :84-113
+            old = st["vol0"] if st is not None else np.zeros(0, F)
+            d = (P[:, None, :] - P[None, :, :]).astype(F)
+            dd = ((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]).astype(F)
+            M0 = dd <= h * h                                                             # compute_self_contacts, self included
+            W0, G0 = self._kernels(d, dd, M0)
+            raw = np.zeros(n, F)
+            raw[:min(n, len(old))] = old[:min(n, len(old))]                              # Vec::resize keeps old entries (:89)
+            raw = (raw + two * (W0 * mass[None, :]).sum(axis=1, dtype=F)).astype(F)      # both ends of every ordered pair
+            st = dict(pos0=P.copy(), M0=M0, W0=W0, G0=G0, vol0=(mass / raw).astype(F))
+            self._becker_state[(fi, force_index)] = st
+        M0, W0, G0, vol0, P0 = st["M0"], st["W0"], st["G0"], st["vol0"], st["pos0"]
+        p_ji = (P[None, :, :] - P[:, None, :]).astype(F)                                 # [i, j] = p_j - p_i
+        p0_ji = (P0[None, :, :] - P0[:, None, :]).astype(F)
+        coeff = np.where(M0, W0 * mass[None, :], F(0)).astype(F)
+        a_pq = np.einsum("ijr,ijc->irc", p_ji, p0_ji * coeff[..., None]).astype(F)      # compute_rotations :115-137
+        R = np.zeros((n, 3, 3), F)
+        for i in range(n):
+            u, _, vt = np.linalg.svd(a_pq[i].astype(np.float64))
+            r = u @ vt
+            if np.linalg.det(r) < 0:
+                u[:, -1] *= -1
+                r = u @ vt
+            R[i] = r.astype(F)
+        rt_p = np.einsum("icr,ijc->ijr", R, p_ji).astype(F)                              # R_i^T p_ji  (inverse_transform_vector)
+        u_ji = (rt_p - p0_ji).astype(F)
+        gv = np.where(M0[..., None], G0 * vol0[None, :, None], F(0)).astype(F)           # gradient * volumes0[j]
+        grad_tr = np.einsum("ijr,ijc->irc", gv, u_ji).astype(F)                          # compute_stresses :139-262
+        k = F(0.564)
+        if nonlinear:
+            J = (grad_tr + np.eye(3, dtype=F)[None]).astype(F)
+            JJt = np.einsum("irk,ick->irc", J, J).astype(F)
+            e = np.stack([JJt[:, 0, 0] - one, JJt[:, 1, 1] - one, JJt[:, 2, 2] - one], -1).astype(F)
+            sh = np.stack([JJt[:, 1, 0], JJt[:, 2, 0], JJt[:, 2, 1]], -1).astype(F)
+            s012 = np.stack([d0 * e[:, 0] + d1 * e[:, 1] + d1 * e[:, 2], d1 * e[:, 0] + d0 * e[:, 1] + d1 * e[:, 2],
+                             d1 * e[:, 0] + d1 * e[:, 1] + d0 * e[:, 2]], -1).astype(F) * k
+        else:
+            e = np.stack([grad_tr[:, 0, 0], grad_tr[:, 1, 1], grad_tr[:, 2, 2]], -1).astype(F)
+            sh = np.stack([grad_tr[:, 1, 0] + grad_tr[:, 0, 1], grad_tr[:, 2, 0] + grad_tr[:, 0, 2],
+                           grad_tr[:, 1, 2] + grad_tr[:, 2, 1]], -1).astype(F)
+            s012 = np.stack([d0 * e[:, 0] + d1 * e[:, 1] + d1 * e[:, 2], d1 * e[:, 0] + d0 * e[:, 1] + d1 * e[:, 2],
+                             d1 * e[:, 0] + d1 * e[:, 1] + d0 * e[:, 2]], -1).astype(F)
+        s345 = (sh * k * d2).astype(F)
+        S = np.zeros((n, 3, 3), F)                                                       # sym_mat_mul_vec layout :28-39
+        S[:, 0, 0], S[:, 1, 1], S[:, 2, 2] = s012[:, 0], s012[:, 1], s012[:, 2]
+        S[:, 0, 1] = S[:, 1, 0] = s345[:, 0]
+        S[:, 0, 2] = S[:, 2, 0] = s345[:, 1]
+        S[:, 1, 2] = S[:, 2, 1] = s345[:, 2]
+        d_ij = gv                                                                        # gradient * volumes0[j]
+        d_ji = np.where(M0[..., None], G0 * (-vol0)[:, None, None], F(0)).astype(F)      # gradient * (-volumes0[i])
+        sd_ij = np.einsum("irc,ijc->ijr", S, d_ij).astype(F)                             # stress[i] * d_ij
+        sd_ji = np.einsum("jrc,ijc->ijr", S, d_ji).astype(F)                             # stress[j] * d_ji
+        if nonlinear:
+            f_ji = ((sd_ij + np.einsum("irc,ijc->ijr", grad_tr, sd_ij)) * (-vol0)[:, None, None]).astype(F)
+            f_ij = ((sd_ji + np.einsum("jrc,ijc->ijr", grad_tr, sd_ji)) * (-vol0)[None, :, None]).astype(F)
+        else:
+            f_ji = (sd_ij * (-vol0)[:, None, None]).astype(F)
+            f_ij = (sd_ji * (-vol0)[None, :, None]).astype(F)
+        force = ((np.einsum("jrc,ijc->ijr", R, f_ij) - np.einsum("irc,ijc->ijr", R, f_ji)) * F(0.5)).astype(F)
+        force = np.where(M0[..., None], force, F(0))
+        a = (force.sum(axis=1, dtype=F) / mass[:, None]).astype(F)
+        out = acc.copy()
+        out[idx] = (out[idx] + a).astype(F)
+        return out
 
     def step(self, dt, gravity=(0.0, -9.81, 0.0)):
         """liquid_world.rs:67-158 + dfsph_solver.rs:667-708"""

@@ -79,6 +79,27 @@ def test_dfsph_viscosity_matches_dense_restatement(two):
         assert np.abs(vo - vn).max() <= 1e-4 * np.abs(vo).max()
 
 
+@pytest.mark.parametrize("nonlinear", [True, False], ids=["nonlinear", "linear"])
+def test_becker2009_elasticity_matches_dense_restatement(nonlinear):
+    """Row a15.  The oracle restates nalgebra's iterative `Rotation3::from_matrix_eps`; the numpy restatement takes the
+    rotation from an f64 SVD polar decomposition instead — an independent check of that third-party routine and of the
+    rest-pose bookkeeping (volumes0 double counting, stresses with the 0.564 constant, corotated forces)."""
+    sc = _scene(5, forces=(scenes.becker2009_elasticity(5.0e4, 0.3, nonlinear),))
+    o = OracleWorld(sc["particle_radius"], 2.0)
+    n = NumpyDFSPH(sc["particle_radius"], 2.0)
+    fo = _run(o, sc, 4, 2, 3)
+    fn = _run(n, sc, 4, 2, 3)
+    g = np.array([0.0, -9.81, 0.0], np.float32)
+    acc_o = o.debug(fo[0], "acceleration")
+    scale = np.abs(acc_o - g).max()
+    assert scale > 5.0                                    # the elastic force is acting
+    assert np.abs(acc_o - n.acc).max() <= 1e-4 * scale
+    po, vo = o.read_fluid(fo[0])
+    pn, vn = n.read_fluid(fn[0])
+    assert np.abs(po - pn).max() <= 1e-5 * float(o.h)
+    assert np.abs(vo - vn).max() <= 1e-4
+
+
 def test_two_fluids_free_running_match():
     sc = _scene(9, two_fluids=True, forces=(scenes.xsph_viscosity(0.5, 0.0),))
     o = OracleWorld(sc["particle_radius"], 2.0)
