@@ -14,6 +14,13 @@
  *     (the memory layout of Vec<Point3<f32>> / Vec<Vector3<f32>>).
  *   - A world has one logical owner (matches `&mut self`); calls on one world
  *     must be externally serialised; different worlds are independent.
+ *     Callbacks (host forces, coupling managers) run on the calling thread
+ *     inside sph_world_step*; they may call the read / write / query entry
+ *     points of the SAME world re-entrantly, but not step it or add / remove
+ *     fluids.
+ *   - Fluid and boundary handles are (slot | generation << 16), like the
+ *     reference's arena handles: removing an object invalidates only its own
+ *     handle; a later add may reuse the slot under a new generation.
  *   - Errors: every call returns an sph_status; sph_last_error() gives text.
  *     Reference `assert!`/panic sites map to SPH_ERR_ZERO_DENSITY /
  *     SPH_ERR_INVALID; the Rust shim turns them back into panics.
@@ -149,6 +156,49 @@ sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid, const sph_force_de
 typedef void (*sph_host_force_fn)(void* user, float dt, float inv_dt, float kernel_radius, size_t n, const float* positions_xyz,
                                   const float* velocities_xyz, const float* densities, float* accelerations_xyz);
 sph_status sph_fluid_push_host_force(sph_world* w, uint32_t fluid, sph_host_force_fn fn, void* user);
+
+/* The same plugin hook with the COMPLETE argument list of NonPressureForce::solve (nonpressure_force.rs:15-27):
+ * timestep, kernel radius, fluid_fluid_contacts, fluid_boundaries_contacts, the fluid, the boundaries, the densities.
+ * Contacts (contacts.rs:12-27 `Contact {i_model, j_model, i, j, weight, gradient}`) are materialised on request as CSR
+ * over the fluid's particles in ORIGINAL index order: the contacts of particle i are entries ff_offsets[i] ..
+ * ff_offsets[i+1]; `j` is the neighbour's index INSIDE its own fluid / boundary, `j_model` that object's slot
+ * (handle & 0xFFFF; == ctx.fluid_index for same-fluid contacts); the self contact (j == i, gradient 0) is included, as
+ * in the reference.  All pointers are host memory owned by the library for the duration of the call. */
+enum { SPH_HOST_FORCE_CONTACTS = 1u,    /* fill ff_* / fb_* */
+       SPH_HOST_FORCE_BOUNDARIES = 2u   /* fill boundaries[] (positions, velocities, volumes) */ };
+typedef struct {
+    size_t n;
+    const float* positions_xyz;   /* boundary.positions  boundary.rs:13 */
+    const float* velocities_xyz;  /* boundary.velocities boundary.rs:15 */
+    const float* volumes;         /* boundary.volumes    boundary.rs:17 (this step's) */
+} sph_boundary_view;
+typedef struct {
+    float dt, inv_dt;             /* TimestepManager::dt() / inv_dt() at the call (the previous step's: dfsph_solver.rs:693-702) */
+    float kernel_radius, particle_radius;
+    uint32_t fluid;               /* handle of the fluid the force belongs to */
+    uint32_t fluid_index;         /* its slot == the i_model / j_model value of same-fluid contacts */
+    float density0;
+    size_t n;                     /* particles of the fluid */
+    const float* positions_xyz;
+    const float* velocities_xyz;
+    const float* densities;       /* solve()'s `densities` argument */
+    const float* volumes;         /* fluid.volumes (NULL in slab-decomposed worlds) */
+    float* accelerations_xyz;     /* fluid.accelerations: add to it in place */
+    const uint32_t* ff_offsets;   /* n + 1 */
+    const uint32_t* ff_j;
+    const uint32_t* ff_j_model;
+    const float* ff_weight;       /* contact.weight   = W(|x_ij|)      helper.rs:19 */
+    const float* ff_gradient_xyz; /* contact.gradient = grad W(x_ij)   helper.rs:24-25 */
+    const uint32_t* fb_offsets;
+    const uint32_t* fb_j;
+    const uint32_t* fb_j_model;
+    const float* fb_weight;
+    const float* fb_gradient_xyz;
+    size_t n_boundaries;          /* number of boundary slots (removed ones have n == 0) */
+    const sph_boundary_view* boundaries;
+} sph_host_force_ctx;
+typedef void (*sph_host_force_fn2)(void* user, const sph_host_force_ctx* ctx);
+sph_status sph_fluid_push_host_force2(sph_world* w, uint32_t fluid, sph_host_force_fn2 fn, void* user, uint32_t flags);
 /* Fluid::add_particles fluid.rs:126-150 */
 sph_status sph_fluid_append(sph_world* w, uint32_t fluid, const float* pos_xyz, const float* vel_xyz, size_t n);
 /* Fluid::delete_particle_at_next_timestep fluid.rs:71-76; applied at the next step (fluid.rs:88-98). */
@@ -158,6 +208,12 @@ sph_status sph_fluid_write(sph_world* w, uint32_t fluid, const float* pos_xyz, c
 /* Reads fluid.positions / fluid.velocities in ORIGINAL index order. NULL = skip. */
 sph_status sph_fluid_read(sph_world* w, uint32_t fluid, float* pos_xyz, float* vel_xyz, size_t cap, size_t* n);
 sph_status sph_fluid_count(sph_world* w, uint32_t fluid, size_t* n);
+/* LiquidWorld::remove_fluid liquid_world.rs:171-173 (the handle dies, the others stay valid). */
+sph_status sph_fluid_remove(sph_world* w, uint32_t fluid);
+/* Zero-copy read-back for renderers (testbed_plugin.rs:361-376 copies fluid.positions every frame): DEVICE pointers to
+ * packed xyz f32 in ORIGINAL index order, valid until the next call on this world. */
+sph_status sph_fluid_map_positions(sph_world* w, uint32_t fluid, const float** device_xyz, size_t* n);
+sph_status sph_fluid_map_velocities(sph_world* w, uint32_t fluid, const float** device_xyz, size_t* n);
 
 /* LiquidWorld::add_boundary liquid_world.rs:166 + Boundary::new boundary.rs:28-46.
  * want_forces != 0  <=>  boundary.forces = Some(..) (boundary.rs:21). */
@@ -165,6 +221,12 @@ sph_status sph_boundary_add(sph_world* w, const float* pos_xyz, const float* vel
                             uint32_t memberships, uint32_t filter, int want_forces, uint32_t* handle);
 /* CouplingManager::update_boundaries rewriting boundary particles (coupling_manager.rs:12-20). */
 sph_status sph_boundary_write(sph_world* w, uint32_t boundary, const float* pos_xyz, const float* vel_xyz, size_t n);
+/* LiquidWorld::remove_boundary liquid_world.rs:176-178. */
+sph_status sph_boundary_remove(sph_world* w, uint32_t boundary);
+/* A coupled collider re-samples its boundary every step with a varying particle count (fluids_pipeline.rs:175-245:
+ * positions.clear(); push(..)): replaces the whole particle set. */
+sph_status sph_boundary_set_particles(sph_world* w, uint32_t boundary, const float* pos_xyz, const float* vel_xyz, size_t n);
+sph_status sph_boundary_count(sph_world* w, uint32_t boundary, size_t* n);
 /* boundary.forces read by CouplingManager::transmit_forces (coupling_manager.rs:22-27). */
 sph_status sph_boundary_read_forces(sph_world* w, uint32_t boundary, float* f_xyz, size_t cap);
 /* boundary.volumes after compute_boundary_volumes (dfsph_solver.rs:72-96). */
@@ -179,8 +241,44 @@ sph_status sph_boundary_read_volumes(sph_world* w, uint32_t boundary, float* vol
 sph_status sph_world_particles_in_aabb(sph_world* w, const float mins[3], const float maxs[3], uint32_t* kinds, uint32_t* handles,
                                        uint32_t* indices, size_t cap, size_t* n);
 
+/* LiquidWorld::particles_intersecting_shape liquid_world.rs:246-281 for the shapes a C ABI can name (parry `Shape` trait
+ * objects cannot cross it): the cells of the posed shape's AABB (shape.compute_aabb(pos)), every particle in them with
+ * shape.distance_to_point(pos, p, solid = true) <= particle_radius.  rotation_rowmajor == NULL: identity.  Output as
+ * sph_world_particles_in_aabb. */
+enum { SPH_SHAPE_BALL = 1,     /* p[0] = radius */
+       SPH_SHAPE_CUBOID = 2,   /* p[0..2] = half extents */
+       SPH_SHAPE_CAPSULE = 3   /* p[0] = half height (segment along local y), p[1] = radius */ };
+typedef struct {
+    int32_t kind;
+    float   p[4];
+} sph_shape;
+sph_status sph_world_particles_in_shape(sph_world* w, const sph_shape* shape, const float translation[3], const float rotation_rowmajor[9],
+                                        uint32_t* kinds, uint32_t* handles, uint32_t* indices, size_t cap, size_t* n);
+
 /* LiquidWorld::step  liquid_world.rs:62-158 */
 sph_status sph_world_step(sph_world* w, float dt, const float gravity[3]);
+
+/* trait CouplingManager (coupling/coupling_manager.rs:9-28) + LiquidWorld::step_with_coupling (liquid_world.rs:67-158).
+ * update_boundaries runs after this substep's FLUID particles are in the cell grid and before the boundaries are
+ * (liquid_world.rs:86-103): particle queries issued from it return fluid particles only, and it may rewrite boundaries
+ * (sph_boundary_write / sph_boundary_set_particles) and push fluid particles out (sph_fluid_read / sph_fluid_write), as
+ * DynamicContactSampling does (fluids_pipeline.rs:192-255).  transmit_forces runs after the solve (liquid_world.rs:146)
+ * and reads sph_boundary_read_forces.  dt / inv_dt are the TimestepManager's values at each call. */
+typedef struct {
+    void (*update_boundaries)(void* user, sph_world* w, float dt, float inv_dt, float h, float particle_radius);
+    void (*transmit_forces)(void* user, sph_world* w, float dt, float inv_dt);
+    void* user;
+} sph_coupling_manager;
+sph_status sph_world_step_with_coupling(sph_world* w, float dt, const float gravity[3], const sph_coupling_manager* coupling);
+
+/* Snapshot / restore of everything the solver carries ACROSS steps: positions, velocities, velocity_changes
+ * (dfsph_solver.rs:44, carried :704-706), the lagging dt / inv_dt (timestep_manager.rs:29-30), IISPH warm-start pressures
+ * (iisph_solver.rs:673-677), Becker-2009 rest pose and rotations (becker2009_elasticity.rs:84-135), volumes, particle ids,
+ * slab planes.  The blob restores into a world with the same fluids / forces / boundaries pushed in the same order (the
+ * scene description stays with the caller).  In deterministic mode a restored run is bit-identical to the original. */
+sph_status sph_world_snapshot_size(sph_world* w, size_t* bytes);
+sph_status sph_world_snapshot_save(sph_world* w, void* buffer, size_t capacity, size_t* written);
+sph_status sph_world_snapshot_load(sph_world* w, const void* buffer, size_t length);
 /* Parity/bench aid: run exactly this many velocity-change updates in the next steps'
  * divergence / pressure loops instead of the error-driven break (negative = free running). */
 sph_status sph_world_force_iterations(sph_world* w, int32_t n_divergence, int32_t n_pressure);

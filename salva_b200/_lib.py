@@ -44,6 +44,37 @@ _fp, _u8p, _vp = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.c_void_p
 HOST_FORCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float),
                             C.POINTER(C.c_float), C.POINTER(C.c_float))
 
+
+
+class BoundaryView(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("positions_xyz", C.POINTER(C.c_float)), ("velocities_xyz", C.POINTER(C.c_float)),
+                ("volumes", C.POINTER(C.c_float))]
+
+
+class HostForceCtx(C.Structure):
+    _u32p, _f32p = C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+    _fields_ = [("dt", C.c_float), ("inv_dt", C.c_float), ("kernel_radius", C.c_float), ("particle_radius", C.c_float),
+                ("fluid", C.c_uint32), ("fluid_index", C.c_uint32), ("density0", C.c_float), ("n", C.c_size_t),
+                ("positions_xyz", _f32p), ("velocities_xyz", _f32p), ("densities", _f32p), ("volumes", _f32p),
+                ("accelerations_xyz", _f32p),
+                ("ff_offsets", _u32p), ("ff_j", _u32p), ("ff_j_model", _u32p), ("ff_weight", _f32p), ("ff_gradient_xyz", _f32p),
+                ("fb_offsets", _u32p), ("fb_j", _u32p), ("fb_j_model", _u32p), ("fb_weight", _f32p), ("fb_gradient_xyz", _f32p),
+                ("n_boundaries", C.c_size_t), ("boundaries", C.POINTER(BoundaryView))]
+
+
+class Shape(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("p", C.c_float * 4)]
+
+
+HOST_FORCE_FN2 = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(HostForceCtx))
+COUPLING_UPDATE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float)
+COUPLING_TRANSMIT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_float, C.c_float)
+
+
+class CouplingManagerC(C.Structure):
+    _fields_ = [("update_boundaries", COUPLING_UPDATE_FN), ("transmit_forces", COUPLING_TRANSMIT_FN), ("user", C.c_void_p)]
+
+
 # every symbol include/sph.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "sph_world_desc_default": (None, [C.POINTER(WorldDesc)]),
@@ -78,6 +109,19 @@ SYMBOLS = {
     "sph_world_set_slab": (C.c_int, [_vp, C.c_int32, C.c_int32]),
     "sph_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "sph_fluid_set_ids": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t]),
+    "sph_fluid_push_host_force2": (C.c_int, [_vp, C.c_uint32, HOST_FORCE_FN2, _vp, C.c_uint32]),
+    "sph_fluid_remove": (C.c_int, [_vp, C.c_uint32]),
+    "sph_fluid_map_positions": (C.c_int, [_vp, C.c_uint32, C.POINTER(_fp), C.POINTER(C.c_size_t)]),
+    "sph_fluid_map_velocities": (C.c_int, [_vp, C.c_uint32, C.POINTER(_fp), C.POINTER(C.c_size_t)]),
+    "sph_boundary_remove": (C.c_int, [_vp, C.c_uint32]),
+    "sph_boundary_set_particles": (C.c_int, [_vp, C.c_uint32, _fp, _fp, C.c_size_t]),
+    "sph_boundary_count": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_size_t)]),
+    "sph_world_particles_in_shape": (C.c_int, [_vp, C.POINTER(Shape), _fp, _fp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                               C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sph_world_step_with_coupling": (C.c_int, [_vp, C.c_float, _fp, C.POINTER(CouplingManagerC)]),
+    "sph_world_snapshot_size": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
+    "sph_world_snapshot_save": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sph_world_snapshot_load": (C.c_int, [_vp, _vp, C.c_size_t]),
     "sph_fluid_read_ids": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t]),
 }
 
@@ -90,7 +134,10 @@ def lib():
             raise RuntimeError("libsalva_b200.so is not built (run `python -c 'import __graft_entry__ as g; "
                                "g.build()'`); there is no CPU fallback")
         L = C.CDLL(LIB_PATH)
+        ab_build = bool(os.environ.get("SALVA_B200_LIB"))  # A/B experiment builds may predate the newest entry points
         for name, (res, args) in SYMBOLS.items():
+            if ab_build and not hasattr(L, name):
+                continue
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

@@ -35,7 +35,9 @@ namespace {
 
 // All worlds of a process share the module's __constant__ block; API calls are serialised per process
 // (GPU work of different worlds on one device would serialise anyway) and re-upload it on entry.
-std::mutex g_mutex;
+// recursive: host-force and coupling callbacks run inside sph_world_step and may call back into the API (reads,
+// boundary rewrites, queries) on the same thread
+std::recursive_mutex g_mutex;
 const void* g_const_owner = nullptr;
 
 inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
@@ -75,6 +77,8 @@ constexpr int FORCE_HOST_CALLBACK = 100;  // internal kind of sph_fluid_push_hos
 struct ForceRec {
     sph_force_desc d;
     sph_host_force_fn host_fn = nullptr;
+    sph_host_force_fn2 host_fn2 = nullptr;  // context-style callback (contacts / boundaries on request)
+    uint32_t host_flags = 0;
     void* host_user = nullptr;
     ElasticityState* elastic = nullptr;  // Becker2009 rest-pose state (sph_elasticity.cuh)
     uint32_t visc_iters = 0;             // DFSPHViscosity: acceleration updates of the last solve
@@ -88,11 +92,15 @@ struct FluidRec {
     std::vector<uint8_t> pending_delete;
     size_t n_pending = 0;
     float uniform_mass = 0.f;  // common particle mass if all volumes are equal, else 0
+    bool alive = true;         // false after LiquidWorld::remove_fluid (liquid_world.rs:171-173); the slot is reused by the next add
+    uint32_t gen = 0;          // handle = slot | gen << 16 (the reference's arena handles carry a generation too)
 };
 struct BoundaryRec {
     size_t n = 0, offset = 0;
     uint32_t memberships = 1, filter = 0xFFFFFFFFu;
     bool want_forces = false;
+    bool alive = true;
+    uint32_t gen = 0;
 };
 
 sph_status iisph_step(sph_world* w, float dt_total, const float g[3]);
@@ -111,6 +119,7 @@ void slab_release(sph_world* w);
 const float* iisph_pred(sph_world* w);
 sph_status elasticity_solve(sph_world* w, uint32_t fluid, ForceRec& fr);
 void elasticity_release(ForceRec& fr);
+sph_status elasticity_restore(sph_world* w, ForceRec& fr, size_t n, uint32_t cap0, uint32_t stride0, const char* blob);
 sph_status viscosity_solve(sph_world* w, uint32_t fluid, ForceRec& fr);
 void viscosity_release(sph_world* w);
 inline float __uint_as_float_host(uint32_t u) {
@@ -125,7 +134,7 @@ struct SlabState {
     int lo = INT_MIN, hi = INT_MAX;  // owned cell columns [lo, hi) in absolute cell coordinates floor(x / h)
     int has_left = 0, has_right = 0;
     void* comm = nullptr;
-    DBuf<uint32_t> d_cnt, flag, flag_o, gid_l, gid_r;
+    DBuf<uint32_t> d_cnt, flag, flag_o, gid_l, gid_r, gid_cl, gid_cr;
     DBuf<unsigned long long> d_cnt64;
     DBuf<float4> out_l[3], out_r[3], col_l[3], col_r[3];
     bool global_valid = false;
@@ -203,12 +212,20 @@ struct sph_world {
     int uni_eval_mode = 1, uni_upd_mode = 1;  // 1: position record through the texture pipe, 2: through the LSU pipe
     DBuf<float4> pvx4, pk4;
     DBuf<float2> vyz2;
+    DBuf<Rec8> rec8;      // 256-bit gather records (pos, v*, rho) of the pressure-loop evaluations (sph_kernels.cuh Rec8)
+    int use_rec8 = 0;
     cudaTextureObject_t tex_pvx = 0, tex_vyz = 0, tex_pk = 0;
     const void* tex_pvx_ptr = nullptr;
     const void* tex_vyz_ptr = nullptr;
     const void* tex_pk_ptr = nullptr;
     DBuf<float> he_colors, he_gradc;  // He2014 colours / squared colour-gradient norms (he2014_surface_tension.rs:16-17)
     DBuf<uint32_t> q_out, q_count;     // particles_intersecting_aabb results
+    DBuf<float> map_pos, map_vel;      // sph_fluid_map_positions / _velocities: ORIGINAL-order device views
+    bool in_coupling = false;          // inside CouplingManager::update_boundaries: the grid holds fluids only (liquid_world.rs:90-103)
+    const sph_coupling_manager* coupling = nullptr;
+    // ParticlesContacts materialised for host plugins (original order CSR)
+    DBuf<uint32_t> ct_cnt[2], ct_j[2], ct_model[2];
+    DBuf<float> ct_w[2], ct_g[2];
     DBuf<uint32_t> d_ticket;      // last-block ticket of the in-kernel error reduction (kept at 0 between launches)
     bool errsum_ready = false;    // the last evaluation launch already reduced its partials into errsum
     DBuf<LoopCtl> d_ctl;          // device-side Jacobi loop control (sph_kernels.cuh LoopCtl)
@@ -278,6 +295,27 @@ namespace {
         }                                                                              \
     } while (0)
 
+inline uint32_t make_handle(size_t slot, uint32_t gen) { return (uint32_t)slot | (gen << 16); }
+// slot of a live fluid / boundary handle, or -1
+inline int fluid_slot(const sph_world* w, uint32_t handle) {
+    const uint32_t slot = handle & 0xFFFFu;
+    if (slot >= w->fluids.size() || !w->fluids[slot].alive || (w->fluids[slot].gen & 0xFFFFu) != (handle >> 16)) return -1;
+    return (int)slot;
+}
+inline int boundary_slot(const sph_world* w, uint32_t handle) {
+    const uint32_t slot = handle & 0xFFFFu;
+    if (slot >= w->bounds.size() || !w->bounds[slot].alive || (w->bounds[slot].gen & 0xFFFFu) != (handle >> 16)) return -1;
+    return (int)slot;
+}
+#define FLUID_OR_FAIL(var, handle)                                                                   \
+    const int var##_slot_ = fluid_slot(w, handle);                                                   \
+    if (var##_slot_ < 0) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", (unsigned)(handle)); \
+    const uint32_t var = (uint32_t)var##_slot_;
+#define BOUNDARY_OR_FAIL(var, handle)                                                                   \
+    const int var##_slot_ = boundary_slot(w, handle);                                                   \
+    if (var##_slot_ < 0) return w->fail(SPH_ERR_INVALID, "bad boundary handle %u", (unsigned)(handle)); \
+    const uint32_t var = (uint32_t)var##_slot_;
+
 enum { SP_DIV_EVAL = 0, SP_DIV_UPD, SP_PRED, SP_PUPD, SP_COUNT };
 sph_status span_begin(sph_world* w, int slot) {
     if (w->n_spans == w->spans.size()) {
@@ -315,6 +353,11 @@ void fill_static_consts(sph_world* w) {
     c.h2 = w->h * w->h;
     c.sigma = 8.0f / (3.14159265358979323846f * w->h * w->h * w->h);
     c.dsigma = c.sigma / w->h;
+    c.dsigma6 = 6.0f * c.dsigma;
+    {
+        const double a = (double)F32_EPS * (double)F32_EPS, b = 1.0e-5 * (double)w->h * 1.0e-5 * (double)w->h;
+        c.g_t2 = (float)std::max(a, b);
+    }
     c.n_fluid = (uint32_t)w->Ntot;
     c.i_begin = w->own_begin;
     c.n_owned = (uint32_t)w->N;
@@ -439,6 +482,7 @@ sph_status ensure_fluid_buffers(sph_world* w) {
     CU(w->pvx4.ensure(N));
     CU(w->pk4.ensure(N));
     CU(w->vyz2.ensure(N));
+    if (w->use_rec8) CU(w->rec8.ensure(N));
     CU(w->acc.ensure(N));
     CU(w->dbg_acc.ensure(N));
     CU(w->dens.ensure(N + 8));
@@ -459,7 +503,7 @@ sph_status ensure_fluid_buffers(sph_world* w) {
     }
     CU(w->nbr_b.ensure((size_t)w->cap_b * w->stride));
     uint32_t nblk = cdiv(std::max<size_t>(N, 1), PASS_T);
-    CU(w->partial.ensure((size_t)nblk * std::max<size_t>(1, w->fluids.size())));
+    CU(w->partial.ensure((size_t)(nblk + 3) * std::max<size_t>(1, w->fluids.size())));  // +3: a slab pass may run as three sub-range launches
     CU(w->errsum.ensure(MAX_FLUIDS));
     return SPH_OK;
 }
@@ -660,7 +704,9 @@ sph_status phase_grid(sph_world* w) {
     LAUNCH(k_cell_hist, N, 256, w->pos[c].p, (uint32_t)N, w->cid.p, w->rank.p, w->cstart.p);
     TRY(scan_exclusive(w, w->cstart.p, ncell + 1));
     LAUNCH(k_cell_scatter, N, 256, (uint32_t)N, w->cid.p, w->rank.p, w->cstart.p, w->perm.p);
-    if (w->desc.deterministic) LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->cstart.p, w->perm.p);
+    if (w->desc.deterministic)
+        LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->cstart.p, w->perm.p, (const uint32_t*)w->gid[c].p,
+               w->fluids.size() > 1 ? (const float4*)w->vel[c].p : (const float4*)nullptr);
     if (N) {
         GatherSet g;
         memset(&g, 0, sizeof g);
@@ -690,7 +736,7 @@ sph_status phase_grid(sph_world* w) {
         LAUNCH(k_cell_hist, B, 256, w->bpos[bc].p, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p);
         TRY(scan_exclusive(w, w->bstart.p, ncell + 1));
         LAUNCH(k_cell_scatter, B, 256, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p, w->bperm.p);
-        if (w->desc.deterministic) LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->bstart.p, w->bperm.p);
+        if (w->desc.deterministic) LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->bstart.p, w->bperm.p, (const uint32_t*)nullptr, (const float4*)nullptr);
         GatherSet g;
         memset(&g, 0, sizeof g);
         g.in4[0] = w->bpos[bc].p; g.out4[0] = w->bpos[bc ^ 1].p;
@@ -1099,7 +1145,10 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
         uint32_t* tk = (w->single_launch && !gate) ? w->d_ticket.p : nullptr;
         if (w->unimass) {
             const bool ptex = w->uni_eval_mode == 1;
-            if (predict) {
+            if (predict && w->use_rec8 && !w->slab.active && !gate) {
+                LAUNCH_R((k_vel_divergence_r8<true>), rg, w->rec8.p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt,
+                         w->d_scal.p + 7, tk, w->errsum.p);
+            } else if (predict) {
                 if (ptex) LAUNCH_R((k_vel_divergence_u<true, true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
                                    w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
                 else LAUNCH_R((k_vel_divergence_u<true, false>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
@@ -1149,8 +1198,9 @@ sph_status launch_vel_update(sph_world* w, bool pressure, const int* gate = null
     return run_parts(w, w->unimass ? a : a1, w->unimass ? 3 : 1, nullptr, [&](Range rg, uint32_t) -> sph_status {
         if (w->unimass) {
             const bool ptex = w->uni_upd_mode == 1;
+            Rec8* rec = (pressure && w->use_rec8 && !w->slab.active && !gate) ? w->rec8.p : nullptr;
             BOOL3(k_vel_update_u, bf, pressure, ptex, rg, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p,
-                  w->bforce.p, w->inv_dt, gate);
+                  rec, w->dens.p, w->bforce.p, w->inv_dt, gate);
         } else {
             // measured (profiles/r1_v1_*): the texture pipe helps the float4 v* gather (-12 %) but not the 4-byte kappa gather
             BOOL4(k_vel_update, multi, bf, pressure, false, rg, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->kappa.p, w->tex_kappa, w->vc[c].p, w->vs.p,
@@ -1158,6 +1208,118 @@ sph_status launch_vel_update(sph_world* w, bool pressure, const int* gate = null
         }
         return SPH_OK;
     });
+}
+
+// ---- ParticlesContacts materialisation + the context-style host plugin call (nonpressure_force.rs:15-27) ---------------
+struct HostContacts {
+    std::vector<uint32_t> offsets, j, model;
+    std::vector<float> weight, gradient;
+};
+// which = 0: fluid-fluid contacts, 1: fluid-boundary contacts of fluid `f`'s particles, CSR in the fluid's original order
+sph_status materialise_contacts(sph_world* w, uint32_t f, int which, HostContacts* out) {
+    const FluidRec& fl = w->fluids[f];
+    const size_t N = w->N, Nf = fl.n;
+    const int c = w->cur, bc = w->bcur;
+    const uint32_t ob = w->own_begin;
+    const uint32_t cap = which ? w->cap_b : w->cap_f;
+    const uint32_t* cnt = which ? w->cnt_b.p : w->cnt_f.p;
+    CU(w->ct_cnt[which].ensure(N + 1));
+    LAUNCH(k_contacts_count, N, 256, (uint32_t)N, w->orig[c].p + ob, cnt + ob, cap, w->ct_cnt[which].p);
+    CU(cudaMemsetAsync(w->ct_cnt[which].p + N, 0, sizeof(uint32_t), w->st));
+    TRY(scan_exclusive(w, w->ct_cnt[which].p, N + 1));
+    std::vector<uint32_t> scan(Nf + 1);
+    CU(cudaMemcpyAsync(scan.data(), w->ct_cnt[which].p + fl.offset, (Nf + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+    uint32_t total = 0;
+    CU(cudaMemcpyAsync(&total, w->ct_cnt[which].p + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    CU(w->ct_j[which].ensure(std::max<size_t>(total, 1)));
+    CU(w->ct_model[which].ensure(std::max<size_t>(total, 1)));
+    CU(w->ct_w[which].ensure(std::max<size_t>(total, 1)));
+    CU(w->ct_g[which].ensure(3 * std::max<size_t>(total, 1)));
+    OffsetTable tab;
+    memset(&tab, 0, sizeof tab);
+    if (which) {
+        for (size_t b = 0; b < w->bounds.size(); ++b) tab.off[b] = (uint32_t)w->bounds[b].offset;
+        if (w->B)
+            LAUNCH((k_contacts_fill<true>), N, 128, (uint32_t)N, w->pos[c].p, w->bpos[bc].p, w->bvel[bc].p, w->orig[c].p, w->borig[bc].p, w->nbr_b.p, cnt, cap,
+                   w->ct_cnt[which].p, tab, w->ct_j[which].p, w->ct_model[which].p, w->ct_w[which].p, w->ct_g[which].p);
+    } else {
+        for (size_t k = 0; k < w->fluids.size(); ++k) tab.off[k] = (uint32_t)w->fluids[k].offset;
+        LAUNCH((k_contacts_fill<false>), N, 128, (uint32_t)N, w->pos[c].p, w->pos[c].p, w->vel[c].p, w->orig[c].p, w->orig[c].p, w->nbr_f.p, cnt, cap,
+               w->ct_cnt[which].p, tab, w->ct_j[which].p, w->ct_model[which].p, w->ct_w[which].p, w->ct_g[which].p);
+    }
+    const uint32_t first = scan[0], nent = scan[Nf] - scan[0];
+    out->offsets.resize(Nf + 1);
+    for (size_t i = 0; i <= Nf; ++i) out->offsets[i] = scan[i] - first;
+    out->j.resize(nent);
+    out->model.resize(nent);
+    out->weight.resize(nent);
+    out->gradient.resize(3 * (size_t)nent);
+    if (nent) {
+        CU(cudaMemcpyAsync(out->j.data(), w->ct_j[which].p + first, nent * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+        CU(cudaMemcpyAsync(out->model.data(), w->ct_model[which].p + first, nent * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+        CU(cudaMemcpyAsync(out->weight.data(), w->ct_w[which].p + first, nent * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+        CU(cudaMemcpyAsync(out->gradient.data(), w->ct_g[which].p + 3 * (size_t)first, 3 * (size_t)nent * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+    }
+    CU(cudaStreamSynchronize(w->st));
+    return SPH_OK;
+}
+
+sph_status call_host_force2(sph_world* w, uint32_t f, ForceRec& fr, std::vector<float>& hp, std::vector<float>& hv, std::vector<float>& hd,
+                            std::vector<float>& ha) {
+    if (w->tile) return w->fail(SPH_ERR_INVALID, "host plugins with contacts need gather_backend 0");
+    if (w->slab.active && (fr.host_flags & SPH_HOST_FORCE_CONTACTS))
+        return w->fail(SPH_ERR_INVALID, "materialised contacts are not available in slab-decomposed worlds");
+    const FluidRec& fl = w->fluids[f];
+    sph_host_force_ctx ctx;
+    memset(&ctx, 0, sizeof ctx);
+    ctx.dt = w->dt;
+    ctx.inv_dt = w->inv_dt;
+    ctx.kernel_radius = w->h;
+    ctx.particle_radius = w->desc.particle_radius;
+    ctx.fluid = make_handle(f, fl.gen);
+    ctx.fluid_index = f;
+    ctx.density0 = fl.density0;
+    ctx.n = fl.n;
+    ctx.positions_xyz = hp.data();
+    ctx.velocities_xyz = hv.data();
+    ctx.densities = hd.data();
+    ctx.accelerations_xyz = ha.data();
+    std::vector<float> vol;
+    if (!w->slab.active && w->h_vol.size() >= fl.offset + fl.n) ctx.volumes = w->h_vol.data() + fl.offset;
+    HostContacts ff, fb;
+    if (fr.host_flags & SPH_HOST_FORCE_CONTACTS) {
+        TRY(materialise_contacts(w, f, 0, &ff));
+        TRY(materialise_contacts(w, f, 1, &fb));
+        ctx.ff_offsets = ff.offsets.data(); ctx.ff_j = ff.j.data(); ctx.ff_j_model = ff.model.data();
+        ctx.ff_weight = ff.weight.data(); ctx.ff_gradient_xyz = ff.gradient.data();
+        ctx.fb_offsets = fb.offsets.data(); ctx.fb_j = fb.j.data(); ctx.fb_j_model = fb.model.data();
+        ctx.fb_weight = fb.weight.data(); ctx.fb_gradient_xyz = fb.gradient.data();
+    }
+    std::vector<sph_boundary_view> views;
+    std::vector<float> bvol;
+    if (fr.host_flags & SPH_HOST_FORCE_BOUNDARIES) {
+        bvol.resize(w->B);
+        if (w->B) {
+            const int bc = w->bcur;
+            CU(w->o_c.ensure(3 * std::max(w->N, w->B)));
+            LAUNCH(k_export_w, w->B, 256, (uint32_t)w->B, w->borig[bc].p, w->bpos[bc].p, w->o_c.p);
+            CU(cudaMemcpyAsync(bvol.data(), w->o_c.p, w->B * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+            CU(cudaStreamSynchronize(w->st));
+        }
+        views.resize(w->bounds.size());
+        for (size_t b = 0; b < w->bounds.size(); ++b) {
+            const BoundaryRec& br = w->bounds[b];
+            views[b].n = br.alive ? br.n : 0;
+            views[b].positions_xyz = w->hb_pos.data() + 3 * br.offset;
+            views[b].velocities_xyz = w->hb_vel.data() + 3 * br.offset;
+            views[b].volumes = bvol.data() + br.offset;
+        }
+        ctx.n_boundaries = views.size();
+        ctx.boundaries = views.data();
+    }
+    fr.host_fn2(fr.host_user, &ctx);
+    return SPH_OK;
 }
 
 // predict_advection dfsph_solver.rs:580-603: every fluid's forces in push order
@@ -1254,7 +1416,9 @@ sph_status phase_forces(sph_world* w) {
                     CU(cudaMemcpyAsync(ha.data(), w->o_c.p + 3 * fl.offset, 3 * Nf * sizeof(float), cudaMemcpyDeviceToHost, w->st));
                     CU(cudaMemcpyAsync(hd.data(), w->o_mass.p + fl.offset, Nf * sizeof(float), cudaMemcpyDeviceToHost, w->st));
                     CU(cudaStreamSynchronize(w->st));
-                    fr.host_fn(fr.host_user, w->dt, w->inv_dt, w->h, Nf, hp.data(), hv.data(), hd.data(), ha.data());
+                    if (fr.host_fn2) TRY(call_host_force2(w, (uint32_t)f, fr, hp, hv, hd, ha));
+                    else fr.host_fn(fr.host_user, w->dt, w->inv_dt, w->h, Nf, hp.data(), hv.data(), hd.data(), ha.data());
+                    TRY(enter(w));  // the callback may have used another world of this process
                     CU(cudaMemcpyAsync(w->o_c.p + 3 * fl.offset, ha.data(), 3 * Nf * sizeof(float), cudaMemcpyHostToDevice, w->st));
                     LAUNCH(k_import_acc, N, 256, (uint32_t)N, w->orig[c].p + ob, w->o_c.p, (uint32_t)fl.offset, (uint32_t)(fl.offset + Nf), w->acc.p + ob);
                     CU(cudaStreamSynchronize(w->st));  // host vectors go out of scope
@@ -1388,8 +1552,9 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     TRY(phase_forces(w));
     CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
     timestep_advance(w, dt_total);  // :702
+    const bool r8 = w->use_rec8 && w->unimass && !w->slab.active;
     LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p, w->unimass ? w->pvx4.p : nullptr,
-           w->unimass ? w->vyz2.p : nullptr);
+           w->unimass ? w->vyz2.p : nullptr, w->pos[c].p, r8 ? w->rec8.p : nullptr, w->dens.p);
     TRY(refresh_vstar(w));
     CU(cudaEventRecord(w->ev[EV_INTEG], w->st));
     // pressure_solve :432-464
@@ -1428,7 +1593,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     return SPH_OK;
 }
 
-sph_status world_step(sph_world* w, float dt, const float g[3]) {
+sph_status world_step(sph_world* w, float dt, const float g[3], const sph_coupling_manager* coupling = nullptr) {
     TRY(enter(w));
     w->launches = 0;
     w->stats_exchanges = 0;
@@ -1456,6 +1621,25 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
     TRY(phase_grid(w));
     w->grid_ready = true;
     w->ever_stepped = true;
+    if (coupling && coupling->update_boundaries) {
+        // CouplingManager::update_boundaries runs after the FLUIDS of this substep are in the grid and before the boundaries
+        // are (liquid_world.rs:86-103): queries issued by the callback see the fluid particles only.  The callback may rewrite
+        // boundaries (count included) and fluid positions / velocities; the grid is then rebuilt from the edited state
+        // (the reference keeps edited particles in their stale cells; re-binning them is the only deviation).
+        CU(cudaStreamSynchronize(w->st));
+        w->in_coupling = true;
+        w->lists_valid = true;  // sentinel: a fluid write in the callback clears it
+        coupling->update_boundaries(coupling->user, w, w->dt, w->inv_dt, w->h, w->desc.particle_radius);
+        w->in_coupling = false;
+        TRY(enter(w));
+        if (w->staged) return w->fail(SPH_ERR_INVALID, "update_boundaries must not add / remove fluids or particles");
+        if (w->b_dirty || !w->lists_valid) {
+            TRY(upload_boundaries(w));
+            w->stats.n_boundary_particles = w->B;
+            TRY(phase_grid(w));
+        }
+        w->lists_valid = false;
+    }
     CU(cudaEventRecord(w->ev[EV_GRID], w->st));
     // evaluate_kernels + compute_densities (liquid_world.rs:123-134) + compute_alphas (dfsph_solver.rs:679-684), enqueued
     // speculatively by the neighbour phase (EV_NBR is recorded there, between the two)
@@ -1521,6 +1705,7 @@ sph_status world_step(sph_world* w, float dt, const float g[3]) {
         w->stats.pressure_update_ms = acc[SP_PUPD];
     }
     if (flag) return w->fail(SPH_ERR_ZERO_DENSITY, "zero density (reference asserts dfsph_solver.rs:92,145,662)");
+    if (coupling && coupling->transmit_forces) coupling->transmit_forces(coupling->user, w, w->dt, w->inv_dt);  // liquid_world.rs:146
     return SPH_OK;
 }
 
@@ -1560,7 +1745,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     *out = nullptr;
     if (!(desc->particle_radius > 0.f) || !(desc->smoothing_factor > 0.f)) return SPH_ERR_INVALID;
     if (desc->solver != SPH_SOLVER_DFSPH && desc->solver != SPH_SOLVER_IISPH) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || desc->device < 0 || desc->device >= ndev) return SPH_ERR_CUDA;
     if (cudaSetDevice(desc->device) != cudaSuccess) return SPH_ERR_CUDA;
@@ -1570,6 +1755,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     w->tile = desc->gather_backend == 1 && desc->solver == SPH_SOLVER_DFSPH;  // the tile backend covers the DFSPH passes only
     if (const char* t = getenv("SALVA_B200_DEVICE_LOOPS")) w->device_loops = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_GCACHE")) w->use_gcache = atoi(t);
+    if (const char* t = getenv("SALVA_B200_REC8")) w->use_rec8 = atoi(t);
     if (const char* t = getenv("SALVA_B200_FUSE_DIV")) w->fuse_div = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_FUSE_XSPH")) w->fuse_xsph = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_UNI_EVAL")) w->uni_eval_mode = atoi(t);
@@ -1598,7 +1784,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
 
 void sph_world_destroy(sph_world* w) {
     if (!w) return;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     cudaSetDevice(w->desc.device);
     if (w->st) cudaStreamSynchronize(w->st);
     for (int k = 0; k < 2; ++k) {
@@ -1621,7 +1807,7 @@ void sph_world_destroy(sph_world* w) {
         for (auto& fr : f.forces) elasticity_release(fr);
     for (cudaTextureObject_t t : {w->tex_pvx, w->tex_vyz, w->tex_pk})
         if (t) cudaDestroyTextureObject(t);
-    w->pvx4.release(); w->pk4.release(); w->vyz2.release();
+    w->pvx4.release(); w->pk4.release(); w->vyz2.release(); w->rec8.release();
     if (w->tex_vs) cudaDestroyTextureObject(w->tex_vs);
     if (w->tex_kappa) cudaDestroyTextureObject(w->tex_kappa);
     for (auto& s : w->spans) {
@@ -1644,12 +1830,16 @@ void sph_world_destroy(sph_world* w) {
 sph_status sph_fluid_add(sph_world* w, const float* pos, const float* vel, const float* volumes, size_t n, float density0, uint32_t memberships,
                          uint32_t filter, uint32_t* handle) {
     if (!w) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     if (n && !pos) return w->fail(SPH_ERR_INVALID, "sph_fluid_add: null positions");
-    if (w->fluids.size() >= (size_t)MAX_FLUIDS) return w->fail(SPH_ERR_INVALID, "too many fluids (max %d)", MAX_FLUIDS);
+    size_t slot = w->fluids.size();
+    for (size_t k = 0; k < w->fluids.size(); ++k)
+        if (!w->fluids[k].alive) { slot = k; break; }
+    if (slot >= (size_t)MAX_FLUIDS) return w->fail(SPH_ERR_INVALID, "too many fluids (max %d)", MAX_FLUIDS);
     TRY(enter(w));
     TRY(stage_down(w));
     FluidRec f;
+    if (slot < w->fluids.size()) f.gen = w->fluids[slot].gen + 1;
     f.n = n;
     f.density0 = density0;
     f.memberships = memberships;
@@ -1657,25 +1847,35 @@ sph_status sph_fluid_add(sph_world* w, const float* pos, const float* vel, const
     f.pending_delete.assign(n, 0);
     float r = w->desc.particle_radius;
     float pv = r * r * r * (float)(8.0 * 0.8);  // fluid.rs:110-120
-    w->h_pos.insert(w->h_pos.end(), pos, pos + 3 * n);
-    if (vel) w->h_vel.insert(w->h_vel.end(), vel, vel + 3 * n);
-    else w->h_vel.insert(w->h_vel.end(), 3 * n, 0.f);
-    w->h_vc.insert(w->h_vc.end(), 3 * n, 0.f);
-    if (volumes) w->h_vol.insert(w->h_vol.end(), volumes, volumes + n);
-    else w->h_vol.insert(w->h_vol.end(), n, pv);
-    w->h_press.insert(w->h_press.end(), n, 0.f);
-    w->h_gid.resize(w->h_vol.size() - n);
-    for (size_t i = 0; i < n; ++i) w->h_gid.push_back((uint32_t)i);
-    w->fluids.push_back(f);
+    // the host arrays are ordered by slot: a reused slot's (empty) range sits at its offset
+    if (slot == w->fluids.size()) w->fluids.push_back(FluidRec());
+    w->fluids[slot].n = 0;
     recompute_offsets(w);
-    if (handle) *handle = (uint32_t)w->fluids.size() - 1;
+    const size_t at = w->fluids[slot].offset;
+    w->h_press.resize(w->h_vol.size(), 0.f);
+    w->h_gid.resize(w->h_vol.size());
+    w->h_pos.insert(w->h_pos.begin() + 3 * at, pos, pos + 3 * n);
+    if (vel) w->h_vel.insert(w->h_vel.begin() + 3 * at, vel, vel + 3 * n);
+    else w->h_vel.insert(w->h_vel.begin() + 3 * at, 3 * n, 0.f);
+    w->h_vc.insert(w->h_vc.begin() + 3 * at, 3 * n, 0.f);
+    if (volumes) w->h_vol.insert(w->h_vol.begin() + at, volumes, volumes + n);
+    else w->h_vol.insert(w->h_vol.begin() + at, n, pv);
+    w->h_press.insert(w->h_press.begin() + at, n, 0.f);
+    {
+        std::vector<uint32_t> ids(n);
+        for (size_t i = 0; i < n; ++i) ids[i] = (uint32_t)i;
+        w->h_gid.insert(w->h_gid.begin() + at, ids.begin(), ids.end());
+    }
+    w->fluids[slot] = f;
+    recompute_offsets(w);
+    if (handle) *handle = make_handle(slot, f.gen);
     return SPH_OK;
 }
 
-sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid, const sph_force_desc* force) {
+sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid_h, const sph_force_desc* force) {
     if (!w || !force) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     if (force->kind < 0 || force->kind > SPH_FORCE_DFSPH_VISCOSITY) return w->fail(SPH_ERR_INVALID, "unknown force kind %d", force->kind);
     if (force->kind == SPH_FORCE_WCSPH_TENSION && force->p[1] != 0.f)
         return w->fail(SPH_ERR_INVALID,
@@ -1689,10 +1889,10 @@ sph_status sph_fluid_push_force(sph_world* w, uint32_t fluid, const sph_force_de
     return SPH_OK;
 }
 
-sph_status sph_fluid_push_host_force(sph_world* w, uint32_t fluid, sph_host_force_fn fn, void* user) {
+sph_status sph_fluid_push_host_force(sph_world* w, uint32_t fluid_h, sph_host_force_fn fn, void* user) {
     if (!w || !fn) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     ForceRec fr;
     memset(&fr.d, 0, sizeof fr.d);
     fr.d.kind = FORCE_HOST_CALLBACK;
@@ -1703,10 +1903,10 @@ sph_status sph_fluid_push_host_force(sph_world* w, uint32_t fluid, sph_host_forc
 }
 
 // Fluid::add_particles fluid.rs:126-150 — appended at the end of the fluid's index range.
-sph_status sph_fluid_append(sph_world* w, uint32_t fluid, const float* pos, const float* vel, size_t n) {
+sph_status sph_fluid_append(sph_world* w, uint32_t fluid_h, const float* pos, const float* vel, size_t n) {
     if (!w) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     if (n == 0) return SPH_OK;
     if (!pos) return w->fail(SPH_ERR_INVALID, "sph_fluid_append: null positions");
     TRY(enter(w));
@@ -1734,10 +1934,10 @@ sph_status sph_fluid_append(sph_world* w, uint32_t fluid, const float* pos, cons
     return SPH_OK;
 }
 
-sph_status sph_fluid_delete(sph_world* w, uint32_t fluid, const uint8_t* mask, size_t n) {
+sph_status sph_fluid_delete(sph_world* w, uint32_t fluid_h, const uint8_t* mask, size_t n) {
     if (!w || !mask) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     FluidRec& f = w->fluids[fluid];
     if (n != f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_delete: mask length %zu != particle count %zu", n, f.n);
     for (size_t i = 0; i < n; ++i)
@@ -1748,18 +1948,18 @@ sph_status sph_fluid_delete(sph_world* w, uint32_t fluid, const uint8_t* mask, s
     return SPH_OK;
 }
 
-sph_status sph_fluid_count(sph_world* w, uint32_t fluid, size_t* n) {
+sph_status sph_fluid_count(sph_world* w, uint32_t fluid_h, size_t* n) {
     if (!w || !n) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     *n = w->fluids[fluid].n;
     return SPH_OK;
 }
 
-sph_status sph_fluid_write(sph_world* w, uint32_t fluid, const float* pos, const float* vel, size_t n) {
+sph_status sph_fluid_write(sph_world* w, uint32_t fluid_h, const float* pos, const float* vel, size_t n) {
     if (!w) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     FluidRec& f = w->fluids[fluid];
     if (n != f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_write: length %zu != particle count %zu", n, f.n);
     if (n == 0 || (!pos && !vel)) return SPH_OK;
@@ -1786,10 +1986,10 @@ sph_status sph_fluid_write(sph_world* w, uint32_t fluid, const float* pos, const
     return SPH_OK;
 }
 
-sph_status sph_fluid_read(sph_world* w, uint32_t fluid, float* pos, float* vel, size_t cap, size_t* n_out) {
+sph_status sph_fluid_read(sph_world* w, uint32_t fluid_h, float* pos, float* vel, size_t cap, size_t* n_out) {
     if (!w) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     FluidRec& f = w->fluids[fluid];
     if (n_out) *n_out = f.n;
     if (cap < f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_read: capacity %zu < particle count %zu", cap, f.n);
@@ -1819,28 +2019,36 @@ sph_status sph_fluid_read(sph_world* w, uint32_t fluid, float* pos, float* vel, 
 sph_status sph_boundary_add(sph_world* w, const float* pos, const float* vel, size_t n, uint32_t memberships, uint32_t filter, int want_forces,
                             uint32_t* handle) {
     if (!w) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     if (n && !pos) return w->fail(SPH_ERR_INVALID, "sph_boundary_add: null positions");
-    if (w->bounds.size() >= (size_t)MAX_BOUNDARIES) return w->fail(SPH_ERR_INVALID, "too many boundaries (max %d)", MAX_BOUNDARIES);
+    size_t slot = w->bounds.size();
+    for (size_t k = 0; k < w->bounds.size(); ++k)
+        if (!w->bounds[k].alive) { slot = k; break; }
+    if (slot >= (size_t)MAX_BOUNDARIES) return w->fail(SPH_ERR_INVALID, "too many boundaries (max %d)", MAX_BOUNDARIES);
     BoundaryRec b;
+    if (slot < w->bounds.size()) b.gen = w->bounds[slot].gen + 1;
     b.n = n;
     b.memberships = memberships;
     b.filter = filter;
     b.want_forces = want_forces != 0;
-    w->hb_pos.insert(w->hb_pos.end(), pos, pos + 3 * n);
-    if (vel) w->hb_vel.insert(w->hb_vel.end(), vel, vel + 3 * n);
-    else w->hb_vel.insert(w->hb_vel.end(), 3 * n, 0.f);
-    w->bounds.push_back(b);
+    if (slot == w->bounds.size()) w->bounds.push_back(BoundaryRec());
+    w->bounds[slot].n = 0;
+    recompute_offsets(w);
+    const size_t at = w->bounds[slot].offset;
+    w->hb_pos.insert(w->hb_pos.begin() + 3 * at, pos, pos + 3 * n);
+    if (vel) w->hb_vel.insert(w->hb_vel.begin() + 3 * at, vel, vel + 3 * n);
+    else w->hb_vel.insert(w->hb_vel.begin() + 3 * at, 3 * n, 0.f);
+    w->bounds[slot] = b;
     recompute_offsets(w);
     w->b_dirty = true;
-    if (handle) *handle = (uint32_t)w->bounds.size() - 1;
+    if (handle) *handle = make_handle(slot, b.gen);
     return SPH_OK;
 }
 
-sph_status sph_boundary_write(sph_world* w, uint32_t boundary, const float* pos, const float* vel, size_t n) {
+sph_status sph_boundary_write(sph_world* w, uint32_t boundary_h, const float* pos, const float* vel, size_t n) {
     if (!w) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (boundary >= w->bounds.size()) return w->fail(SPH_ERR_INVALID, "bad boundary handle %u", boundary);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    BOUNDARY_OR_FAIL(boundary, boundary_h)
     BoundaryRec& b = w->bounds[boundary];
     if (n != b.n) return w->fail(SPH_ERR_INVALID, "sph_boundary_write: length %zu != particle count %zu", n, b.n);
     if (pos) memcpy(w->hb_pos.data() + 3 * b.offset, pos, 3 * n * sizeof(float));
@@ -1849,8 +2057,8 @@ sph_status sph_boundary_write(sph_world* w, uint32_t boundary, const float* pos,
     return SPH_OK;
 }
 
-static sph_status boundary_export(sph_world* w, uint32_t boundary, float* out, size_t cap, bool forces) {
-    if (boundary >= w->bounds.size()) return w->fail(SPH_ERR_INVALID, "bad boundary handle %u", boundary);
+static sph_status boundary_export(sph_world* w, uint32_t boundary_h, float* out, size_t cap, bool forces) {
+    BOUNDARY_OR_FAIL(boundary, boundary_h)
     BoundaryRec& b = w->bounds[boundary];
     if (cap < b.n) return w->fail(SPH_ERR_INVALID, "capacity %zu < boundary particle count %zu", cap, b.n);
     if (b.n == 0) return SPH_OK;
@@ -1876,36 +2084,38 @@ static sph_status boundary_export(sph_world* w, uint32_t boundary, float* out, s
 
 sph_status sph_boundary_read_forces(sph_world* w, uint32_t boundary, float* f_xyz, size_t cap) {
     if (!w || !f_xyz) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     return boundary_export(w, boundary, f_xyz, cap, true);
 }
 sph_status sph_boundary_read_volumes(sph_world* w, uint32_t boundary, float* volumes, size_t cap) {
     if (!w || !volumes) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     return boundary_export(w, boundary, volumes, cap, false);
 }
 
-// LiquidWorld::particles_intersecting_aabb liquid_world.rs:211-243
-sph_status sph_world_particles_in_aabb(sph_world* w, const float mins[3], const float maxs[3], uint32_t* kinds, uint32_t* handles, uint32_t* indices,
-                                       size_t cap, size_t* n) {
-    if (!w || !mins || !maxs || !n || (cap && (!kinds || !handles || !indices))) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+// Shared runner of particles_intersecting_aabb / particles_intersecting_shape: the cells [key(mins), key(maxs)] of the last
+// step's grid (hgrid.rs:122-133), every particle in them tested by query_near().
+static sph_status run_query(sph_world* w, AabbQuery q, const float mins[3], const float maxs[3], uint32_t* kinds, uint32_t* handles, uint32_t* indices,
+                            size_t cap, size_t* n) {
     *n = 0;
     if (!w->grid_ready) {
         if (!w->ever_stepped) return SPH_OK;  // no step yet: the reference's grid is empty
-        return w->fail(SPH_ERR_INVALID, "particles_in_aabb: host edits are pending; the last step's cell grid no longer describes the particles");
+        return w->fail(SPH_ERR_INVALID, "particle query: host edits are pending; the last step's cell grid no longer describes the particles");
     }
-    if (w->b_dirty) return w->fail(SPH_ERR_INVALID, "particles_in_aabb: a boundary rewrite is pending; step first");
+    if (w->b_dirty && !w->in_coupling) return w->fail(SPH_ERR_INVALID, "particle query: a boundary rewrite is pending; step first");
+    for (int a = 0; a < 3; ++a)
+        if (std::isnan(mins[a]) || std::isnan(maxs[a])) return w->fail(SPH_ERR_INVALID, "particle query: NaN bounds");
     TRY(enter(w));
     const Consts& hc = w->hc;
     int lo[3], hi[3];
     const int go[3] = {hc.ox, hc.oy, hc.oz}, gn[3] = {hc.nx, hc.ny, hc.nz};
-    for (int a = 0; a < 3; ++a) {  // hgrid.rs:41-52 keys, clipped to the dense grid (cells outside hold nothing)
-        lo[a] = std::max((int)std::floor(mins[a] / w->h), go[a]);
-        hi[a] = std::min((int)std::floor(maxs[a] / w->h), go[a] + gn[a] - 1);
+    for (int a = 0; a < 3; ++a) {  // hgrid.rs:41-52 keys, clipped IN FLOAT to the dense grid (cells outside hold nothing; +-inf / FLT_MAX bounds are legal)
+        const float flo = std::floor(mins[a] / w->h), fhi = std::floor(maxs[a] / w->h);
+        if (fhi < (float)go[a] || flo > (float)(go[a] + gn[a] - 1)) return SPH_OK;
+        lo[a] = (int)std::fmax(flo, (float)go[a]);
+        hi[a] = (int)std::fmin(fhi, (float)(go[a] + gn[a] - 1));
         if (hi[a] < lo[a]) return SPH_OK;
     }
-    AabbQuery q;
     q.lx = lo[0]; q.ly = lo[1]; q.lz = lo[2];
     q.dx = hi[0] - lo[0] + 1; q.dy = hi[1] - lo[1] + 1; q.dz = hi[2] - lo[2] + 1;
     for (int a = 0; a < 3; ++a) { q.mins[a] = mins[a]; q.maxs[a] = maxs[a]; }
@@ -1914,13 +2124,14 @@ sph_status sph_world_particles_in_aabb(sph_world* w, const float mins[3], const 
     q.slot_hi = w->own_begin + (uint32_t)w->N;
     const size_t cells = (size_t)q.dx * q.dy * q.dz;
     int c = w->cur, bc = w->bcur;
+    const bool with_bounds = w->B && !w->in_coupling;  // during update_boundaries the grid holds fluids only (liquid_world.rs:90-103)
     CU(w->q_count.ensure(1));
     size_t qcap = std::max<size_t>(w->q_out.cap / 2, 4096);
     uint32_t found = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         CU(w->q_out.ensure(2 * qcap));
         CU(cudaMemsetAsync(w->q_count.p, 0, sizeof(uint32_t), w->st));
-        LAUNCH(k_aabb_query, cells, 128, q, w->N ? w->pos[c].p : nullptr, w->cstart.p, w->orig[c].p, w->B ? w->bpos[bc].p : nullptr, w->bstart.p,
+        LAUNCH(k_aabb_query, cells, 128, q, w->N ? w->pos[c].p : nullptr, w->cstart.p, w->orig[c].p, with_bounds ? w->bpos[bc].p : nullptr, w->bstart.p,
                w->borig[bc].p, w->q_out.p, (uint32_t)qcap, w->q_count.p);
         CU(cudaMemcpyAsync(&found, w->q_count.p, sizeof found, cudaMemcpyDeviceToHost, w->st));
         CU(cudaStreamSynchronize(w->st));
@@ -1938,10 +2149,10 @@ sph_status sph_world_particles_in_aabb(sph_world* w, const float mins[3], const 
         Hit h{kind, 0u, g};
         if (kind == 0) {
             for (size_t f = 0; f < w->fluids.size(); ++f)
-                if (g >= w->fluids[f].offset && g < w->fluids[f].offset + w->fluids[f].n) { h.handle = (uint32_t)f; h.index = g - (uint32_t)w->fluids[f].offset; }
+                if (g >= w->fluids[f].offset && g < w->fluids[f].offset + w->fluids[f].n) { h.handle = make_handle(f, w->fluids[f].gen); h.index = g - (uint32_t)w->fluids[f].offset; }
         } else {
             for (size_t b = 0; b < w->bounds.size(); ++b)
-                if (g >= w->bounds[b].offset && g < w->bounds[b].offset + w->bounds[b].n) { h.handle = (uint32_t)b; h.index = g - (uint32_t)w->bounds[b].offset; }
+                if (g >= w->bounds[b].offset && g < w->bounds[b].offset + w->bounds[b].n) { h.handle = make_handle(b, w->bounds[b].gen); h.index = g - (uint32_t)w->bounds[b].offset; }
         }
         hits[k] = h;
     }
@@ -1957,10 +2168,77 @@ sph_status sph_world_particles_in_aabb(sph_world* w, const float mins[3], const 
     return SPH_OK;
 }
 
+// LiquidWorld::particles_intersecting_aabb liquid_world.rs:211-243
+sph_status sph_world_particles_in_aabb(sph_world* w, const float mins[3], const float maxs[3], uint32_t* kinds, uint32_t* handles, uint32_t* indices,
+                                       size_t cap, size_t* n) {
+    if (!w || !mins || !maxs || !n || (cap && (!kinds || !handles || !indices))) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    AabbQuery q;
+    memset(&q, 0, sizeof q);
+    q.kind = 0;
+    return run_query(w, q, mins, maxs, kinds, handles, indices, cap, n);
+}
+
+// LiquidWorld::particles_intersecting_shape liquid_world.rs:246-281 for the shapes a C ABI can name: ball, cuboid, capsule
+// (parry's Shape trait objects cannot cross the boundary).  The cells come from the shape's AABB under `pos`, exactly
+// as `shape.compute_aabb(pos)` feeds cells_intersecting_aabb; the test is distance_to_point(pos, p, solid) <= particle_radius.
+sph_status sph_world_particles_in_shape(sph_world* w, const sph_shape* shape, const float translation[3], const float rotation_rowmajor[9], uint32_t* kinds,
+                                        uint32_t* handles, uint32_t* indices, size_t cap, size_t* n) {
+    if (!w || !shape || !translation || !n || (cap && (!kinds || !handles || !indices))) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    AabbQuery q;
+    memset(&q, 0, sizeof q);
+    static const float ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const float* R = rotation_rowmajor ? rotation_rowmajor : ident;
+    for (int k = 0; k < 9; ++k) q.rot[k] = R[k];
+    for (int a = 0; a < 3; ++a) q.t[a] = translation[a];
+    float ext[3];  // half extents of the posed shape's AABB
+    switch (shape->kind) {
+        case SPH_SHAPE_BALL:
+            if (!(shape->p[0] >= 0.f)) return w->fail(SPH_ERR_INVALID, "ball radius must be >= 0");
+            q.kind = 1;
+            q.sp[0] = shape->p[0];
+            ext[0] = ext[1] = ext[2] = shape->p[0];
+            break;
+        case SPH_SHAPE_CUBOID:
+            q.kind = 2;
+            for (int a = 0; a < 3; ++a) q.sp[a] = shape->p[a];
+            for (int a = 0; a < 3; ++a) ext[a] = std::fabs(R[3 * a]) * shape->p[0] + std::fabs(R[3 * a + 1]) * shape->p[1] + std::fabs(R[3 * a + 2]) * shape->p[2];
+            break;
+        case SPH_SHAPE_CAPSULE:
+            q.kind = 3;
+            q.sp[0] = shape->p[0];
+            q.sp[1] = shape->p[1];
+            for (int a = 0; a < 3; ++a) ext[a] = std::fabs(R[3 * a + 1]) * shape->p[0] + shape->p[1];  // segment along local y, swept by the radius
+            break;
+        default:
+            return w->fail(SPH_ERR_INVALID, "unknown shape kind %d", shape->kind);
+    }
+    float mins[3], maxs[3];
+    for (int a = 0; a < 3; ++a) {
+        mins[a] = translation[a] - ext[a];
+        maxs[a] = translation[a] + ext[a];
+    }
+    return run_query(w, q, mins, maxs, kinds, handles, indices, cap, n);
+}
+
 sph_status sph_world_step(sph_world* w, float dt, const float gravity[3]) {
     if (!w || !gravity) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    if (w->in_coupling) return w->fail(SPH_ERR_INVALID, "sph_world_step called from inside a coupling callback");
     sph_status s = world_step(w, dt, gravity);
+    if (s != SPH_OK) cudaStreamSynchronize(w->st);
+    return s;
+}
+
+// LiquidWorld::step_with_coupling liquid_world.rs:67-158
+sph_status sph_world_step_with_coupling(sph_world* w, float dt, const float gravity[3], const sph_coupling_manager* coupling) {
+    if (!w || !gravity) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    if (w->in_coupling) return w->fail(SPH_ERR_INVALID, "sph_world_step_with_coupling called from inside a coupling callback");
+    if (coupling && w->slab.active) return w->fail(SPH_ERR_INVALID, "coupling callbacks are not supported in slab-decomposed worlds");
+    sph_status s = world_step(w, dt, gravity, coupling);
+    w->in_coupling = false;
     if (s != SPH_OK) cudaStreamSynchronize(w->st);
     return s;
 }
@@ -1981,10 +2259,10 @@ sph_status sph_world_stats(sph_world* w, sph_step_stats* out) {
 float sph_world_h(const sph_world* w) { return w ? w->h : 0.f; }
 float sph_world_particle_radius(const sph_world* w) { return w ? w->desc.particle_radius : 0.f; }
 
-sph_status sph_debug_read(sph_world* w, uint32_t fluid, int what, float* out, size_t cap) {
+sph_status sph_debug_read(sph_world* w, uint32_t fluid_h, int what, float* out, size_t cap) {
     if (!w || !out) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     FluidRec& f = w->fluids[fluid];
     bool vec = what == SPH_DBG_VELOCITY_CHANGE || what == SPH_DBG_ACCELERATION;
     size_t width = vec ? 3 : 1;
@@ -2026,7 +2304,7 @@ const char* sph_version(void) { return "salva_b200 0.1 (sm_100a)"; }
 
 sph_status sph_nccl_unique_id(char out[128]) {
     if (!out) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     std::string err;
     if (!nccl_load(&err)) return SPH_ERR_NCCL;
     nccl_uid id;
@@ -2061,7 +2339,7 @@ static sph_status slab_attach(sph_world* w, void* comm, bool own, int rank, int 
 
 sph_status sph_world_attach_nccl(sph_world* w, void* nccl_comm, int rank, int nranks) {
     if (!w || !nccl_comm) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     if (!nccl_load(&w->err)) return SPH_ERR_NCCL;
     TRY(enter(w));
     return slab_attach(w, nccl_comm, false, rank, nranks);
@@ -2069,7 +2347,7 @@ sph_status sph_world_attach_nccl(sph_world* w, void* nccl_comm, int rank, int nr
 
 sph_status sph_world_create_nccl(sph_world* w, const char unique_id[128], int rank, int nranks) {
     if (!w || !unique_id) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     if (!nccl_load(&w->err)) return SPH_ERR_NCCL;
     TRY(enter(w));
     nccl_uid id;
@@ -2081,17 +2359,17 @@ sph_status sph_world_create_nccl(sph_world* w, const char unique_id[128], int ra
 
 sph_status sph_world_set_slab(sph_world* w, int32_t cell_lo, int32_t cell_hi) {
     if (!w) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
     if ((long long)cell_hi - (long long)cell_lo < 2) return w->fail(SPH_ERR_INVALID, "a slab must be at least 2 cell columns wide");
     w->slab.lo = cell_lo;
     w->slab.hi = cell_hi;
     return SPH_OK;
 }
 
-sph_status sph_fluid_set_ids(sph_world* w, uint32_t fluid, const uint32_t* ids, size_t n) {
+sph_status sph_fluid_set_ids(sph_world* w, uint32_t fluid_h, const uint32_t* ids, size_t n) {
     if (!w || !ids) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     FluidRec& f = w->fluids[fluid];
     if (n != f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_set_ids: length %zu != particle count %zu", n, f.n);
     TRY(enter(w));
@@ -2101,10 +2379,10 @@ sph_status sph_fluid_set_ids(sph_world* w, uint32_t fluid, const uint32_t* ids, 
     return SPH_OK;
 }
 
-sph_status sph_fluid_read_ids(sph_world* w, uint32_t fluid, uint32_t* ids, size_t cap) {
+sph_status sph_fluid_read_ids(sph_world* w, uint32_t fluid_h, uint32_t* ids, size_t cap) {
     if (!w || !ids) return SPH_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (fluid >= w->fluids.size()) return w->fail(SPH_ERR_INVALID, "bad fluid handle %u", fluid);
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
     FluidRec& f = w->fluids[fluid];
     if (cap < f.n) return w->fail(SPH_ERR_INVALID, "sph_fluid_read_ids: capacity %zu < particle count %zu", cap, f.n);
     if (f.n == 0) return SPH_OK;
@@ -2119,6 +2397,309 @@ sph_status sph_fluid_read_ids(sph_world* w, uint32_t fluid, uint32_t* ids, size_
     LAUNCH(k_export_u32, N, 256, (uint32_t)N, w->orig[c].p + w->own_begin, w->gid[c].p + w->own_begin, reinterpret_cast<uint32_t*>(w->o_c.p));
     CU(cudaMemcpyAsync(ids, reinterpret_cast<uint32_t*>(w->o_c.p) + f.offset, f.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
     CU(cudaStreamSynchronize(w->st));
+    return SPH_OK;
+}
+
+
+// fluid.nonpressure_forces.push(Box<dyn NonPressureForce>) with the FULL solve() argument list (nonpressure_force.rs:15-27):
+// timestep, kernel radius, fluid-fluid and fluid-boundary contacts, the fluid, the boundaries, the densities.
+sph_status sph_fluid_push_host_force2(sph_world* w, uint32_t fluid_h, sph_host_force_fn2 fn, void* user, uint32_t flags) {
+    if (!w || !fn) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
+    ForceRec fr;
+    memset(&fr.d, 0, sizeof fr.d);
+    fr.d.kind = FORCE_HOST_CALLBACK;
+    fr.host_fn2 = fn;
+    fr.host_flags = flags;
+    fr.host_user = user;
+    w->fluids[fluid].forces.push_back(fr);
+    return SPH_OK;
+}
+
+// LiquidWorld::remove_fluid liquid_world.rs:171-173.  The handle dies; other handles stay valid (arena semantics).
+sph_status sph_fluid_remove(sph_world* w, uint32_t fluid_h) {
+    if (!w) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
+    if (w->in_coupling) return w->fail(SPH_ERR_INVALID, "fluids cannot be removed from inside a coupling callback");
+    if (w->slab.active) return w->fail(SPH_ERR_INVALID, "sph_fluid_remove is not supported in slab-decomposed worlds");
+    TRY(enter(w));
+    TRY(stage_down(w));
+    FluidRec& f = w->fluids[fluid];
+    const size_t at = f.offset, n = f.n;
+    w->h_press.resize(w->h_vol.size(), 0.f);
+    w->h_gid.resize(w->h_vol.size());
+    w->h_pos.erase(w->h_pos.begin() + 3 * at, w->h_pos.begin() + 3 * (at + n));
+    w->h_vel.erase(w->h_vel.begin() + 3 * at, w->h_vel.begin() + 3 * (at + n));
+    w->h_vc.erase(w->h_vc.begin() + 3 * at, w->h_vc.begin() + 3 * (at + n));
+    w->h_vol.erase(w->h_vol.begin() + at, w->h_vol.begin() + at + n);
+    w->h_press.erase(w->h_press.begin() + at, w->h_press.begin() + at + n);
+    w->h_gid.erase(w->h_gid.begin() + at, w->h_gid.begin() + at + n);
+    for (auto& fr : f.forces) elasticity_release(fr);
+    f.forces.clear();
+    f.pending_delete.clear();
+    f.n_pending = 0;
+    f.n = 0;
+    f.alive = false;
+    recompute_offsets(w);
+    return SPH_OK;
+}
+
+// LiquidWorld::remove_boundary liquid_world.rs:176-178
+sph_status sph_boundary_remove(sph_world* w, uint32_t boundary_h) {
+    if (!w) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    BOUNDARY_OR_FAIL(boundary, boundary_h)
+    BoundaryRec& b = w->bounds[boundary];
+    w->hb_pos.erase(w->hb_pos.begin() + 3 * b.offset, w->hb_pos.begin() + 3 * (b.offset + b.n));
+    w->hb_vel.erase(w->hb_vel.begin() + 3 * b.offset, w->hb_vel.begin() + 3 * (b.offset + b.n));
+    b.n = 0;
+    b.alive = false;
+    b.want_forces = false;
+    recompute_offsets(w);
+    w->b_dirty = true;
+    return SPH_OK;
+}
+
+// A coupled collider re-samples its boundary every step (positions.clear(); push(..) — fluids_pipeline.rs:175-245): the
+// particle COUNT changes, which sph_boundary_write cannot express.
+sph_status sph_boundary_set_particles(sph_world* w, uint32_t boundary_h, const float* pos, const float* vel, size_t n) {
+    if (!w || (n && !pos)) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    BOUNDARY_OR_FAIL(boundary, boundary_h)
+    BoundaryRec& b = w->bounds[boundary];
+    w->hb_pos.erase(w->hb_pos.begin() + 3 * b.offset, w->hb_pos.begin() + 3 * (b.offset + b.n));
+    w->hb_vel.erase(w->hb_vel.begin() + 3 * b.offset, w->hb_vel.begin() + 3 * (b.offset + b.n));
+    w->hb_pos.insert(w->hb_pos.begin() + 3 * b.offset, pos, pos + 3 * n);
+    if (vel) w->hb_vel.insert(w->hb_vel.begin() + 3 * b.offset, vel, vel + 3 * n);
+    else w->hb_vel.insert(w->hb_vel.begin() + 3 * b.offset, 3 * n, 0.f);
+    b.n = n;
+    recompute_offsets(w);
+    w->b_dirty = true;
+    return SPH_OK;
+}
+
+sph_status sph_boundary_count(sph_world* w, uint32_t boundary_h, size_t* n) {
+    if (!w || !n) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    BOUNDARY_OR_FAIL(boundary, boundary_h)
+    *n = w->bounds[boundary].n;
+    return SPH_OK;
+}
+
+// Zero-copy read-back for renderers (testbed_plugin.rs:361-376 copies fluid.positions every frame): a DEVICE pointer to the
+// fluid's positions / velocities as packed xyz f32 in ORIGINAL index order.  Valid until the next call on this world.
+static sph_status fluid_map(sph_world* w, uint32_t fluid_h, bool velocities, const float** dev, size_t* n) {
+    FLUID_OR_FAIL(fluid, fluid_h)
+    TRY(enter(w));
+    if (w->staged) {  // nothing on the device yet: build the device state (what the next step would do first)
+        TRY(apply_pending_deletes(w));
+        TRY(stage_up(w));
+    }
+    const FluidRec& f = w->fluids[fluid];
+    DBuf<float>& buf = velocities ? w->map_vel : w->map_pos;
+    const size_t N = w->N;
+    CU(buf.ensure(3 * std::max<size_t>(N, 1)));
+    const int c = w->cur;
+    LAUNCH(k_export3, N, 256, (uint32_t)N, w->orig[c].p + w->own_begin, (velocities ? w->vel[c].p : w->pos[c].p) + w->own_begin, buf.p);
+    CU(cudaStreamSynchronize(w->st));
+    *dev = buf.p + 3 * f.offset;
+    *n = f.n;
+    return SPH_OK;
+}
+sph_status sph_fluid_map_positions(sph_world* w, uint32_t fluid_h, const float** dev_xyz, size_t* n) {
+    if (!w || !dev_xyz || !n) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    return fluid_map(w, fluid_h, false, dev_xyz, n);
+}
+sph_status sph_fluid_map_velocities(sph_world* w, uint32_t fluid_h, const float** dev_xyz, size_t* n) {
+    if (!w || !dev_xyz || !n) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    return fluid_map(w, fluid_h, true, dev_xyz, n);
+}
+
+// ---- snapshot / restore of the state the solver carries across steps ----------------------------------------------------
+// velocity_changes (dfsph_solver.rs:44, carried :704-706), the lagging dt / inv_dt (timestep_manager.rs:29-30), IISPH
+// warm-start pressures (iisph_solver.rs:673-677), Becker-2009 rest pose + rotations (becker2009_elasticity.rs:84-135),
+// particle ids, volumes, slab planes.  The blob restores into a world with the SAME fluids / forces / boundaries pushed in
+// the same order (scene description is the caller's); particle counts may differ from the world's current ones.
+namespace {
+constexpr uint32_t SNAP_MAGIC = 0x53485053u;  // "SPHS"
+struct SnapHeader {
+    uint32_t magic, version, solver, n_fluid_slots;
+    float dt, inv_dt;
+    int32_t slab_lo, slab_hi;
+    uint64_t n_particles, total_bytes;
+};
+struct SnapFluid {
+    uint64_t n;
+    uint32_t alive, n_forces;
+};
+struct SnapElastic {
+    uint64_t n;
+    uint32_t cap0, stride0;
+};
+struct Writer {
+    char* p;
+    size_t cap, off = 0;
+    void put(const void* src, size_t bytes) {
+        if (p && off + bytes <= cap) memcpy(p + off, src, bytes);
+        off += bytes;
+    }
+};
+// walks the blob layout; with a null buffer it only measures.  Device-resident pieces (elasticity) are downloaded here.
+sph_status snapshot_write(sph_world* w, Writer& wr) {
+    SnapHeader h;
+    memset(&h, 0, sizeof h);
+    h.magic = SNAP_MAGIC;
+    h.version = 1;
+    h.solver = (uint32_t)w->desc.solver;
+    h.n_fluid_slots = (uint32_t)w->fluids.size();
+    h.dt = w->dt;
+    h.inv_dt = w->inv_dt;
+    h.slab_lo = w->slab.lo;
+    h.slab_hi = w->slab.hi;
+    h.n_particles = w->N;
+    const size_t header_at = wr.off;
+    wr.put(&h, sizeof h);
+    for (auto& f : w->fluids) {
+        SnapFluid sf{f.n, f.alive ? 1u : 0u, (uint32_t)f.forces.size()};
+        wr.put(&sf, sizeof sf);
+    }
+    const size_t N = w->N;
+    wr.put(w->h_pos.data(), 3 * N * sizeof(float));
+    wr.put(w->h_vel.data(), 3 * N * sizeof(float));
+    wr.put(w->h_vc.data(), 3 * N * sizeof(float));
+    wr.put(w->h_vol.data(), N * sizeof(float));
+    wr.put(w->h_press.data(), N * sizeof(float));
+    wr.put(w->h_gid.data(), N * sizeof(uint32_t));
+    for (auto& f : w->fluids)
+        for (auto& fr : f.forces) {
+            SnapElastic se{0, 0, 0};
+            const ElasticityState* E = fr.elastic;
+            if (fr.d.kind == SPH_FORCE_BECKER2009_ELASTICITY && E && E->n) se = SnapElastic{E->n, E->cap0, E->stride0};
+            wr.put(&se, sizeof se);
+            if (!se.n) continue;
+            const size_t n = E->n, nl = (size_t)E->cap0 * E->stride0;
+            const size_t bytes = n * sizeof(float4) + n * sizeof(uint32_t) + nl * sizeof(uint32_t) + 9 * n * sizeof(float);
+            if (wr.p && wr.off + bytes <= wr.cap) {
+                char* dst = wr.p + wr.off;
+                CU(cudaMemcpyAsync(dst, E->pos0, n * sizeof(float4), cudaMemcpyDeviceToHost, w->st));
+                dst += n * sizeof(float4);
+                CU(cudaMemcpyAsync(dst, E->cnt0, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+                dst += n * sizeof(uint32_t);
+                CU(cudaMemcpyAsync(dst, E->nbr0, nl * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->st));
+                dst += nl * sizeof(uint32_t);
+                CU(cudaMemcpyAsync(dst, E->rot, 9 * n * sizeof(float), cudaMemcpyDeviceToHost, w->st));
+                CU(cudaStreamSynchronize(w->st));
+            }
+            wr.off += bytes;
+        }
+    if (wr.p && header_at + sizeof h <= wr.cap) {
+        h.total_bytes = wr.off - header_at;
+        memcpy(wr.p + header_at, &h, sizeof h);
+    }
+    return SPH_OK;
+}
+}  // namespace
+
+sph_status sph_world_snapshot_size(sph_world* w, size_t* bytes) {
+    if (!w || !bytes) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    if (w->in_coupling) return w->fail(SPH_ERR_INVALID, "snapshots cannot be taken from inside a coupling callback");
+    TRY(enter(w));
+    TRY(apply_pending_deletes(w));
+    TRY(stage_down(w));  // host vectors = truth in original order; the next step re-uploads (same results: the sorted order is canonical)
+    Writer wr{nullptr, 0};
+    TRY(snapshot_write(w, wr));
+    *bytes = wr.off;
+    return SPH_OK;
+}
+
+sph_status sph_world_snapshot_save(sph_world* w, void* buffer, size_t capacity, size_t* written) {
+    if (!w || !buffer) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    if (w->in_coupling) return w->fail(SPH_ERR_INVALID, "snapshots cannot be taken from inside a coupling callback");
+    TRY(enter(w));
+    TRY(apply_pending_deletes(w));
+    TRY(stage_down(w));
+    Writer wr{static_cast<char*>(buffer), capacity};
+    TRY(snapshot_write(w, wr));
+    if (written) *written = wr.off;
+    if (wr.off > capacity) return w->fail(SPH_ERR_INVALID, "snapshot needs %zu bytes, buffer holds %zu", wr.off, capacity);
+    return SPH_OK;
+}
+
+sph_status sph_world_snapshot_load(sph_world* w, const void* buffer, size_t length) {
+    if (!w || !buffer) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    if (w->in_coupling) return w->fail(SPH_ERR_INVALID, "snapshots cannot be loaded from inside a coupling callback");
+    const char* p = static_cast<const char*>(buffer);
+    size_t off = 0;
+    auto need = [&](size_t bytes) { return off + bytes <= length; };
+    SnapHeader h;
+    if (!need(sizeof h)) return w->fail(SPH_ERR_INVALID, "snapshot truncated");
+    memcpy(&h, p, sizeof h);
+    off += sizeof h;
+    if (h.magic != SNAP_MAGIC || h.version != 1) return w->fail(SPH_ERR_INVALID, "not a salva_b200 snapshot (magic %08x version %u)", h.magic, h.version);
+    if (h.total_bytes > length) return w->fail(SPH_ERR_INVALID, "snapshot truncated: %llu bytes expected, %zu given", (unsigned long long)h.total_bytes, length);
+    if (h.solver != (uint32_t)w->desc.solver || h.n_fluid_slots != w->fluids.size())
+        return w->fail(SPH_ERR_INVALID, "snapshot was taken from a differently configured world (solver %u, %u fluids)", h.solver, h.n_fluid_slots);
+    std::vector<SnapFluid> sf(h.n_fluid_slots);
+    if (!need(sf.size() * sizeof(SnapFluid))) return w->fail(SPH_ERR_INVALID, "snapshot truncated");
+    memcpy(sf.data(), p + off, sf.size() * sizeof(SnapFluid));
+    off += sf.size() * sizeof(SnapFluid);
+    uint64_t total = 0;
+    for (size_t k = 0; k < sf.size(); ++k) {
+        if ((sf[k].alive != 0) != w->fluids[k].alive || sf[k].n_forces != w->fluids[k].forces.size())
+            return w->fail(SPH_ERR_INVALID, "snapshot fluid %zu does not match the world (alive %u, %u forces)", k, sf[k].alive, sf[k].n_forces);
+        total += sf[k].n;
+    }
+    if (total != h.n_particles) return w->fail(SPH_ERR_INVALID, "snapshot particle counts are inconsistent");
+    const size_t N = (size_t)h.n_particles;
+    if (!need((3 * 3 + 2) * N * sizeof(float) + N * sizeof(uint32_t))) return w->fail(SPH_ERR_INVALID, "snapshot truncated");
+    TRY(enter(w));
+    TRY(stage_down(w));  // flips the world to "host vectors are the truth"; their content is replaced below
+    auto take = [&](void* dst, size_t bytes) {
+        memcpy(dst, p + off, bytes);
+        off += bytes;
+    };
+    w->h_pos.resize(3 * N); take(w->h_pos.data(), 3 * N * sizeof(float));
+    w->h_vel.resize(3 * N); take(w->h_vel.data(), 3 * N * sizeof(float));
+    w->h_vc.resize(3 * N);  take(w->h_vc.data(), 3 * N * sizeof(float));
+    w->h_vol.resize(N);     take(w->h_vol.data(), N * sizeof(float));
+    w->h_press.resize(N);   take(w->h_press.data(), N * sizeof(float));
+    w->h_gid.resize(N);     take(w->h_gid.data(), N * sizeof(uint32_t));
+    for (size_t k = 0; k < sf.size(); ++k) {
+        w->fluids[k].n = (size_t)sf[k].n;
+        w->fluids[k].pending_delete.assign((size_t)sf[k].n, 0);
+        w->fluids[k].n_pending = 0;
+    }
+    recompute_offsets(w);
+    w->dt = h.dt;
+    w->inv_dt = h.inv_dt;
+    if (w->slab.active) {
+        w->slab.lo = h.slab_lo;
+        w->slab.hi = h.slab_hi;
+        w->slab.global_valid = false;
+    }
+    w->Ntot = w->N;
+    w->own_begin = 0;
+    for (auto& f : w->fluids)
+        for (auto& fr : f.forces) {
+            SnapElastic se;
+            if (!need(sizeof se)) return w->fail(SPH_ERR_INVALID, "snapshot truncated");
+            take(&se, sizeof se);
+            elasticity_release(fr);
+            if (!se.n) continue;
+            const size_t n = (size_t)se.n, nl = (size_t)se.cap0 * se.stride0;
+            if (!need(n * sizeof(float4) + n * sizeof(uint32_t) + nl * sizeof(uint32_t) + 9 * n * sizeof(float))) return w->fail(SPH_ERR_INVALID, "snapshot truncated");
+            TRY(elasticity_restore(w, fr, n, se.cap0, se.stride0, p + off));
+            off += n * sizeof(float4) + n * sizeof(uint32_t) + nl * sizeof(uint32_t) + 9 * n * sizeof(float);
+        }
+    w->lists_valid = false;
+    w->grid_ready = false;
     return SPH_OK;
 }
 

@@ -34,6 +34,8 @@ struct Consts {
     float h, inv_h, h2;          // h2 = h*h rounded once (contacts.rs:285 `h * h`)
     float sigma;                 // 8 / (pi h^3)            cubic_spline_kernel.rs:18
     float dsigma;                // sigma / h               cubic_spline_kernel.rs:79
+    float dsigma6;               // 6 sigma / h
+    float g_t2;                  // gradient is zero unless |x_ij|^2 > g_t2 = max(eps^2, (1e-5 h)^2)  (kernel.rs:19 + cubic_spline_kernel.rs:64)
     int ox, oy, oz;              // grid origin in cell coordinates (one padding cell each side)
     int nx, ny, nz;
     int ntx, nty, ntz;           // tile grid (sph_tile.cuh): 2 x 2 cell columns x TILE_Z cells per tile
@@ -85,6 +87,17 @@ __device__ __forceinline__ float kernel_gfac(float d2, float r, float inv_r) {
     return zero ? 0.0f : C.dsigma * rhs * inv_r;
 }
 
+#ifndef SPH_FAST_PAIR
+#define SPH_FAST_PAIR 1
+#endif
+// MUFU.RSQ without the denormal-rescue sequence rsqrtf() compiles to (3 extra instructions per contact): operands
+// here are squared distances >= g_t2 ~ 1e-14 or exactly 0 (self contact: +inf, masked by the d2 > g_t2 select).
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct Pair {        // geometry of one (i, j) contact
     float dx, dy, dz;  // x_i - x_j
     float d2, r;
@@ -98,10 +111,38 @@ __device__ __forceinline__ Pair make_pair(const float4& pi, const float4& pj) {
     p.dy = pi.y - pj.y;
     p.dz = pi.z - pj.z;
     p.d2 = fmaf(p.dz, p.dz, fmaf(p.dy, p.dy, p.dx * p.dx));
+#if SPH_FAST_PAIR
+    // Lean evaluation (about half the instructions of the guarded one below): contacts come from lists built with
+    // d^2 <= h^2, so q <= 1 up to rounding (where (1 - q)^2 ~ 1e-14 anyway), and the two "zero gradient" guards of the
+    // reference (|x_ij|^2 > eps^2, q > 1e-5) collapse into one select on d2.  d2 == 0 gives inv_r = +inf and NaNs in
+    // r / q, all discarded by the selects (never multiplied).
+    const float inv_r = rsqrt_ftz(p.d2);
+    const bool nz = p.d2 > C.g_t2;
+    p.r = nz ? p.d2 * inv_r : 0.f;
+    const float q = p.r * C.inv_h;
+    const float t = 1.0f - q;
+    const bool inner = q <= 0.5f;
+    if (NEED_W) {
+        const float q2 = q * q;
+        const float a = fmaf(fmaf(q2, q, -q2), 6.0f, 1.0f);
+        const float b = (t * t) * (t * 2.0f);
+        p.w = C.sigma * (inner ? a : b);
+    } else {
+        p.w = 0.f;
+    }
+    if (NEED_G) {
+        const float a = fmaf(q, 3.0f, -2.0f) * q;
+        const float b = -t * t;
+        p.g = nz ? (C.dsigma6 * inv_r) * (inner ? a : b) : 0.f;
+    } else {
+        p.g = 0.f;
+    }
+#else
     float inv_r = rsqrtf(fmaxf(p.d2, 1.0e-30f));
     p.r = p.d2 * inv_r;
     p.w = NEED_W ? kernel_w(p.r) : 0.f;
     p.g = NEED_G ? kernel_gfac(p.d2, p.r, inv_r) : 0.f;
+#endif
     return p;
 }
 
@@ -213,17 +254,30 @@ __global__ void k_cell_scatter(uint32_t n, const uint32_t* __restrict__ cid, con
     perm[start[cid[i]] + rank[i]] = i;
 }
 
-// Deterministic mode: atomics hand out in-cell ranks in arbitrary order; sort each cell's slice of perm
-// ascending so the sorted order (and every f32 summation order downstream) is reproducible.
-__global__ void k_cell_sort(uint32_t ncell, const uint32_t* __restrict__ start, uint32_t* __restrict__ perm) {
+// Deterministic mode: atomics hand out in-cell ranks in arbitrary order; sort each cell's slice of perm so the sorted
+// order (and every f32 summation order downstream) is reproducible.  The in-cell order is CANONICAL — ascending
+// (fluid, particle id), a pure function of the particle set — so a world restored from a snapshot, a world whose state
+// went through the host, and the ranks of a slab decomposition (ghost columns!) all see the same order and produce
+// bit-identical sums.  key == nullptr (boundaries): ascending previous slot, i.e. insertion order.
+__device__ __forceinline__ unsigned long long sort_key(uint32_t src, const uint32_t* __restrict__ gid, const float4* __restrict__ vel) {
+    if (!gid) return src;
+    const uint32_t f = vel ? fid_of(vel[src]) : 0u;
+    return ((unsigned long long)f << 32) | gid[src];
+}
+__global__ void k_cell_sort(uint32_t ncell, const uint32_t* __restrict__ start, uint32_t* __restrict__ perm, const uint32_t* __restrict__ gid,
+                            const float4* __restrict__ vel) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
     uint32_t s = start[c], e = start[c + 1];
     for (uint32_t a = s + 1; a < e; ++a) {
-        uint32_t v = perm[a];
+        const uint32_t v = perm[a];
+        const unsigned long long kv = sort_key(v, gid, vel);
         uint32_t b = a;
-        while (b > s && perm[b - 1] > v) {
-            perm[b] = perm[b - 1];
+        while (b > s) {
+            const uint32_t u = perm[b - 1];
+            const unsigned long long ku = sort_key(u, gid, vel);
+            if (ku < kv || (ku == kv && u < v)) break;
+            perm[b] = u;
             --b;
         }
         perm[b] = v;
@@ -550,6 +604,19 @@ __global__ void k_loop_decide(LoopCtl* __restrict__ ctl, const float* __restrict
     }
 }
 
+struct __align__(32) Rec8 {
+    float x, y, z, vx, vy, vz, rho, pad;
+};
+__device__ __forceinline__ void ld_rec8(const Rec8* __restrict__ p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+__device__ __forceinline__ void st_rec8(Rec8* p, float x, float y, float z, float vx, float vy, float vz, float rho) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(vx), "f"(vy), "f"(vz), "f"(rho), "f"(0.f)
+                 : "memory");
+}
+
 // v* = vel + vc after the reorder (the divergence solve works on vel + vc carried over from the previous step, Appendix A.3.2)
 __global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __restrict__ vc, float4* __restrict__ vs, const float4* __restrict__ pos,
                              float4* __restrict__ pvx, float2* __restrict__ vyz) {
@@ -596,7 +663,8 @@ __global__ void k_set_gravity(const float4* __restrict__ vel, float4* __restrict
 
 // a18: integrate_and_clear_accelerations dfsph_solver.rs:505-518 (+ v* = vel + vc)
 __global__ void k_integrate_acc(const float4* __restrict__ vel, float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ acc, float dt,
-                                float4* __restrict__ dbg_acc, float4* __restrict__ pvx, float2* __restrict__ vyz) {
+                                float4* __restrict__ dbg_acc, float4* __restrict__ pvx, float2* __restrict__ vyz, const float4* __restrict__ pos,
+                                Rec8* __restrict__ rec, const float* __restrict__ dens) {
     SPH_OWNED_INDEX(i)
     float4 a = acc[i], c = vc[i], v = vel[i];
     if (dbg_acc) dbg_acc[i] = a;
@@ -604,7 +672,10 @@ __global__ void k_integrate_acc(const float4* __restrict__ vel, float4* __restri
     vc[i] = c;
     float sx = v.x + c.x, sy = v.y + c.y, sz = v.z + c.z;
     vs[i] = make_float4(sx, sy, sz, 0.f);
-    if (pvx) {
+    if (rec) {
+        const float4 p = pos[i];
+        st_rec8(rec + i, p.x, p.y, p.z, sx, sy, sz, dens[i]);
+    } else if (pvx) {
         pvx[i].w = sx;  // xyz already hold the position
         vyz[i] = make_float2(sy, sz);
     }
@@ -764,11 +835,11 @@ __global__ void k_slab_scatter(uint32_t n_slots, const uint32_t* __restrict__ fk
         keep_orig[d] = scan_o[orig[s]];
         if (fcl[s]) {
             uint32_t e = scl[s];
-            col_l.pos[e] = p; col_l.vel[e] = v; col_l.vc[e] = c;
+            col_l.pos[e] = p; col_l.vel[e] = v; col_l.vc[e] = c; col_l.gid[e] = gid[s];
         }
         if (fcr[s]) {
             uint32_t e = scr[s];
-            col_r.pos[e] = p; col_r.vel[e] = v; col_r.vc[e] = c;
+            col_r.pos[e] = p; col_r.vel[e] = v; col_r.vc[e] = c; col_r.gid[e] = gid[s];
         }
     } else if (fl[s]) {
         uint32_t d = sl[s];
@@ -806,12 +877,36 @@ struct AabbQuery {
     int lx, ly, lz, dx, dy, dz;  // first cell and extent (cells) of the box
     float mins[3], maxs[3], radius;
     uint32_t slot_lo, slot_hi;   // owned fluid slots (ghost copies of a slab world are skipped)
+    // particles_intersecting_shape (liquid_world.rs:246-281): kind 0 = the box itself (distance < radius, :224),
+    // 1 = ball, 2 = cuboid, 3 = capsule (segment along local y), each posed by the isometry (rot, t): point p is hit
+    // when shape.distance_to_point(pos, p, solid) <= radius (:263)
+    int kind;
+    float rot[9], t[3];          // world = rot * local + t (row-major rotation)
+    float sp[3];                 // ball: radius; cuboid: half extents; capsule: half height, radius
 };
-__device__ __forceinline__ bool aabb_near(const AabbQuery& q, const float4& p) {
-    float ex = fmaxf(fmaxf(q.mins[0] - p.x, p.x - q.maxs[0]), 0.f);
-    float ey = fmaxf(fmaxf(q.mins[1] - p.y, p.y - q.maxs[1]), 0.f);
-    float ez = fmaxf(fmaxf(q.mins[2] - p.z, p.z - q.maxs[2]), 0.f);
-    return __fsqrt_rn(dist2_exact(ex, ey, ez)) < q.radius;
+__device__ __forceinline__ bool query_near(const AabbQuery& q, const float4& p) {
+    if (q.kind == 0) {
+        float ex = fmaxf(fmaxf(q.mins[0] - p.x, p.x - q.maxs[0]), 0.f);
+        float ey = fmaxf(fmaxf(q.mins[1] - p.y, p.y - q.maxs[1]), 0.f);
+        float ez = fmaxf(fmaxf(q.mins[2] - p.z, p.z - q.maxs[2]), 0.f);
+        return __fsqrt_rn(dist2_exact(ex, ey, ez)) < q.radius;
+    }
+    // local point = rot^T (p - t)
+    const float wx = p.x - q.t[0], wy = p.y - q.t[1], wz = p.z - q.t[2];
+    const float lx = q.rot[0] * wx + q.rot[3] * wy + q.rot[6] * wz;
+    const float ly = q.rot[1] * wx + q.rot[4] * wy + q.rot[7] * wz;
+    const float lz = q.rot[2] * wx + q.rot[5] * wy + q.rot[8] * wz;
+    float d;
+    if (q.kind == 1) {
+        d = fmaxf(__fsqrt_rn(dist2_exact(lx, ly, lz)) - q.sp[0], 0.f);
+    } else if (q.kind == 2) {
+        float ex = fmaxf(fabsf(lx) - q.sp[0], 0.f), ey = fmaxf(fabsf(ly) - q.sp[1], 0.f), ez = fmaxf(fabsf(lz) - q.sp[2], 0.f);
+        d = __fsqrt_rn(dist2_exact(ex, ey, ez));
+    } else {
+        float cy = fminf(fmaxf(ly, -q.sp[0]), q.sp[0]);  // closest point of the segment
+        d = fmaxf(__fsqrt_rn(dist2_exact(lx, ly - cy, lz)) - q.sp[1], 0.f);
+    }
+    return d <= q.radius;
 }
 __global__ void k_aabb_query(AabbQuery q, const float4* __restrict__ pos, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ orig,
                              const float4* __restrict__ bpos, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ borig,
@@ -825,7 +920,7 @@ __global__ void k_aabb_query(AabbQuery q, const float4* __restrict__ pos, const 
     if (pos) {
         uint32_t s = max(cstart[c], q.slot_lo), e = min(cstart[c + 1], q.slot_hi);
         for (uint32_t j = s; j < e; ++j)
-            if (aabb_near(q, pos[j])) {
+            if (query_near(q, pos[j])) {
                 uint32_t k = atomicAdd(count, 1u);
                 if (k < cap) {
                     out[2 * (size_t)k] = 0u;
@@ -835,13 +930,51 @@ __global__ void k_aabb_query(AabbQuery q, const float4* __restrict__ pos, const 
     }
     if (bpos) {
         for (uint32_t j = bstart[c]; j < bstart[c + 1]; ++j)
-            if (aabb_near(q, bpos[j])) {
+            if (query_near(q, bpos[j])) {
                 uint32_t k = atomicAdd(count, 1u);
                 if (k < cap) {
                     out[2 * (size_t)k] = 1u;
                     out[2 * (size_t)k + 1] = borig[j];
                 }
             }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ParticlesContacts materialisation for host NonPressureForce plugins (nonpressure_force.rs:15-27 hands
+// `fluid_fluid_contacts` / `fluid_boundaries_contacts` to solve(); Contact = {i_model, j_model, i, j, weight, gradient},
+// contacts.rs:12-27).  CSR in ORIGINAL particle order; entries of a particle keep the list order (ascending sorted j).
+// ------------------------------------------------------------------------------------------------
+struct OffsetTable {
+    uint32_t off[MAX_FLUIDS > MAX_BOUNDARIES ? MAX_FLUIDS + 1 : MAX_BOUNDARIES + 1];
+};
+__global__ void k_contacts_count(uint32_t n, const uint32_t* __restrict__ orig, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t* __restrict__ out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) out[orig[s]] = min(cnt[s], cap);
+}
+// one thread per sorted slot: writes its particle's contacts at scan[orig[s]]..
+template <bool BOUNDARY>
+__global__ void k_contacts_fill(uint32_t n, const float4* __restrict__ pos, const float4* __restrict__ other_pos, const float4* __restrict__ other_vel,
+                                const uint32_t* __restrict__ orig, const uint32_t* __restrict__ other_orig, const uint32_t* __restrict__ nbr,
+                                const uint32_t* __restrict__ cnt, uint32_t cap, const uint32_t* __restrict__ scan, OffsetTable tab, uint32_t* __restrict__ out_j,
+                                uint32_t* __restrict__ out_model, float* __restrict__ out_w, float* __restrict__ out_g) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t i = s + C.i_begin;
+    const float4 pi = pos[i];
+    const uint32_t m = min(cnt[i], cap);
+    size_t base = scan[orig[i]];
+    for (uint32_t k = 0; k < m; ++k) {
+        const uint32_t j = BOUNDARY ? nbr[(size_t)k * C.stride + i] : nbr[((size_t)(k >> 2) * C.stride + i) * 4 + (k & 3)];
+        const float4 pj = other_pos[j];
+        const Pair p = make_pair<true, true>(pi, pj);
+        const uint32_t model = fid_of(other_vel[j]);
+        out_j[base + k] = other_orig[j] - tab.off[model];
+        out_model[base + k] = model;
+        out_w[base + k] = p.w;
+        out_g[3 * (base + k) + 0] = p.g * p.dx;
+        out_g[3 * (base + k) + 1] = p.g * p.dy;
+        out_g[3 * (base + k) + 2] = p.g * p.dz;
     }
 }
 

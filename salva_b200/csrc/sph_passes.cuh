@@ -527,6 +527,78 @@ k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, con
     reduce_error<false>(e, 0u, valid, partial, sm, ticket, errsum);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 256-bit gather records (sm_100 LDG.E.256): rec8[i] = (x, y, z, v*x, v*y, v*z, rho, unused), 32-byte aligned, so an
+// evaluation pays ONE gather instruction per contact instead of two (position record + velocity record).  The gather
+// passes are bound by L1TEX wavefronts (one per distinct 128-byte line a warp-wide gather touches, ~8 per instruction,
+// profiles/r1_*), not by bytes: halving the gather instructions per contact is what moves them.
+// ------------------------------------------------------------------------------------------------
+template <bool PREDICT>
+__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
+k_vel_divergence_r8(const Rec8* __restrict__ rec, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
+                    const float* __restrict__ alpha, float* __restrict__ out, float4* __restrict__ pk4, float* __restrict__ partial, float dt,
+                    int* __restrict__ err, uint32_t* __restrict__ ticket, float* __restrict__ errsum, Range rg) {
+    __shared__ float sm[32];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < rg.count;
+    i += rg.begin;
+    float e = 0.f;
+    if (valid) {
+        float4 a, b;
+        ld_rec8(rec + i, a, b);
+        const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
+        const float vix = a.w, viy = b.x, viz = b.y;
+        const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
+        float d = 0.f;
+        if (PREDICT || L.cnt_f[i] + L.cnt_b[i] >= 20u) {
+            const uint32_t n = min(L.cnt_f[i], C.cap_f);
+            const uint32_t nq = (n + 3u) >> 2;
+            const uint4* col = L.nbr_f + i;
+            uint4 J = nq ? ld_list(col) : make_uint4(i, i, i, i);
+            for (uint32_t q = 0; q < nq; ++q) {
+                uint4 Jn = J;
+                if (q + 1 < nq) Jn = ld_list(col + (size_t)(q + 1) * C.stride);
+                const uint32_t j[4] = {J.x, J.y, J.z, J.w};
+                float4 pj[4], wj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ld_rec8(rec + j[u], pj[u], wj[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {  // padded tail slots are self contacts: zero gradient
+                    Pair p = make_pair<false, true>(pi, pj[u]);
+                    float dv = (vix - pj[u].w) * p.dx + (viy - wj[u].x) * p.dy + (viz - wj[u].y) * p.dz;
+                    d = fmaf(dv * p.g, mass, d);
+                }
+                J = Jn;
+            }
+            for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+                float dv;
+                if (PREDICT) {
+                    float4 vj = __ldg(&bvel[j]);
+                    dv = (vix - vj.x) * p.dx + (viy - vj.y) * p.dy + (viz - vj.z) * p.dz;
+                } else {
+                    dv = vix * p.dx + viy * p.dy + viz * p.dz;
+                }
+                d = fmaf(dv * p.g, pj.w * rho0, d);
+            });
+        }
+        float kap;
+        if (PREDICT) {
+            float pd = fmaf(d, dt, dens[i]);
+            if (pd == 0.f) atomicOr(err, 1);
+            out[i] = pd;
+            kap = fmaxf((pd - rho0) * alpha[i], 0.f);
+            e = pd < rho0 ? 0.f : pd / rho0 - 1.0f;
+        } else {
+            d = fmaxf(d, 0.f);
+            out[i] = d;
+            kap = d * alpha[i];
+            e = d / rho0;
+        }
+        pk4[i] = make_float4(a.x, a.y, a.z, kap);
+    }
+    reduce_error<false>(e, 0u, valid, partial, sm, ticket, errsum);
+}
+
 // compute_divergences (a7) + the fluid term of XSPHViscosity::solve (a12, xsph_viscosity.rs:52-69) in ONE sweep.
 // XSPH is evaluated on `fluid.velocities` right after update_velocities folded vc into them (dfsph_solver.rs:688-697),
 // i.e. on exactly the v* the divergence loop's LAST evaluation gathers; so every stand-alone evaluation also accumulates
@@ -585,8 +657,8 @@ k_vel_divergence_xsph_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx
 template <bool BFORCE, bool PRESSURE, bool POS_TEX>
 __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_update_u(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
-               float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ pvx, float2* __restrict__ vyz, float* __restrict__ bforce,
-               float inv_dt, const int* __restrict__ gate, Range rg) {
+               float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ pvx, float2* __restrict__ vyz, Rec8* __restrict__ rec,
+               const float* __restrict__ dens, float* __restrict__ bforce, float inv_dt, const int* __restrict__ gate, Range rg) {
     if (gate && !*gate) return;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rg.count) return;
@@ -622,8 +694,12 @@ k_vel_update_u(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const fl
     vc[i] = c4;
     const float sx = v.x + c4.x, sy = v.y + c4.y, sz = v.z + c4.z;
     vs[i] = make_float4(sx, sy, sz, 0.f);
-    pvx[i] = make_float4(a.x, a.y, a.z, sx);
-    vyz[i] = make_float2(sy, sz);
+    if (rec) {
+        st_rec8(rec + i, a.x, a.y, a.z, sx, sy, sz, dens[i]);
+    } else {
+        pvx[i] = make_float4(a.x, a.y, a.z, sx);
+        vyz[i] = make_float2(sy, sz);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -5,8 +5,9 @@
 // The x-major sort keeps a whole yz-plane of cells contiguous, so after the sort the arrays are laid out as
 //     [ left ghosts | my left boundary column | interior | my right boundary column | right ghosts ]
 // and every per-iteration exchange (rho, kappa, v*, normals) is an ncclSend/ncclRecv of a contiguous array range
-// with NO pack kernel.  Sender and receiver agree on the order inside a column because both run the same stable
-// counting sort over the same particles in the same arrival order (deterministic mode is forced on).
+// with NO pack kernel.  Sender and receiver agree on the order inside a column because the in-cell order of the
+// counting sort is canonical (ascending particle id, k_cell_sort) and ghost particles travel WITH their ids
+// (deterministic mode is forced on).
 // Only the first exchange of a step (positions/velocities of the boundary columns, before the sort) and the
 // migration of particles that crossed a plane need a compaction.
 //
@@ -76,7 +77,8 @@ void slab_release(sph_world* w) {
     if (S.ev_done) cudaEventDestroy(S.ev_done);
     if (S.comm_st) cudaStreamDestroy(S.comm_st);
     S.comm_st = nullptr; S.ev_ready = nullptr; S.ev_done = nullptr;
-    S.d_cnt.release(); S.flag.release(); S.flag_o.release(); S.gid_l.release(); S.gid_r.release(); S.d_cnt64.release();
+    S.d_cnt.release(); S.flag.release(); S.flag_o.release(); S.gid_l.release(); S.gid_r.release(); S.gid_cl.release(); S.gid_cr.release();
+    S.d_cnt64.release();
     for (int a = 0; a < 3; ++a) {
         S.out_l[a].release();
         S.out_r[a].release();
@@ -193,6 +195,8 @@ sph_status slab_begin_step(sph_world* w) {
     }
     CU(S.gid_l.ensure(std::max<uint32_t>(nl, 1)));
     CU(S.gid_r.ensure(std::max<uint32_t>(nr, 1)));
+    CU(S.gid_cl.ensure(std::max<uint32_t>(ncl, 1)));
+    CU(S.gid_cr.ensure(std::max<uint32_t>(ncr, 1)));
     w->N = n_new;
     w->Ntot = (size_t)n_new + ghl + ghr;
     w->fluids[0].n = n_new;
@@ -204,7 +208,7 @@ sph_status slab_begin_step(sph_world* w) {
     const int d = c ^ 1;
     SlabOut keep{w->pos[d].p, w->vel[d].p, w->vc[d].p, w->gid[d].p};
     SlabOut ol{S.out_l[0].p, S.out_l[1].p, S.out_l[2].p, S.gid_l.p}, orr{S.out_r[0].p, S.out_r[1].p, S.out_r[2].p, S.gid_r.p};
-    SlabOut cl{S.col_l[0].p, S.col_l[1].p, S.col_l[2].p, nullptr}, cr{S.col_r[0].p, S.col_r[1].p, S.col_r[2].p, nullptr};
+    SlabOut cl{S.col_l[0].p, S.col_l[1].p, S.col_l[2].p, S.gid_cl.p}, cr{S.col_r[0].p, S.col_r[1].p, S.col_r[2].p, S.gid_cr.p};
     LAUNCH(k_slab_scatter, n_slots, 256, n_slots, f[0], f[1], f[2], f[3], f[4], sc[0], sc[1], sc[2], sc[3], sc[4], S.flag_o.p, w->pos[c].p, w->vel[c].p,
            w->vc[c].p, w->orig[c].p, w->gid[c].p, keep, w->orig[d].p, ol, orr, cl, cr);
     // ---- one data exchange: emigrants + boundary columns out, immigrants + ghost columns in --------------------------------
@@ -219,7 +223,9 @@ sph_status slab_begin_step(sph_world* w) {
             if (gcol_l) NC(g_nccl.Recv(dst4[a] + g0, (size_t)gcol_l * 16, NCCL_CHAR, L, S.comm, w->st));
         }
         if (nl) NC(g_nccl.Send(S.gid_l.p, (size_t)nl * 4, NCCL_CHAR, L, S.comm, w->st));
+        if (ncl) NC(g_nccl.Send(S.gid_cl.p, (size_t)ncl * 4, NCCL_CHAR, L, S.comm, w->st));
         if (im_l) NC(g_nccl.Recv(w->gid[d].p + nk, (size_t)im_l * 4, NCCL_CHAR, L, S.comm, w->st));
+        if (gcol_l) NC(g_nccl.Recv(w->gid[d].p + g0, (size_t)gcol_l * 4, NCCL_CHAR, L, S.comm, w->st));
     }
     if (R >= 0) {
         for (int a = 0; a < 3; ++a) {
@@ -229,7 +235,9 @@ sph_status slab_begin_step(sph_world* w) {
             if (gcol_r) NC(g_nccl.Recv(dst4[a] + g1, (size_t)gcol_r * 16, NCCL_CHAR, R, S.comm, w->st));
         }
         if (nr) NC(g_nccl.Send(S.gid_r.p, (size_t)nr * 4, NCCL_CHAR, R, S.comm, w->st));
+        if (ncr) NC(g_nccl.Send(S.gid_cr.p, (size_t)ncr * 4, NCCL_CHAR, R, S.comm, w->st));
         if (im_r) NC(g_nccl.Recv(w->gid[d].p + nk + im_l, (size_t)im_r * 4, NCCL_CHAR, R, S.comm, w->st));
+        if (gcol_r) NC(g_nccl.Recv(w->gid[d].p + g1, (size_t)gcol_r * 4, NCCL_CHAR, R, S.comm, w->st));
     }
     NC(g_nccl.GroupEnd());
     // my own emigrants are my ghosts now (after the neighbour's column, see the header comment)
@@ -238,10 +246,9 @@ sph_status slab_begin_step(sph_world* w) {
         if (nr) CU(cudaMemcpyAsync(dst4[a] + g1 + gcol_r, S.out_r[a].p, (size_t)nr * 16, cudaMemcpyDeviceToDevice, w->st));
     }
     if (im_l + im_r) LAUNCH(k_iota_from, im_l + im_r, 256, im_l + im_r, nk, w->orig[d].p + nk);
-    if (ghl + ghr) {  // ghosts carry no original index / id
-        CU(cudaMemsetAsync(w->orig[d].p + n_new, 0xFF, (size_t)(ghl + ghr) * 4, w->st));
-        CU(cudaMemsetAsync(w->gid[d].p + n_new, 0xFF, (size_t)(ghl + ghr) * 4, w->st));
-    }
+    if (nl) CU(cudaMemcpyAsync(w->gid[d].p + g0 + gcol_l, S.gid_l.p, (size_t)nl * 4, cudaMemcpyDeviceToDevice, w->st));
+    if (nr) CU(cudaMemcpyAsync(w->gid[d].p + g1 + gcol_r, S.gid_r.p, (size_t)nr * 4, cudaMemcpyDeviceToDevice, w->st));
+    if (ghl + ghr) CU(cudaMemsetAsync(w->orig[d].p + n_new, 0xFF, (size_t)(ghl + ghr) * 4, w->st));  // ghosts carry no original index (ids they do: the sort key)
     S.migrated_out = nl + nr;
     S.migrated_in = im_l + im_r;
     // slot ranges after the sort follow from the counts alone (CFL: immigrants land in my boundary columns)

@@ -117,6 +117,52 @@ class WCSPHSurfaceTension:
         self.params = [fluid_tension_coefficient, boundary_tension_coefficient]
 
 
+class Ball:
+    """parry Ball(radius) for particles_intersecting_shape"""
+    kind = 1
+
+    def __init__(self, radius):
+        self.params = [radius]
+
+
+class Cuboid:
+    """parry Cuboid(half_extents)"""
+    kind = 2
+
+    def __init__(self, half_extents):
+        self.params = list(half_extents)
+
+
+class Capsule:
+    """parry Capsule along local y: half_height, radius"""
+    kind = 3
+
+    def __init__(self, half_height, radius):
+        self.params = [half_height, radius]
+
+
+class CouplingManager:
+    """trait CouplingManager (coupling/coupling_manager.rs:9-28).  Subclass and override; `world` is the LiquidWorld being
+    stepped (queries issued from update_boundaries see fluid particles only, liquid_world.rs:86-103)."""
+
+    def update_boundaries(self, world, dt, inv_dt, h, particle_radius):
+        pass
+
+    def transmit_forces(self, world, dt, inv_dt):
+        pass
+
+
+class ContactsView:
+    """ParticlesContacts (contacts.rs:83-121) of one fluid as CSR numpy views: offsets (n+1), j, j_model, weight, gradient (m, 3)."""
+
+    def __init__(self, offsets, j, j_model, weight, gradient):
+        self.offsets, self.j, self.j_model, self.weight, self.gradient = offsets, j, j_model, weight, gradient
+
+    def particle_contacts(self, i):
+        """contacts.rs:107-110: slice of particle i's contacts"""
+        return slice(int(self.offsets[i]), int(self.offsets[i + 1]))
+
+
 class Fluid:
     """fluid.rs:12-68: host description handed to LiquidWorld.add_fluid."""
 
@@ -250,6 +296,119 @@ class LiquidWorld:
         cb = _lib.HOST_FORCE_FN(tramp)
         self._callbacks.append(cb)  # keep the trampoline alive as long as the world
         self._ck(self._L.sph_fluid_push_host_force(self._w, fluid, cb, None))
+
+    def push_host_force2(self, fluid, solve, contacts=True, boundaries=True):
+        """NonPressureForce::solve with its full argument list (nonpressure_force.rs:15-27).  solve(ctx) gets an object with
+        dt, inv_dt, kernel_radius, particle_radius, fluid, fluid_index, density0, positions, velocities, densities,
+        volumes, accelerations (add in place) and — on request — fluid_fluid_contacts / fluid_boundaries_contacts
+        (ContactsView) and boundaries (list of dicts with positions / velocities / volumes)."""
+        import types
+
+        def arr(ptr, shape, dtype=np.float32):
+            n = int(np.prod(shape))
+            if n == 0 or not ptr:
+                return np.zeros(shape, dtype)
+            return np.ctypeslib.as_array(ptr, (n,)).view(dtype).reshape(shape)
+
+        def tramp(_user, cp):
+            c = cp.contents
+            n = c.n
+            ctx = types.SimpleNamespace(dt=c.dt, inv_dt=c.inv_dt, kernel_radius=c.kernel_radius, particle_radius=c.particle_radius,
+                                        fluid=c.fluid, fluid_index=c.fluid_index, density0=c.density0,
+                                        positions=arr(c.positions_xyz, (n, 3)), velocities=arr(c.velocities_xyz, (n, 3)),
+                                        densities=arr(c.densities, (n,)), volumes=arr(c.volumes, (n,)) if c.volumes else None,
+                                        accelerations=arr(c.accelerations_xyz, (n, 3)),
+                                        fluid_fluid_contacts=None, fluid_boundaries_contacts=None, boundaries=None)
+            if c.ff_offsets:
+                off = arr(c.ff_offsets, (n + 1,), np.uint32)
+                m = int(off[-1]) if n else 0
+                ctx.fluid_fluid_contacts = ContactsView(off, arr(c.ff_j, (m,), np.uint32), arr(c.ff_j_model, (m,), np.uint32),
+                                                        arr(c.ff_weight, (m,)), arr(c.ff_gradient_xyz, (m, 3)))
+                off = arr(c.fb_offsets, (n + 1,), np.uint32)
+                m = int(off[-1]) if n else 0
+                ctx.fluid_boundaries_contacts = ContactsView(off, arr(c.fb_j, (m,), np.uint32), arr(c.fb_j_model, (m,), np.uint32),
+                                                             arr(c.fb_weight, (m,)), arr(c.fb_gradient_xyz, (m, 3)))
+            if c.boundaries:
+                ctx.boundaries = [dict(positions=arr(c.boundaries[b].positions_xyz, (c.boundaries[b].n, 3)),
+                                       velocities=arr(c.boundaries[b].velocities_xyz, (c.boundaries[b].n, 3)),
+                                       volumes=arr(c.boundaries[b].volumes, (c.boundaries[b].n,))) for b in range(c.n_boundaries)]
+            solve(ctx)
+
+        cb = _lib.HOST_FORCE_FN2(tramp)
+        self._callbacks.append(cb)
+        self._ck(self._L.sph_fluid_push_host_force2(self._w, fluid, cb, None, (1 if contacts else 0) | (2 if boundaries else 0)))
+
+    def remove_fluid(self, fluid):
+        """LiquidWorld::remove_fluid liquid_world.rs:171-173"""
+        self._ck(self._L.sph_fluid_remove(self._w, fluid))
+
+    def remove_boundary(self, b):
+        """LiquidWorld::remove_boundary liquid_world.rs:176-178"""
+        self._ck(self._L.sph_boundary_remove(self._w, b))
+        self._nb.pop(b, None)
+
+    def set_boundary_particles(self, b, positions, velocities=None):
+        """Replace a boundary's whole particle set (a coupled collider re-samples it every step, fluids_pipeline.rs:175-245)."""
+        p = _f32(positions, (-1, 3))
+        v = _f32(velocities, (-1, 3))
+        self._ck(self._L.sph_boundary_set_particles(self._w, b, _fp(p), _fp(v), len(p)))
+        self._nb[b] = len(p)
+
+    def step_with_coupling(self, dt, gravity, coupling):
+        """LiquidWorld::step_with_coupling liquid_world.rs:67-158 with a CouplingManager (coupling_manager.rs:9-28)."""
+        g = np.asarray(gravity, np.float32)
+        upd = _lib.COUPLING_UPDATE_FN(lambda _u, _w, dt_, inv_dt, h, r: coupling.update_boundaries(self, dt_, inv_dt, h, r))
+        tr = _lib.COUPLING_TRANSMIT_FN(lambda _u, _w, dt_, inv_dt: coupling.transmit_forces(self, dt_, inv_dt))
+        cm = _lib.CouplingManagerC(upd, tr, None)
+        self._ck(self._L.sph_world_step_with_coupling(self._w, dt, _fp(g), C.byref(cm)))
+
+    def particles_intersecting_shape(self, shape, translation=(0.0, 0.0, 0.0), rotation=None):
+        """liquid_world.rs:246-281 for Ball / Cuboid / Capsule under the isometry (rotation 3x3 row-major, translation)."""
+        sh = _lib.Shape()
+        sh.kind = shape.kind
+        for i, x in enumerate(shape.params):
+            sh.p[i] = x
+        t = np.ascontiguousarray(translation, np.float32)
+        R = None if rotation is None else np.ascontiguousarray(rotation, np.float32).reshape(9)
+        n = C.c_size_t(0)
+        u32p = C.POINTER(C.c_uint32)
+        cap = 1024
+        while True:
+            k = np.empty(cap, np.uint32)
+            h = np.empty(cap, np.uint32)
+            i = np.empty(cap, np.uint32)
+            self._ck(self._L.sph_world_particles_in_shape(self._w, C.byref(sh), _fp(t), _fp(R), k.ctypes.data_as(u32p), h.ctypes.data_as(u32p),
+                                                          i.ctypes.data_as(u32p), cap, C.byref(n)))
+            if n.value <= cap:
+                return k[:n.value], h[:n.value], i[:n.value]
+            cap = n.value
+
+    # -- snapshot / restore and zero-copy views (include/sph.h) ---------------------------------------------
+    def snapshot(self):
+        """Everything the solver carries across steps (vc, dt lag, IISPH pressures, Becker rest pose, ids) as bytes."""
+        n = C.c_size_t()
+        self._ck(self._L.sph_world_snapshot_size(self._w, C.byref(n)))
+        buf = (C.c_char * n.value)()
+        wr = C.c_size_t()
+        self._ck(self._L.sph_world_snapshot_save(self._w, buf, n.value, C.byref(wr)))
+        return bytes(buf[:wr.value])
+
+    def restore(self, blob):
+        buf = C.create_string_buffer(blob, len(blob))
+        self._ck(self._L.sph_world_snapshot_load(self._w, buf, len(blob)))
+
+    def map_positions(self, fluid, velocities=False):
+        """Device view (no host copy) of fluid.positions in ORIGINAL index order: an object with __cuda_array_interface__
+        (torch.as_tensor(view, device='cuda') / cupy.asarray(view)); valid until the next call on this world."""
+        ptr = C.POINTER(C.c_float)()
+        n = C.c_size_t()
+        fn = self._L.sph_fluid_map_velocities if velocities else self._L.sph_fluid_map_positions
+        self._ck(fn(self._w, fluid, C.byref(ptr), C.byref(n)))
+        addr = C.cast(ptr, C.c_void_p).value or 0
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n.value, 3), "typestr": "<f4", "data": (addr, True), "version": 2, "strides": None}
+        return _View()
 
     def add_boundary(self, boundary_or_positions, velocities=None, memberships=1, filter=0xFFFFFFFF,
                      want_forces=False):

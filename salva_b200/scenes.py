@@ -69,9 +69,9 @@ def cube_fluid(ni, nj, nk, particle_rad):
     return np.stack([x, y, z], axis=-1).reshape(-1, 3).astype(F32)
 
 
-def _splitmix64(seed, n):
+def _splitmix64(seed, n, start=0):
     with np.errstate(over="ignore"):
-        k = np.arange(1, n + 1, dtype=np.uint64)
+        k = np.arange(start + 1, start + n + 1, dtype=np.uint64)
         z = np.uint64(seed) + k * np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
@@ -79,10 +79,11 @@ def _splitmix64(seed, n):
     return z
 
 
-def jitter(points, particle_rad, seed, amplitude=0.05):
-    """delta in [-amplitude*r, amplitude*r)^3 from splitmix64(seed) in particle-index order."""
+def jitter(points, particle_rad, seed, amplitude=0.05, first_index=0):
+    """delta in [-amplitude*r, amplitude*r)^3 from splitmix64(seed) in particle-index order; `first_index` is the
+    global index of points[0] (a rank that generates only its slab of a block gets the same bytes as the whole block)."""
     n = len(points)
-    u = (_splitmix64(seed, 3 * n) >> np.uint64(40)).astype(F32) * F32(1.0 / (1 << 24))  # [0,1)
+    u = (_splitmix64(seed, 3 * n, 3 * first_index) >> np.uint64(40)).astype(F32) * F32(1.0 / (1 << 24))  # [0,1)
     d = (u * F32(2.0) - F32(1.0)) * F32(amplitude) * F32(particle_rad)
     return (points + d.reshape(n, 3)).astype(F32)
 
@@ -159,9 +160,27 @@ def block_lattice(nx, ny, nz, particle_rad, origin=(0.0, 0.0, 0.0)):
     return pts.reshape(-1, 3)
 
 
-def _dam_break(nx, ny, nz, r, dt, forces, solver=DFSPH, name="", tank_x_factor=2.0, jitter_seed=0x5A17A):
+def _dam_break(nx, ny, nz, r, dt, forces, solver=DFSPH, name="", tank_x_factor=2.0, jitter_seed=0x5A17A, compress=1.0, amplitude=0.05,
+               x_range=None):
+    """Block of nx*ny*nz particles (lattice spacing 2r*compress, jittered) in an open tank.  compress < 1 starts the block
+    over-dense (0.93 ~ rest density, 0.90 ~ +10 %: the Jacobi loops run several iterations from the first step).
+    x_range = (i0, i1) generates only the lattice planes i0 <= i < i1 (the slab of one rank) with the same bytes."""
     s = 2.0 * r
-    pts = jitter(block_lattice(nx, ny, nz, r), r, jitter_seed)
+    if x_range is None:
+        pts = jitter(block_lattice(nx, ny, nz, r * compress), r, jitter_seed, amplitude=amplitude)
+    else:
+        i0, i1 = x_range
+        # same f32 arithmetic as block_lattice: x = (2 i + 1) * r for the global lattice index i
+        rr = F32(r * compress)
+        x = (np.arange(i0, i1, dtype=F32) * F32(2.0) + F32(1.0)) * rr
+        y = (np.arange(ny, dtype=F32) * F32(2.0) + F32(1.0)) * rr
+        z = (np.arange(nz, dtype=F32) * F32(2.0) + F32(1.0)) * rr
+        blk = np.empty((i1 - i0, ny, nz, 3), F32)
+        blk[..., 0] = x[:, None, None]
+        blk[..., 1] = y[None, :, None]
+        blk[..., 2] = z[None, None, :]
+        blk = blk.reshape(-1, 3)
+        pts = jitter(blk, r, jitter_seed, amplitude=amplitude, first_index=i0 * ny * nz)
     lo = (-r, -r, -r)
     hi = (nx * s * tank_x_factor + r, ny * s + 4 * s + r, nz * s + r)
     # snap hi to the lattice so walls sit exactly one spacing outside the block in z
@@ -204,20 +223,39 @@ def scene_tension_small():
                 boundaries=[dict(positions=tank, want_forces=True)])
 
 
-def scene_c2(n=100):
+def scene_c2(n=100, **kw):
     """1M-particle cube dam-break, DFSPH + XSPHViscosity(0.5, 0), r=0.025, dt=1/1000."""
-    return _dam_break(n, n, n, 0.025, 1.0 / 1000.0, [xsph_viscosity(0.5, 0.0)], name="C2-dam-%d" % (n ** 3))
+    return _dam_break(n, n, n, 0.025, 1.0 / 1000.0, [xsph_viscosity(0.5, 0.0)], name="C2-dam-%d" % (n ** 3), **kw)
 
 
-def scene_c3(n=216):
+def scene_c3(n=216, **kw):
     """10M particles, DFSPH + Akinci2013SurfaceTension(1, 0) (roofline capture config)."""
     return _dam_break(n, n, n, 0.025, 1.0 / 1000.0, [akinci2013_surface_tension(1.0, 0.0)],
-                      name="C3-dam-%d" % (n ** 3))
+                      name="C3-dam-%d" % (n ** 3), **kw)
 
 
-def scene_c4(nx=512, ny=250, nz=250):
+def scene_c4(nx=512, ny=250, nz=250, **kw):
     """32M particles DFSPH (no extra force), long axis = slab axis x."""
-    return _dam_break(nx, ny, nz, 0.025, 1.0 / 1000.0, [], name="C4-dam-%d" % (nx * ny * nz), tank_x_factor=1.25)
+    return _dam_break(nx, ny, nz, 0.025, 1.0 / 1000.0, [], name="C4-dam-%d" % (nx * ny * nz), tank_x_factor=1.25, **kw)
+
+
+def slab_scene(scene_fn, rank, nranks, nx, **kw):
+    """Rank `rank`'s slab of a dam-break scene whose block is nx lattice planes long in x, generated WITHOUT building the
+    other ranks' particles: h = 4r, so lattice planes 2c and 2c+1 fall in cell column c and (jitter < r) never leave it;
+    rank r owns the cell columns [r*ncol/nranks, (r+1)*ncol/nranks).  Returns the partitioned scene dict that
+    salva_b200.slab.populate_slab() accepts (fluids carry global ids, `slab` = owned cell columns)."""
+    ncol = nx // 2
+    assert nx % 2 == 0 and ncol >= 2 * nranks, "block too short for %d slabs" % nranks
+    c0, c1 = rank * ncol // nranks, (rank + 1) * ncol // nranks
+    sc = scene_fn(x_range=(2 * c0, 2 * c1), **kw)
+    f = sc["fluids"][0]
+    ny_nz = len(f["positions"]) // (2 * (c1 - c0))
+    f["ids"] = (np.arange(len(f["positions"]), dtype=np.int64) + 2 * c0 * ny_nz).astype(np.uint32)
+    planes = [-2 ** 31] + [r * ncol // nranks for r in range(1, nranks)] + [2 ** 31 - 1]
+    sc["slab"] = (planes[rank], planes[rank + 1])
+    sc["planes"] = planes
+    sc["partitioned"] = True
+    return sc
 
 
 def scene_c5(n=100):

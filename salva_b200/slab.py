@@ -86,7 +86,7 @@ def broadcast_unique_id(make_id, rank, device=None):
 def populate_slab(world, scene, rank, nranks, unique_id, planes=None):
     """Add rank's slab of `scene` to `world` and join the decomposition.  Returns (fluid handles, boundary handles)."""
     from . import scenes
-    part = partition_scene(scene, rank, nranks, planes)
+    part = scene if scene.get("partitioned") else partition_scene(scene, rank, nranks, planes)
     fh, bh = scenes.populate(world, part)
     for h, f in zip(fh, part["fluids"]):
         world.set_ids(h, f["ids"])

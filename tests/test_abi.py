@@ -33,6 +33,29 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.StepStats) == 12 * 4 + 4 * 4 + 2 * 4 + 3 * 8 + 4 + 3 * 4 + 8 + 4 * 4
 
 
+def test_ctypes_struct_sizes_match_a_c_compiler(tmp_path):
+    """The python binding's struct layouts against gcc's view of include/sph.h (sizes and a few offsets)."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "sph.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(sph_world_desc), sizeof(sph_force_desc), sizeof(sph_step_stats),
+           sizeof(sph_host_force_ctx), sizeof(sph_boundary_view), sizeof(sph_shape), sizeof(sph_coupling_manager),
+           offsetof(sph_host_force_ctx, ff_offsets), offsetof(sph_host_force_ctx, boundaries));
+    return 0;
+}
+''')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(_lib.WorldDesc), C.sizeof(_lib.ForceDesc), C.sizeof(_lib.StepStats), C.sizeof(_lib.HostForceCtx),
+            C.sizeof(_lib.BoundaryView), C.sizeof(_lib.Shape), C.sizeof(_lib.CouplingManagerC),
+            _lib.HostForceCtx.ff_offsets.offset, _lib.HostForceCtx.boundaries.offset]
+    assert got == want
+
+
 def test_product_does_not_import_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py may import, link or execute anything under oracle/."""
     pat = re.compile(r"^\s*(from|import)\s+oracle\b|#include\s*[\"<].*oracle|liboracle|CDLL\(.*oracle", re.M)
