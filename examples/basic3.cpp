@@ -24,7 +24,7 @@ int main(int argc, char** argv) {
     const float PARTICLE_RADIUS = 0.05f, SMOOTHING_FACTOR = 2.0f;
     int steps = argc > 1 ? atoi(argv[1]) : 20;
     try {
-        LiquidWorld world(DFSPHSolver(), PARTICLE_RADIUS, SMOOTHING_FACTOR);
+        LiquidWorld world(DFSPHSolver<>(), PARTICLE_RADIUS, SMOOTHING_FACTOR);
         const int n = 15;
         Fluid fluid = cube_fluid(n, n, n, PARTICLE_RADIUS, 1000.0f);
         for (auto& p : fluid.positions) p.y += 0.2f + n * PARTICLE_RADIUS;  // transform_by(translation) basic3.rs:37-41

@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
     const float PARTICLE_RADIUS = 0.025f, SMOOTHING_FACTOR = 2.0f;
     int steps = argc > 1 ? atoi(argv[1]) : 20;
     try {
-        LiquidWorld world(DFSPHSolver(), PARTICLE_RADIUS, SMOOTHING_FACTOR);
+        LiquidWorld world(DFSPHSolver<>(), PARTICLE_RADIUS, SMOOTHING_FACTOR);
         const int n = 10;
         std::vector<Point3> points;  // examples3d/helper.rs:4-20
         for (int i = 0; i < n; ++i)

@@ -68,6 +68,14 @@ enum { SPH_FORCE_XSPH_VISCOSITY = 0,        /* p[0]=fluid coeff, p[1]=boundary c
                                                p[2]=max_viscosity_iter (50), p[3]=max_viscosity_error (0.01)
                                                dfsph_viscosity.rs:86-124 */ };
 
+/* Kernel type parameters of the solver, DFSPHSolver<KernelDensity, KernelGradient> dfsph_solver.rs:17-20 /
+ * IISPHSolver<..> iisph_solver.rs:17-20: contact.weight uses the density kernel, contact.gradient the gradient kernel
+ * (helper.rs:24-25). */
+enum { SPH_KERNEL_CUBIC_SPLINE = 0,  /* kernel/cubic_spline_kernel.rs:12-80 (default) */
+       SPH_KERNEL_POLY6 = 1,         /* kernel/poly6_kernel.rs:12-40 */
+       SPH_KERNEL_SPIKY = 2,         /* kernel/spiky_kernel.rs:12-40 */
+       SPH_KERNEL_VISCOSITY = 3      /* kernel/viscosity_kernel.rs:12-51 */ };
+
 typedef struct {
     int32_t  solver;                 /* SPH_SOLVER_* */
     float    particle_radius;        /* liquid_world.rs:41 */
@@ -85,6 +93,8 @@ typedef struct {
     int32_t  deterministic;          /* 1: stable in-cell ordering => bit-reproducible run to run */
     int32_t  gather_backend;         /* 0: L1/texture gathers over 32-bit global lists (default, fastest measured);
                                         1: tile-staged shared memory via TMA bulk copies + 16-bit tile-local lists */
+    int32_t  kernel_density;         /* SPH_KERNEL_*: KernelDensity  (0 = CubicSplineKernel) */
+    int32_t  kernel_gradient;        /* SPH_KERNEL_*: KernelGradient (0 = CubicSplineKernel) */
 } sph_world_desc;
 
 typedef struct {
@@ -210,6 +220,11 @@ sph_status sph_fluid_read(sph_world* w, uint32_t fluid, float* pos_xyz, float* v
 sph_status sph_fluid_count(sph_world* w, uint32_t fluid, size_t* n);
 /* LiquidWorld::remove_fluid liquid_world.rs:171-173 (the handle dies, the others stay valid). */
 sph_status sph_fluid_remove(sph_world* w, uint32_t fluid);
+/* Replaces a fluid's whole particle set: positions, velocities, velocity_changes (dfsph_solver.rs:44, the part of the
+ * velocity DFSPH carries between steps; NULL = zeros) and ids (NULL = 0..n-1).  Used by the slab worlds' plane re-balancing
+ * (salva_b200/slab.py rebalance), where particles change rank wholesale.  sph_debug_read(SPH_DBG_VELOCITY_CHANGE) reads vc. */
+sph_status sph_fluid_replace_particles(sph_world* w, uint32_t fluid, const float* pos_xyz, const float* vel_xyz, const float* vc_xyz,
+                                       const uint32_t* ids, size_t n);
 /* Zero-copy read-back for renderers (testbed_plugin.rs:361-376 copies fluid.positions every frame): DEVICE pointers to
  * packed xyz f32 in ORIGINAL index order, valid until the next call on this world. */
 sph_status sph_fluid_map_positions(sph_world* w, uint32_t fluid, const float** device_xyz, size_t* n);

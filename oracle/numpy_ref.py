@@ -35,10 +35,54 @@ def _dw(r, h):
     return sigma * rhs / h
 
 
+def _powi(x, n):
+    r = np.ones_like(x, dtype=F)
+    for _ in range(n):
+        r = (r * x).astype(F)
+    return r
+
+
+def _w_kind(kind, r, h):
+    """kernel/poly6_kernel.rs:12-24, spiky_kernel.rs:12-24, viscosity_kernel.rs:12-32 (dim3); kind 0 = cubic spline"""
+    if kind == 0:
+        return _w(r, h)
+    inside = r <= h
+    if kind == 1:
+        norm = F(315.0 / 64.0) / (F(np.pi) * _powi(h, 9))
+        return np.where(inside, norm * _powi(h * h - r * r, 3), F(0)).astype(F)
+    if kind == 2:
+        norm = F(15.0) / (F(np.pi) * _powi(h, 6))
+        return np.where(inside, norm * _powi(h - r, 3), F(0)).astype(F)
+    norm = F(15.0) / (F(2.0) * F(np.pi) * _powi(h, 3))
+    rs = np.where(r > 0, r, F(1))
+    rr_hh = rs * rs / (h * h)
+    val = norm * (rr_hh * (F(1.0) - rs / (F(2.0) * h)) + h / (F(2.0) * rs) - F(1.0))
+    return np.where(inside & (r > 0), val, F(0)).astype(F)
+
+
+def _dw_kind(kind, r, h):
+    """poly6_kernel.rs:26-39, spiky_kernel.rs:26-39, viscosity_kernel.rs:34-50"""
+    if kind == 0:
+        return _dw(r, h)
+    inside = r <= h
+    if kind == 1:
+        norm = F(315.0 / 64.0) / (F(np.pi) * _powi(h, 9))
+        return np.where(inside, norm * _powi(h * h - r * r, 2) * r * F(-6.0), F(0)).astype(F)
+    if kind == 2:
+        norm = F(15.0) / (F(np.pi) * _powi(h, 6))
+        return np.where(inside, -norm * _powi(h - r, 2) * F(3.0), F(0)).astype(F)
+    norm = F(15.0) / (F(2.0) * F(np.pi) * _powi(h, 3))
+    rs = np.where(r > 0, r, F(1))
+    rr, hh = rs * rs, h * h
+    val = norm * (F(-3.0) * rr / (F(2.0) * hh * h) + F(2.0) * rs / hh - h / (F(2.0) * rr))
+    return np.where(inside & (r > 0), val, F(0)).astype(F)
+
+
 class NumpyDFSPH:
     """Single-threaded dense restatement; fluids are concatenated, boundaries are concatenated."""
 
-    def __init__(self, particle_radius, smoothing_factor=2.0, min_neighbors=20):
+    def __init__(self, particle_radius, smoothing_factor=2.0, min_neighbors=20, kernel_density=0, kernel_gradient=0):
+        self.kernel_density, self.kernel_gradient = kernel_density, kernel_gradient
         self.r = F(particle_radius)
         self.h = F(particle_radius) * F(smoothing_factor) * F(2.0)
         self.dt = F(0.0)
@@ -97,11 +141,11 @@ class NumpyDFSPH:
 
     def _kernels(self, d, d2, mask):
         r = np.sqrt(d2).astype(F)
-        W = np.where(mask, _w(r, self.h), F(0)).astype(F)
+        W = np.where(mask, _w_kind(self.kernel_density, r, self.h), F(0)).astype(F)
         ok = d2 > EPS * EPS
         rs = np.where(ok, r, F(1))
         dirs = (d / rs[..., None]).astype(F)
-        G = np.where((mask & ok)[..., None], dirs * _dw(r, self.h)[..., None], F(0)).astype(F)
+        G = np.where((mask & ok)[..., None], dirs * _dw_kind(self.kernel_gradient, r, self.h)[..., None], F(0)).astype(F)
         return W, G
 
     def contacts(self):

@@ -85,8 +85,58 @@ static inline float dw_scalar(float r, float h) {
     }
     return normalizer * rhs / h;
 }
+// ---- kernel/poly6_kernel.rs:12-40, spiky_kernel.rs:12-40, viscosity_kernel.rs:12-51 (dim3): the solver's
+//      KernelDensity / KernelGradient type parameters (dfsph_solver.rs:17-20, iisph_solver.rs:17-20) ------------------
+enum { KERNEL_CUBIC_SPLINE = 0, KERNEL_POLY6 = 1, KERNEL_SPIKY = 2, KERNEL_VISCOSITY = 3 };
+static inline float powi(float x, int n) {  // f32::powi: repeated multiplication
+    float r = 1.0f;
+    for (int k = 0; k < n; ++k) r *= x;
+    return r;
+}
+static inline float w_scalar_kind(int kind, float r, float h) {
+    switch (kind) {
+        case KERNEL_POLY6: {
+            float normalizer = (float)(315.0 / 64.0) / (PI_F * powi(h, 9));
+            return r <= h ? normalizer * powi(h * h - r * r, 3) : 0.0f;
+        }
+        case KERNEL_SPIKY: {
+            float normalizer = 15.0f / (PI_F * powi(h, 6));
+            return r <= h ? normalizer * powi(h - r, 3) : 0.0f;
+        }
+        case KERNEL_VISCOSITY: {
+            float normalizer = 15.0f / (2.0f * PI_F * powi(h, 3));
+            if (r > 0.0f && r <= h) {
+                float rr_hh = r * r / (h * h);
+                return normalizer * (rr_hh * (1.0f - r / (2.0f * h)) + h / (2.0f * r) - 1.0f);
+            }
+            return 0.0f;
+        }
+        default: return w_scalar(r, h);
+    }
+}
+static inline float dw_scalar_kind(int kind, float r, float h) {
+    switch (kind) {
+        case KERNEL_POLY6: {
+            float normalizer = (float)(315.0 / 64.0) / (PI_F * powi(h, 9));
+            return r <= h ? normalizer * powi(h * h - r * r, 2) * r * -6.0f : 0.0f;
+        }
+        case KERNEL_SPIKY: {
+            float normalizer = 15.0f / (PI_F * powi(h, 6));
+            return r <= h ? -normalizer * powi(h - r, 2) * 3.0f : 0.0f;
+        }
+        case KERNEL_VISCOSITY: {
+            float normalizer = 15.0f / (2.0f * PI_F * powi(h, 3));
+            if (r > 0.0f && r <= h) {
+                float rr = r * r, hh = h * h, hhh = hh * h;
+                return normalizer * (-3.0f * rr / (2.0f * hhh) + 2.0f * r / hh - h / (2.0f * rr));
+            }
+            return 0.0f;
+        }
+        default: return dw_scalar(r, h);
+    }
+}
 // ---- kernel/kernel.rs:13-15,27-29: points_apply = scalar_apply(|p1-p2|) ---------------------------
-static inline float kernel_w(V3 p1, V3 p2, float h) { return w_scalar(std::sqrt(norm2(p1 - p2)), h); }
+static inline float kernel_w(V3 p1, V3 p2, float h, int kind = KERNEL_CUBIC_SPLINE) { return w_scalar_kind(kind, std::sqrt(norm2(p1 - p2)), h); }
 // ---- kernel/kernel.rs:18-24,32-34 + nalgebra Unit::try_new_and_get(v, eps):
 //      Some((v / |v|, |v|)) iff |v|^2 > eps^2 ---------------------------------------------------------
 static inline bool unit_and_norm(V3 v, V3* dir, float* n) {
@@ -99,10 +149,10 @@ static inline bool unit_and_norm(V3 v, V3* dir, float* n) {
     }
     return false;
 }
-static inline V3 kernel_grad(V3 p1, V3 p2, float h) {
+static inline V3 kernel_grad(V3 p1, V3 p2, float h, int kind = KERNEL_CUBIC_SPLINE) {
     V3 dir;
     float n;
-    if (unit_and_norm(p1 - p2, &dir, &n)) return dir * dw_scalar(n, h);
+    if (unit_and_norm(p1 - p2, &dir, &n)) return dir * dw_scalar_kind(kind, n, h);
     return ZERO3;
 }
 
@@ -264,6 +314,7 @@ struct World {
     // timestep_manager.rs:21-31
     float dt = 0.f, inv_dt = 0.f, total_step_size = 0.f, remaining_time = 0.f;
     int sort_contacts = 1;
+    int kernel_density = KERNEL_CUBIC_SPLINE, kernel_gradient = KERNEL_CUBIC_SPLINE;  // DFSPHSolver<KernelDensity, KernelGradient>
     int force_div = -1, force_press = -1;
 
     std::vector<Fluid> fluids;
@@ -414,16 +465,16 @@ static void evaluate_kernels(World& w) {
         for (long i = 0; i < (long)lists.size(); ++i)
             for (Contact& c : lists[i]) {
                 V3 pi = w.fluids[c.i_model].positions[c.i], pj = w.fluids[c.j_model].positions[c.j];
-                c.weight = kernel_w(pi, pj, w.h);
-                c.gradient = kernel_grad(pi, pj, w.h);
+                c.weight = kernel_w(pi, pj, w.h, w.kernel_density);
+                c.gradient = kernel_grad(pi, pj, w.h, w.kernel_gradient);
             }
         auto& blists = w.fb[f].lists;
 #pragma omp parallel for schedule(static)
         for (long i = 0; i < (long)blists.size(); ++i)
             for (Contact& c : blists[i]) {
                 V3 pi = w.fluids[c.i_model].positions[c.i], pj = w.boundaries[c.j_model].positions[c.j];
-                c.weight = kernel_w(pi, pj, w.h);
-                c.gradient = kernel_grad(pi, pj, w.h);
+                c.weight = kernel_w(pi, pj, w.h, w.kernel_density);
+                c.gradient = kernel_grad(pi, pj, w.h, w.kernel_gradient);
             }
     }
     for (size_t b = 0; b < w.boundaries.size(); ++b) {
@@ -432,8 +483,8 @@ static void evaluate_kernels(World& w) {
         for (long i = 0; i < (long)lists.size(); ++i)
             for (Contact& c : lists[i]) {
                 V3 pi = w.boundaries[c.i_model].positions[c.i], pj = w.boundaries[c.j_model].positions[c.j];
-                c.weight = kernel_w(pi, pj, w.h);
-                c.gradient = kernel_grad(pi, pj, w.h);
+                c.weight = kernel_w(pi, pj, w.h, w.kernel_density);
+                c.gradient = kernel_grad(pi, pj, w.h, w.kernel_gradient);
             }
     }
 }
@@ -685,11 +736,6 @@ static void solve_artificial(World& w, size_t f, Force& fc) {
     }
 }
 
-static inline float powi(float x, int n) {
-    float r = 1.f;
-    for (int k = 0; k < n; ++k) r *= x;
-    return r;
-}
 // ---- surface_tension/akinci2013_surface_tension.rs:71-88 (dim3) ----------------------------------
 static inline float cohesion_kernel(float r, float h) {
     float normalizer = 32.0f / (PI_F * powi(h, 9));
@@ -1605,6 +1651,12 @@ void* orc_world_create(const orc_desc* d) {
     return w;
 }
 void orc_world_destroy(void* p) { delete (World*)p; }
+void orc_world_set_kernels(void* p, int kernel_density, int kernel_gradient) {
+    ((World*)p)->kernel_density = kernel_density;
+    ((World*)p)->kernel_gradient = kernel_gradient;
+}
+float orc_kernel_w_kind(int kind, float r, float h) { return w_scalar_kind(kind, r, h); }
+float orc_kernel_dw_kind(int kind, float r, float h) { return dw_scalar_kind(kind, r, h); }
 
 static void copy_v3(std::vector<V3>& dst, const float* src, size_t n) {
     dst.resize(n);

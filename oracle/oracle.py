@@ -77,6 +77,10 @@ def lib():
         for n in ("orc_kernel_w", "orc_kernel_dw", "orc_cohesion_kernel", "orc_adhesion_kernel"):
             getattr(L, n).restype = C.c_float
             getattr(L, n).argtypes = [C.c_float, C.c_float]
+        L.orc_world_set_kernels.argtypes = [vp, C.c_int, C.c_int]
+        for n in ("orc_kernel_w_kind", "orc_kernel_dw_kind"):
+            getattr(L, n).restype = C.c_float
+            getattr(L, n).argtypes = [C.c_int, C.c_float, C.c_float]
         L.orc_max_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -105,7 +109,7 @@ class OracleWorld:
 
     def __init__(self, particle_radius, smoothing_factor=2.0, solver=0, min_pressure_iter=1, max_pressure_iter=50,
                  max_density_error=0.05, min_divergence_iter=1, max_divergence_iter=50, max_divergence_error=0.1,
-                 omega=0.5, sort_contacts=True, num_threads=None):
+                 omega=0.5, sort_contacts=True, num_threads=None, kernel_density=0, kernel_gradient=0):
         self._L = lib()
         if num_threads is None:  # small test scenes: a handful of threads (128 spinning OpenMP threads are far slower)
             num_threads = min(8, os.cpu_count() or 1)
@@ -113,6 +117,8 @@ class OracleWorld:
                     max_density_error, min_divergence_iter, max_divergence_iter, max_divergence_error, omega,
                     int(sort_contacts), num_threads)
         self._w = self._L.orc_world_create(C.byref(d))
+        if kernel_density or kernel_gradient:  # DFSPHSolver<KernelDensity, KernelGradient> dfsph_solver.rs:17-20
+            self._L.orc_world_set_kernels(self._w, kernel_density, kernel_gradient)
         self.h = np.float32(particle_radius) * np.float32(smoothing_factor) * np.float32(2.0)
         self.particle_radius = particle_radius
 

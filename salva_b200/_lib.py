@@ -20,7 +20,7 @@ class WorldDesc(C.Structure):
                 ("min_divergence_iter", C.c_uint32), ("max_divergence_iter", C.c_uint32),
                 ("max_divergence_error", C.c_float), ("omega", C.c_float), ("device", C.c_int32),
                 ("slab_rank", C.c_int32), ("slab_count", C.c_int32), ("deterministic", C.c_int32),
-                ("gather_backend", C.c_int32)]
+                ("gather_backend", C.c_int32), ("kernel_density", C.c_int32), ("kernel_gradient", C.c_int32)]
 
 
 class ForceDesc(C.Structure):
@@ -111,6 +111,7 @@ SYMBOLS = {
     "sph_fluid_set_ids": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t]),
     "sph_fluid_push_host_force2": (C.c_int, [_vp, C.c_uint32, HOST_FORCE_FN2, _vp, C.c_uint32]),
     "sph_fluid_remove": (C.c_int, [_vp, C.c_uint32]),
+    "sph_fluid_replace_particles": (C.c_int, [_vp, C.c_uint32, _fp, _fp, _fp, C.POINTER(C.c_uint32), C.c_size_t]),
     "sph_fluid_map_positions": (C.c_int, [_vp, C.c_uint32, C.POINTER(_fp), C.POINTER(C.c_size_t)]),
     "sph_fluid_map_velocities": (C.c_int, [_vp, C.c_uint32, C.POINTER(_fp), C.POINTER(C.c_size_t)]),
     "sph_boundary_remove": (C.c_int, [_vp, C.c_uint32]),

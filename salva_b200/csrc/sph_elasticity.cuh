@@ -94,7 +94,7 @@ __global__ void k_el_rest_volumes(uint32_t n, const float4* __restrict__ cur, co
     for (uint32_t k = 0; k < cnt; ++k) {
         uint32_t j = nbr0[(size_t)k * stride0 + t];
         float4 pj = cur[j];
-        Pair p = make_pair<true, false>(pi, pj);
+        Pair p = make_pair<true, false, true>(pi, pj);
         // contact (t, j) adds m_j W to vol0[t]; its mirror (j, t) in j's list adds m_j W to vol0[t] again (:105-108)
         acc += 2.0f * pj.w * p.w;
     }
@@ -134,7 +134,7 @@ k_el_rotations(uint32_t n, const float4* __restrict__ cur, const float4* __restr
     for (uint32_t k = 0; k < cnt; ++k) {
         uint32_t j = nbr0[(size_t)k * stride0 + t];
         float4 pj = cur[j], qj = pos0[j];
-        Pair rp = make_pair<true, false>(qi, qj);  // contact.weight at the rest pose
+        Pair rp = make_pair<true, false, true>(qi, qj);  // contact.weight at the rest pose
         float coeff = rp.w * pj.w;
         float3 p = make_float3(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
         float3 q = make_float3((qj.x - qi.x) * coeff, (qj.y - qi.y) * coeff, (qj.z - qi.z) * coeff);
@@ -183,7 +183,7 @@ k_el_stresses(uint32_t n, const float4* __restrict__ cur, const float4* __restri
     for (uint32_t k = 0; k < cnt; ++k) {
         uint32_t j = nbr0[(size_t)k * stride0 + t];
         float4 pj = cur[j], qj = pos0[j];
-        Pair rp = make_pair<false, true>(qi, qj);  // contact.gradient at the rest pose = rp.g * (q_i - q_j)
+        Pair rp = make_pair<false, true, true>(qi, qj);  // contact.gradient at the rest pose = rp.g * (q_i - q_j)
         float3 p = make_float3(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
         float3 u = m3_tmul(R, p);  // inverse_transform_vector
         u.x -= qj.x - qi.x; u.y -= qj.y - qi.y; u.z -= qj.z - qi.z;
@@ -245,7 +245,7 @@ k_el_forces(uint32_t n, const float4* __restrict__ cur, const float4* __restrict
     for (uint32_t k = 0; k < cnt; ++k) {
         uint32_t j = nbr0[(size_t)k * stride0 + t];
         float4 qj = pos0[j];
-        Pair rp = make_pair<false, true>(qi, qj);
+        Pair rp = make_pair<false, true, true>(qi, qj);
         float3 grad = make_float3(rp.g * rp.dx, rp.g * rp.dy, rp.g * rp.dz);
         float3 d_ij = make_float3(grad.x * qj.w, grad.y * qj.w, grad.z * qj.w);
         float3 sd_ij = sym_mul(si, d_ij);

@@ -354,6 +354,16 @@ void fill_static_consts(sph_world* w) {
     c.sigma = 8.0f / (3.14159265358979323846f * w->h * w->h * w->h);
     c.dsigma = c.sigma / w->h;
     c.dsigma6 = 6.0f * c.dsigma;
+    c.kw = w->desc.kernel_density;
+    c.kg = w->desc.kernel_gradient;
+    c.kgen = (c.kw != 0 || c.kg != 0) ? 1 : 0;
+    {
+        const float h = w->h, pi = 3.14159265358979323846f;
+        auto powi = [](float x, int n) { float r = 1.f; for (int k = 0; k < n; ++k) r *= x; return r; };
+        c.poly6_n = (float)(315.0 / 64.0) / (pi * powi(h, 9));
+        c.spiky_n = 15.0f / (pi * powi(h, 6));
+        c.visc_n = 15.0f / (2.0f * pi * powi(h, 3));
+    }
     {
         const double a = (double)F32_EPS * (double)F32_EPS, b = 1.0e-5 * (double)w->h * 1.0e-5 * (double)w->h;
         c.g_t2 = (float)std::max(a, b);
@@ -1745,6 +1755,8 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     *out = nullptr;
     if (!(desc->particle_radius > 0.f) || !(desc->smoothing_factor > 0.f)) return SPH_ERR_INVALID;
     if (desc->solver != SPH_SOLVER_DFSPH && desc->solver != SPH_SOLVER_IISPH) return SPH_ERR_INVALID;
+    if (desc->kernel_density < 0 || desc->kernel_density > SPH_KERNEL_VISCOSITY || desc->kernel_gradient < 0 || desc->kernel_gradient > SPH_KERNEL_VISCOSITY)
+        return SPH_ERR_INVALID;
     std::lock_guard<std::recursive_mutex> lock(g_mutex);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || desc->device < 0 || desc->device >= ndev) return SPH_ERR_CUDA;
@@ -1753,6 +1765,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     w->desc = *desc;
     w->h = desc->particle_radius * desc->smoothing_factor * 2.0f;  // liquid_world.rs:44
     w->tile = desc->gather_backend == 1 && desc->solver == SPH_SOLVER_DFSPH;  // the tile backend covers the DFSPH passes only
+    if (desc->kernel_density || desc->kernel_gradient) w->use_gcache = 0;
     if (const char* t = getenv("SALVA_B200_DEVICE_LOOPS")) w->device_loops = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_GCACHE")) w->use_gcache = atoi(t);
     if (const char* t = getenv("SALVA_B200_REC8")) w->use_rec8 = atoi(t);
@@ -2517,6 +2530,49 @@ sph_status sph_fluid_map_velocities(sph_world* w, uint32_t fluid_h, const float*
     if (!w || !dev_xyz || !n) return SPH_ERR_INVALID;
     std::lock_guard<std::recursive_mutex> lock(g_mutex);
     return fluid_map(w, fluid_h, true, dev_xyz, n);
+}
+
+// Replaces the whole particle set of a fluid: positions, velocities, velocity_changes (dfsph_solver.rs:44 — the part of the
+// velocity the solver carries between steps) and caller-visible ids; volumes return to the default, IISPH pressures to 0.
+// This is what a slab world's plane re-balancing needs (salva_b200/slab.py: particles move between ranks wholesale).
+sph_status sph_fluid_replace_particles(sph_world* w, uint32_t fluid_h, const float* pos, const float* vel, const float* vc, const uint32_t* ids,
+                                       size_t n) {
+    if (!w || (n && !pos)) return SPH_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(g_mutex);
+    FLUID_OR_FAIL(fluid, fluid_h)
+    if (w->in_coupling) return w->fail(SPH_ERR_INVALID, "particles cannot be replaced from inside a coupling callback");
+    TRY(enter(w));
+    TRY(stage_down(w));
+    FluidRec& f = w->fluids[fluid];
+    const size_t at = f.offset, old = f.n;
+    const float r = w->desc.particle_radius, pv = r * r * r * (float)(8.0 * 0.8);
+    w->h_press.resize(w->h_vol.size(), 0.f);
+    w->h_gid.resize(w->h_vol.size());
+    auto splice3 = [&](std::vector<float>& v, const float* src) {
+        v.erase(v.begin() + 3 * at, v.begin() + 3 * (at + old));
+        if (src) v.insert(v.begin() + 3 * at, src, src + 3 * n);
+        else v.insert(v.begin() + 3 * at, 3 * n, 0.f);
+    };
+    splice3(w->h_pos, pos);
+    splice3(w->h_vel, vel);
+    splice3(w->h_vc, vc);
+    w->h_vol.erase(w->h_vol.begin() + at, w->h_vol.begin() + at + old);
+    w->h_vol.insert(w->h_vol.begin() + at, n, pv);
+    w->h_press.erase(w->h_press.begin() + at, w->h_press.begin() + at + old);
+    w->h_press.insert(w->h_press.begin() + at, n, 0.f);
+    w->h_gid.erase(w->h_gid.begin() + at, w->h_gid.begin() + at + old);
+    {
+        std::vector<uint32_t> g(n);
+        for (size_t i = 0; i < n; ++i) g[i] = ids ? ids[i] : (uint32_t)i;
+        w->h_gid.insert(w->h_gid.begin() + at, g.begin(), g.end());
+    }
+    f.n = n;
+    f.pending_delete.assign(n, 0);
+    f.n_pending = 0;
+    for (auto& fr : f.forces) elasticity_release(fr);  // a rest pose belongs to the particle set it was captured from
+    recompute_offsets(w);
+    w->slab.global_valid = false;
+    return SPH_OK;
 }
 
 // ---- snapshot / restore of the state the solver carries across steps ----------------------------------------------------

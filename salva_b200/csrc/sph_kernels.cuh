@@ -36,6 +36,10 @@ struct Consts {
     float dsigma;                // sigma / h               cubic_spline_kernel.rs:79
     float dsigma6;               // 6 sigma / h
     float g_t2;                  // gradient is zero unless |x_ij|^2 > g_t2 = max(eps^2, (1e-5 h)^2)  (kernel.rs:19 + cubic_spline_kernel.rs:64)
+    // DFSPHSolver<KernelDensity, KernelGradient> / IISPHSolver<..> type parameters (dfsph_solver.rs:17-20): 0 = CubicSpline
+    // (default, the lean path), 1 = Poly6, 2 = Spiky, 3 = Viscosity; kgen != 0 <=> any of the two is not the cubic spline
+    int kw, kg, kgen;
+    float poly6_n, spiky_n, visc_n;  // 315/(64 pi h^9), 15/(pi h^6), 15/(2 pi h^3)
     int ox, oy, oz;              // grid origin in cell coordinates (one padding cell each side)
     int nx, ny, nz;
     int ntx, nty, ntz;           // tile grid (sph_tile.cuh): 2 x 2 cell columns x TILE_Z cells per tile
@@ -98,19 +102,79 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
     return y;
 }
 
+// kernel/poly6_kernel.rs:12-40, spiky_kernel.rs:12-40, viscosity_kernel.rs:12-51 (dim3), evaluated like the reference
+// (IEEE sqrt / division, powi as repeated products); kind 0 falls through to the cubic spline.
+__device__ __forceinline__ float kernel_w_kind(int kind, float r) {
+    const float h = C.h;
+    if (kind == 1) {
+        const float t = h * h - r * r;
+        return r <= h ? C.poly6_n * (t * t * t) : 0.f;
+    }
+    if (kind == 2) {
+        const float t = h - r;
+        return r <= h ? C.spiky_n * (t * t * t) : 0.f;
+    }
+    if (kind == 3) {
+        if (!(r > 0.f && r <= h)) return 0.f;
+        const float rr_hh = __fdiv_rn(r * r, h * h);
+        return C.visc_n * (rr_hh * (1.0f - __fdiv_rn(r, 2.0f * h)) + __fdiv_rn(h, 2.0f * r) - 1.0f);
+    }
+    return kernel_w(r);
+}
+__device__ __forceinline__ float kernel_dw_kind(int kind, float r) {  // scalar_apply_diff
+    const float h = C.h;
+    if (kind == 1) {
+        const float t = h * h - r * r;
+        return r <= h ? C.poly6_n * (t * t) * r * -6.0f : 0.f;
+    }
+    if (kind == 2) {
+        const float t = h - r;
+        return r <= h ? -C.spiky_n * (t * t) * 3.0f : 0.f;
+    }
+    if (kind == 3) {
+        if (!(r > 0.f && r <= h)) return 0.f;
+        const float rr = r * r, hh = h * h;
+        return C.visc_n * (__fdiv_rn(-3.0f * rr, 2.0f * (hh * h)) + __fdiv_rn(2.0f * r, hh) - __fdiv_rn(h, 2.0f * rr));
+    }
+    const float q = __fdiv_rn(r, h);  // cubic_spline_kernel.rs:55-80
+    const float t = 1.0f - q;
+    const float rhs = (q > 1.0f || q <= 1.0e-5f) ? 0.f : (q <= 0.5f ? (q * 3.0f - 2.0f) * q * 6.0f : -t * t * 6.0f);
+    return __fdiv_rn(C.sigma * rhs, h);
+}
+
+#ifndef SPH_GENERIC_KERNELS
+#define SPH_GENERIC_KERNELS 1   // 0 compiles the non-default kernels out (A/B builds measuring what the uniform branch costs)
+#endif
+__device__ __forceinline__ float2 pair_generic(float d2, int need_w, int need_g) {
+    const float r = __fsqrt_rn(d2);
+    float2 o;
+    o.x = need_w ? kernel_w_kind(C.kw, r) : 0.f;
+    o.y = (need_g && d2 > F32_EPS * F32_EPS) ? __fdiv_rn(kernel_dw_kind(C.kg, r), r) : 0.f;
+    return o;
+}
+
 struct Pair {        // geometry of one (i, j) contact
     float dx, dy, dz;  // x_i - x_j
     float d2, r;
     float w;           // contact.weight
     float g;           // contact.gradient = g * (dx, dy, dz)
 };
-template <bool NEED_W, bool NEED_G>
+// CUBIC_ONLY: force plugins with their OWN kernel type parameters (Becker2009Elasticity<CubicSplineKernel, ..>) do not
+// follow the solver's kernels.
+template <bool NEED_W, bool NEED_G, bool CUBIC_ONLY = false>
 __device__ __forceinline__ Pair make_pair(const float4& pi, const float4& pj) {
     Pair p;
     p.dx = pi.x - pj.x;
     p.dy = pi.y - pj.y;
     p.dz = pi.z - pj.z;
     p.d2 = fmaf(p.dz, p.dz, fmaf(p.dy, p.dy, p.dx * p.dx));
+    if (SPH_GENERIC_KERNELS && !CUBIC_ONLY && C.kgen) {  // non-default solver kernels: uniform branch, off the default path
+        const float2 o = pair_generic(p.d2, NEED_W, NEED_G);
+        p.r = __fsqrt_rn(p.d2);
+        p.w = o.x;
+        p.g = o.y;
+        return p;
+    }
 #if SPH_FAST_PAIR
     // Lean evaluation (about half the instructions of the guarded one below): contacts come from lists built with
     // d^2 <= h^2, so q <= 1 up to rounding (where (1 - q)^2 ~ 1e-14 anyway), and the two "zero gradient" guards of the
@@ -525,7 +589,7 @@ k_boundary_volumes(const float4* __restrict__ bpos, const float4* __restrict__ b
                     if (d2 <= C.h2) {
                         uint32_t bj = fid_of(__ldg(&bvel[j]));
                         if (bi == bj || groups_test(C.bounds[bi].memberships, C.bounds[bi].filter, C.bounds[bj].memberships, C.bounds[bj].filter)) {
-                            den += kernel_w(sqrtf(d2));
+                            den += C.kgen ? kernel_w_kind(C.kw, __fsqrt_rn(d2)) : kernel_w(sqrtf(d2));
                             ++cnt;
                         }
                     }

@@ -40,11 +40,32 @@ class InteractionGroups:
         return (self.memberships & rhs.filter) != 0 and (rhs.memberships & self.filter) != 0
 
 
-class DFSPHSolver:
-    """dfsph_solver.rs:54-70 defaults."""
+class CubicSplineKernel:
+    """kernel/cubic_spline_kernel.rs"""
     kind = 0
 
-    def __init__(self):
+
+class Poly6Kernel:
+    """kernel/poly6_kernel.rs"""
+    kind = 1
+
+
+class SpikyKernel:
+    """kernel/spiky_kernel.rs"""
+    kind = 2
+
+
+class ViscosityKernel:
+    """kernel/viscosity_kernel.rs"""
+    kind = 3
+
+
+class DFSPHSolver:
+    """dfsph_solver.rs:54-70 defaults; DFSPHSolver<KernelDensity, KernelGradient> (dfsph_solver.rs:17-20) as constructor arguments."""
+    kind = 0
+
+    def __init__(self, kernel_density=CubicSplineKernel, kernel_gradient=CubicSplineKernel):
+        self.kernel_density, self.kernel_gradient = kernel_density.kind, kernel_gradient.kind
         self.min_pressure_iter, self.max_pressure_iter, self.max_density_error = 1, 50, 0.05
         self.min_divergence_iter, self.max_divergence_iter, self.max_divergence_error = 1, 50, 0.1
         self.omega = 0.5
@@ -230,6 +251,8 @@ class LiquidWorld:
         d.deterministic = int(deterministic)
         d.slab_rank, d.slab_count = slab_rank, slab_count
         d.gather_backend = gather_backend
+        d.kernel_density = getattr(solver, "kernel_density", 0)
+        d.kernel_gradient = getattr(solver, "kernel_gradient", 0)
         self._w = C.c_void_p()
         st = self._L.sph_world_create(C.byref(d), C.byref(self._w))
         if st != 0:
@@ -501,6 +524,18 @@ class LiquidWorld:
         a = np.empty(n, np.uint32)
         self._ck(self._L.sph_fluid_read_ids(self._w, fluid, a.ctypes.data_as(C.POINTER(C.c_uint32)), n))
         return a
+
+    def replace_particles(self, fluid, positions, velocities=None, velocity_changes=None, ids=None):
+        """Replace a fluid's whole particle set (slab re-balancing: particles change rank wholesale)."""
+        p = _f32(positions, (-1, 3))
+        v = _f32(velocities, (-1, 3))
+        c = _f32(velocity_changes, (-1, 3))
+        i = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        ip = None if i is None else i.ctypes.data_as(C.POINTER(C.c_uint32))
+        self._ck(self._L.sph_fluid_replace_particles(self._w, fluid, _fp(p), _fp(v), _fp(c), ip, len(p)))
+
+    def set_slab(self, cell_lo, cell_hi):
+        self._ck(self._L.sph_world_set_slab(self._w, int(cell_lo), int(cell_hi)))
 
     def init_slab(self, unique_id, rank, nranks, cell_lo, cell_hi):
         """Join the slab decomposition: `unique_id` is the 128-byte NCCL id rank 0 got from nccl_unique_id()."""

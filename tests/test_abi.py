@@ -28,7 +28,7 @@ def test_header_symbols_are_all_bound_and_exported():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.WorldDesc) == 15 * 4
+    assert C.sizeof(_lib.WorldDesc) == 17 * 4
     assert C.sizeof(_lib.ForceDesc) == 4 + 8 * 4
     assert C.sizeof(_lib.StepStats) == 12 * 4 + 4 * 4 + 2 * 4 + 3 * 8 + 4 + 3 * 4 + 8 + 4 * 4
 

@@ -300,3 +300,28 @@ def test_aabb_query_accepts_infinite_and_rejects_nan_bounds():
         assert (kinds == 1).sum() == len(sc["boundaries"][0]["positions"])
     with pytest.raises(Exception):
         w.particles_intersecting_aabb((np.nan, 0, 0), (1, 1, 1))
+
+
+@pytest.mark.parametrize("kd,kg,solver", [(1, 2, 0), (2, 2, 0), (3, 1, 0), (1, 2, 1)], ids=["poly6+spiky", "spiky+spiky", "viscosity+poly6", "iisph-poly6+spiky"])
+def test_non_default_solver_kernels_match_oracle(kd, kg, solver):
+    """DFSPHSolver<KernelDensity, KernelGradient> / IISPHSolver<..> (dfsph_solver.rs:17-20, iisph_solver.rs:17-20)."""
+    from salva_b200.liquid_world import CubicSplineKernel, Poly6Kernel, SpikyKernel, ViscosityKernel
+    K = {0: CubicSplineKernel, 1: Poly6Kernel, 2: SpikyKernel, 3: ViscosityKernel}
+    sc = _scene(37, forces=(scenes.xsph_viscosity(0.5, 0.2),))
+    S = DFSPHSolver if solver == 0 else IISPHSolver
+    gpu = LiquidWorld(S(K[kd], K[kg]), particle_radius=sc["particle_radius"])
+    cpu = OracleWorld(sc["particle_radius"], 2.0, solver=solver, kernel_density=kd, kernel_gradient=kg)
+    (fg,), _ = scenes.populate(gpu, sc)
+    (fc,), _ = scenes.populate(cpu, sc)
+    for w in (gpu, cpu):
+        w.force_iterations(2, 3)
+    for _ in range(4):
+        gpu.step(sc["dt"])
+        cpu.step(sc["dt"])
+    rg, rc = gpu.debug(fg, "density"), cpu.debug(fc, "density")
+    assert np.abs(rg - rc).max() <= 1e-5 * np.abs(rc).max()
+    pg, vg = gpu.read_fluid(fg)
+    pc, vc = cpu.read_fluid(fc)
+    h = float(gpu.h)
+    assert np.abs(pg - pc).max() <= 1e-3 * h
+    assert np.abs(vg - vc).max() <= 1e-3 * h / sc["dt"]

@@ -143,3 +143,20 @@ def test_particles_intersecting_aabb_matches_brute_force():
     want = _aabb_brute_force(w.h, r, mins, maxs, [(0, f, before, now), (1, b, floor, floor)])
     assert got == want
     assert 20 < sum(1 for e in got if e[0] == 0) < len(pts) and any(e[0] == 1 for e in got)
+
+
+def test_non_default_kernels_are_normalised_and_consistent():
+    """kernel/poly6_kernel.rs, spiky_kernel.rs, viscosity_kernel.rs (dim3): each integrates to 1 over its support and
+    scalar_apply_diff is the derivative of scalar_apply (the analytic pin of the oracle's restatement of them)."""
+    from oracle.oracle import lib
+    L = lib()
+    h = 0.2
+    r = np.linspace(1e-4, h, 4001)
+    for kind in (1, 2, 3):
+        W = np.array([L.orc_kernel_w_kind(kind, float(x), h) for x in r], np.float64)
+        dW = np.array([L.orc_kernel_dw_kind(kind, float(x), h) for x in r], np.float64)
+        assert abs(np.trapezoid(4 * np.pi * r * r * W, r) - 1.0) < 2e-3
+        num = np.gradient(W, r)
+        assert np.abs(dW - num)[5:-5].max() <= 2e-2 * np.abs(dW).max()
+        assert L.orc_kernel_w_kind(kind, 1.01 * h, h) == 0.0 and L.orc_kernel_dw_kind(kind, 1.01 * h, h) == 0.0
+    assert L.orc_kernel_w_kind(3, 0.0, h) == 0.0      # viscosity kernel: `r > 0` guard (viscosity_kernel.rs:24)

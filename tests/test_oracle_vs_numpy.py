@@ -141,3 +141,26 @@ def test_iisph_steps_match(two):
             assert np.abs(po - pn).max() < 1e-4 * float(o.h)
             assert np.allclose(o.debug(a, "pressure"), n.press[off:off + cnt], rtol=2e-3, atol=1e-2)
             off += cnt
+
+
+@pytest.mark.parametrize("kd,kg", [(1, 2), (2, 2), (0, 3), (3, 1)], ids=["poly6+spiky", "spiky+spiky", "cubic+viscosity", "viscosity+poly6"])
+def test_non_default_solver_kernels_match_dense_restatement(kd, kg):
+    """DFSPHSolver<KernelDensity, KernelGradient> (dfsph_solver.rs:17-20) with Poly6 / Spiky / Viscosity kernels
+    (kernel/poly6_kernel.rs, spiky_kernel.rs, viscosity_kernel.rs): every contact weight / gradient of the step follows
+    the type parameters (helper.rs:24-25), in the list-based oracle and in the dense numpy restatement alike."""
+    sc = _scene(7, forces=(scenes.xsph_viscosity(0.5, 0.3),))
+    o = OracleWorld(sc["particle_radius"], 2.0, kernel_density=kd, kernel_gradient=kg)
+    n = NumpyDFSPH(sc["particle_radius"], 2.0, kernel_density=kd, kernel_gradient=kg)
+    fo = _run(o, sc, 3, 2, 3)
+    fn = _run(n, sc, 3, 2, 3)
+    po, vo = o.read_fluid(fo[0])
+    pn, vn = n.read_fluid(fn[0])
+    h = float(o.h)
+    assert np.allclose(o.debug(fo[0], "density"), n.dens, rtol=2e-5)
+    assert np.allclose(o.debug(fo[0], "alpha"), n.alpha, rtol=1e-4, atol=1e-12)
+    assert np.abs(po - pn).max() < 1e-4 * h
+    assert np.abs(vo - vn).max() < 1e-4 * h / 0.005 * 10
+    # and the kernels really differ from the default ones
+    d = OracleWorld(sc["particle_radius"], 2.0)
+    fd = _run(d, sc, 1, 2, 3)
+    assert np.abs(d.debug(fd[0], "density") - o.debug(fo[0], "density")).max() > 1.0 or kd == 0

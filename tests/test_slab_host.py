@@ -65,3 +65,64 @@ def test_unique_id_broadcast_and_partition_under_gloo_world_size_2(tmp_path):
     assert all(o["uid_ok"] for o in outs)
     assert outs[0]["total"] == outs[1]["total"] == 16 ** 3 == outs[0]["n"] + outs[1]["n"]
     assert outs[0]["slab"][1] == outs[1]["slab"][0]
+
+
+def test_rebalance_redistribution_under_gloo_world_size_2(tmp_path):
+    """Plane re-balancing: the host logic — global column histogram, new planes, all-to-all of the particle
+    state — as a real 2-rank gloo job: particles are conserved (ids), every particle lands on the owner of its column and the
+    counts end up balanced to a cell column."""
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent("""
+        import os, sys, json
+        sys.path.insert(0, %r)
+        import numpy as np
+        import torch.distributed as dist
+        from salva_b200 import scenes, slab
+        dist.init_process_group("gloo")
+        rank, ws = dist.get_rank(), dist.get_world_size()
+        sc = scenes.scene_c2(16)
+        pos = sc["fluids"][0]["positions"]
+        h = np.float32(0.1)
+        cols = slab.cell_columns(pos, h)
+        # a deliberately bad split: rank 0 owns 1/4 of the columns
+        cut = int(cols.min()) + (int(cols.max()) + 1 - int(cols.min())) // 4
+        mine = (cols < cut) if rank == 0 else (cols >= cut)
+        ids = np.nonzero(mine)[0].astype(np.uint32)
+        p = pos[mine]
+        v = (p * 2).astype(np.float32)
+        c = (p * 3).astype(np.float32)
+        imb, counts = slab.imbalance(len(p))
+        p2, v2, c2, i2, planes = slab.redistribute(p, v, c, ids, h)
+        own = slab.owned_mask(p2, h, planes[rank], planes[rank + 1])
+        out = dict(rank=rank, imb=imb, n_before=int(len(p)), n_after=int(len(p2)), all_owned=bool(own.all()),
+                   payload_ok=bool(np.array_equal(v2, (p2 * 2).astype(np.float32)) and np.array_equal(c2, (p2 * 3).astype(np.float32))
+                                   and np.array_equal(p2, pos[i2])), ids=i2.tolist(), planes=[int(x) for x in planes])
+        json.dump(out, open(os.path.join(%r, "rb%%d.json" %% rank), "w"))
+        dist.destroy_process_group()
+    """ % (ROOT, str(tmp_path))))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    outs = [json.load(open(tmp_path / ("rb%d.json" % k))) for k in range(2)]
+    assert outs[0]["imb"] > 0.3 and outs[0]["imb"] == outs[1]["imb"]
+    assert all(o["all_owned"] and o["payload_ok"] for o in outs)
+    assert sorted(outs[0]["ids"] + outs[1]["ids"]) == list(range(16 ** 3))
+    assert outs[0]["planes"] == outs[1]["planes"]
+    n = np.array([o["n_after"] for o in outs], float)
+    assert n.max() / n.mean() - 1.0 <= 0.15
+
+
+def test_planes_from_histogram_matches_slab_planes():
+    sc = scenes.scene_c2(20)
+    h = np.float32(0.1)
+    pos = sc["fluids"][0]["positions"]
+    cols = slab.cell_columns(pos, h)
+    lo = int(cols.min())
+    hist = np.bincount(cols - lo)
+    for nranks in (2, 3, 4):
+        assert slab.planes_from_histogram(hist, lo, nranks) == slab.slab_planes(pos, h, nranks)
