@@ -113,6 +113,8 @@ struct SlabArray {
 };
 sph_status slab_refresh_n(sph_world* w, const SlabArray* arrays, int n_arrays, cudaStream_t st = nullptr);
 sph_status slab_wait(sph_world* w);
+sph_status p2p_setup(sph_world* w);
+sph_status post_density_refresh(sph_world* w);
 sph_status slab_allreduce(sph_world* w, float* buf, size_t n);
 void iisph_release(sph_world* w);
 void slab_release(sph_world* w);
@@ -128,8 +130,18 @@ inline float __uint_as_float_host(uint32_t u) {
     return f;
 }
 
+struct P2PState {  // NVLink peer-memory exchange (sph_slab.inl)
+    bool on = false;
+    size_t box_bytes = 0;
+    char* base = nullptr;          // my landing zones + flags + reduction table (one cudaIpc-exported allocation)
+    char* peer_base[8] = {};       // the same allocation of every rank, mapped into this process ([rank] == base)
+    uint32_t seq_send[2] = {0, 0}, seq_recv[2] = {0, 0}, red_seq = 0;
+    DBuf<uint32_t> tickets;
+};
+
 struct SlabState {
     bool active = false, own_comm = false;
+    P2PState p2p;
     int rank = 0, nranks = 1;
     int lo = INT_MIN, hi = INT_MAX;  // owned cell columns [lo, hi) in absolute cell coordinates floor(x / h)
     int has_left = 0, has_right = 0;
@@ -212,8 +224,9 @@ struct sph_world {
     int uni_eval_mode = 1, uni_upd_mode = 1;  // 1: position record through the texture pipe, 2: through the LSU pipe
     DBuf<float4> pvx4, pk4;
     DBuf<float2> vyz2;
-    DBuf<Rec8> rec8;      // 256-bit gather records (pos, v*, rho) of the pressure-loop evaluations (sph_kernels.cuh Rec8)
-    int use_rec8 = 0;
+    DBuf<Rec8> rec8, nrec8;  // 256-bit gather records: (pos, v*, rho) of the evaluations, (pos, normal, rho) of the Akinci force pass
+    int use_rec8 = 0;        // 0: off, 1: pressure-loop evaluations, 2: every evaluation of the step (+ fused XSPH / Akinci normals)
+    bool nrec_valid = false;
     cudaTextureObject_t tex_pvx = 0, tex_vyz = 0, tex_pk = 0;
     const void* tex_pvx_ptr = nullptr;
     const void* tex_vyz_ptr = nullptr;
@@ -315,6 +328,10 @@ inline int boundary_slot(const sph_world* w, uint32_t handle) {
     const int var##_slot_ = boundary_slot(w, handle);                                                   \
     if (var##_slot_ < 0) return w->fail(SPH_ERR_INVALID, "bad boundary handle %u", (unsigned)(handle)); \
     const uint32_t var = (uint32_t)var##_slot_;
+
+// 256-bit gather records for EVERY evaluation of the step (SALVA_B200_REC8=2): single-fluid uniform-mass DFSPH on one GPU
+inline bool rec8_full(const sph_world* w) { return w->use_rec8 >= 2 && w->unimass && !w->slab.active && !w->tile && !w->use_gcache; }
+inline bool rec8_predict(const sph_world* w) { return w->use_rec8 >= 1 && w->unimass && !w->slab.active && !w->tile; }
 
 enum { SP_DIV_EVAL = 0, SP_DIV_UPD, SP_PRED, SP_PUPD, SP_COUNT };
 sph_status span_begin(sph_world* w, int slot) {
@@ -735,7 +752,7 @@ sph_status phase_grid(sph_world* w) {
         LAUNCH(k_gather, N, 256, (uint32_t)N, w->perm.p, g);
         w->cur = c ^ 1;
         LAUNCH(k_make_vstar, N, 256, w->vel[w->cur].p, w->vc[w->cur].p, w->vs.p, w->pos[w->cur].p, w->unimass ? w->pvx4.p : nullptr,
-               w->unimass ? w->vyz2.p : nullptr);
+               w->unimass ? w->vyz2.p : nullptr, rec8_full(w) ? w->rec8.p : nullptr);
     }
     // boundaries: same sort — reused while neither the boundaries nor the cell mapping changed (static tanks)
     const int gridkey[6] = {w->hc.ox, w->hc.oy, w->hc.oz, w->hc.nx, w->hc.ny, w->hc.nz};
@@ -862,9 +879,7 @@ sph_status phase_neighbors(sph_world* w, sph_status (*speculative)(sph_world*) =
         CU(cudaMemcpyAsync(hs, w->d_scal.p + 7, 4 * sizeof(int), cudaMemcpyDeviceToHost, w->st));
         CU(cudaEventRecord(w->ev_lists, w->st));
         CU(cudaEventRecord(w->ev[EV_NBR], w->st));
-        // (not in slab worlds: the density pass ends with a ghost exchange, and a rank that has to repeat it alone would
-        //  leave its neighbours waiting in a collective they never enter)
-        const bool early = speculative && !w->slab.active && !w->tile;  // (tile launches need this read-back's slot count)
+        const bool early = speculative && !w->tile;  // (tile launches need this read-back's slot count)
         if (early) TRY(speculative(w));
         CU(cudaEventSynchronize(w->ev_lists));
         if (hs[0]) return w->fail(SPH_ERR_ZERO_DENSITY, "zero boundary-volume denominator (reference assert dfsph_solver.rs:92)");
@@ -908,6 +923,7 @@ sph_status phase_neighbors(sph_world* w, sph_status (*speculative)(sph_world*) =
     }
     CU(cudaGetLastError());
     w->lists_valid = true;
+    if (speculative) TRY(post_density_refresh(w));
     return SPH_OK;
 }
 
@@ -1003,8 +1019,19 @@ sph_status launch_density_alpha(sph_world* w) {
         Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
         DISPATCH1(k_density_alpha, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->g_f.p, w->dens.p, w->alpha.p, w->d_scal.p + 7);
     }
-    TRY(slab_refresh(w, w->dens.p, sizeof(float)));  // XSPH / artificial viscosity / Akinci gather rho_j of ghosts
-    return SPH_OK;
+    return SPH_OK;  // the ghost refresh of rho follows in post_density_refresh(), once the list-capacity check has passed
+}
+// Ghost refresh of what the density pass produced (rho; DFSPH: also kappa of the fused first divergence evaluation).  Kept out
+// of the density launch itself so that the launch stays purely local: it is enqueued SPECULATIVELY behind the neighbour
+// search (before the host knows whether the lists overflowed), and a rank that has to regrow its lists and repeat it must not
+// leave its neighbours waiting in a collective they entered once and it enters twice.
+sph_status post_density_refresh(sph_world* w) {
+    if (!w->slab.active || !w->N) return SPH_OK;
+    if (w->fused_first_div) {
+        SlabArray a[2] = {{w->dens.p, sizeof(float)}, {w->unimass ? (void*)w->pk4.p : (void*)w->kappa.p, w->unimass ? sizeof(float4) : sizeof(float)}};
+        return slab_refresh_n(w, a, 2);
+    }
+    return slab_refresh(w, w->dens.p, sizeof(float));  // XSPH / artificial viscosity / Akinci gather rho_j of ghosts
 }
 // DFSPH: densities + alphas + the first divergence evaluation in one sweep (k_density_alpha_div)
 // Launch over a slot range with n = range count (kernels index rg.begin + thread)
@@ -1094,11 +1121,13 @@ sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
     if (w->unimass) TRY(ensure_tex(w, &w->tex_vyz, &w->tex_vyz_ptr, w->vyz2.p, w->vyz2.cap));
     else TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
     const size_t nf = std::max<size_t>(1, w->fluids.size());
-    SlabArray a[2] = {{w->dens.p, sizeof(float)}, {w->unimass ? (void*)w->pk4.p : (void*)w->kappa.p, w->unimass ? sizeof(float4) : sizeof(float)}};
-    sph_status rs = run_parts(w, a, 2, nblk, [&](Range rg, uint32_t blk) -> sph_status {
+    sph_status rs = run_parts(w, nullptr, 0, nblk, [&](Range rg, uint32_t blk) -> sph_status {
         float* partial = w->partial.p + (size_t)blk * nf;
         uint32_t* tk = w->single_launch ? w->d_ticket.p : nullptr;
-        if (w->unimass)
+        if (rec8_full(w))
+            LAUNCH_R(k_density_alpha_div_r8, rg, w->rec8.p, w->bpos[bc].p, L, w->dens.p, w->alpha.p, w->divv.p, w->pk4.p, partial, w->d_scal.p + 7, tk,
+                     w->errsum.p);
+        else if (w->unimass)
             LAUNCH_R((k_density_alpha_div<false, true>), rg, w->pvx4.p, w->vs.p, (cudaTextureObject_t)0, w->vyz2.p, w->tex_vyz, w->vel[c].p, w->bpos[bc].p, L,
                      w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7, tk, w->errsum.p);
         else if (multi)
@@ -1123,6 +1152,14 @@ bool xsph_fusable(const sph_world* w) {
     if (w->fluids.size() != 1 || w->fluids[0].forces.empty()) return false;
     const sph_force_desc& d = w->fluids[0].forces[0].d;
     return d.kind == SPH_FORCE_XSPH_VISCOSITY && d.p[0] != 0.f && (d.p[1] == 0.f || w->B == 0);
+}
+// Akinci2013 normals (positions + densities only) can ride with any stand-alone divergence evaluation of the step when the
+// evaluations gather the 256-bit records (rho_j comes with them): k_vel_divergence_r8<false, 2>.
+bool akinci_fusable(const sph_world* w) {
+    if (!rec8_full(w) || w->fluids.size() != 1) return false;
+    int n_akinci = 0;
+    for (const ForceRec& fr : w->fluids[0].forces) n_akinci += fr.d.kind == SPH_FORCE_AKINCI2013_TENSION;
+    return n_akinci >= 1;
 }
 
 sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, const int* gate = nullptr) {
@@ -1155,9 +1192,25 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
         uint32_t* tk = (w->single_launch && !gate) ? w->d_ticket.p : nullptr;
         if (w->unimass) {
             const bool ptex = w->uni_eval_mode == 1;
-            if (predict && w->use_rec8 && !w->slab.active && !gate) {
-                LAUNCH_R((k_vel_divergence_r8<true>), rg, w->rec8.p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt,
-                         w->d_scal.p + 7, tk, w->errsum.p);
+            if (predict && rec8_predict(w) && !gate) {
+                LAUNCH_R((k_vel_divergence_r8<true, 0>), rg, w->rec8.p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt,
+                         w->d_scal.p + 7, tk, w->errsum.p, (float4*)nullptr, 0.f, (Rec8*)nullptr);
+            } else if (!predict && rec8_full(w) && !gate) {
+                const float cf = xsf ? w->fluids[0].forces[0].d.p[0] : 0.f;
+                const bool akn = !xsf && akinci_fusable(w);
+                if (akn) CU(w->nrec8.ensure(std::max(w->Ntot, w->N)));
+                if (xsf) {
+                    LAUNCH_R((k_vel_divergence_r8<false, 1>), rg, w->rec8.p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->alpha.p, out, w->pk4.p, partial,
+                             w->dt, w->d_scal.p + 7, tk, w->errsum.p, w->xs.p, cf, (Rec8*)nullptr);
+                    w->xs_valid = true;
+                } else if (akn) {
+                    LAUNCH_R((k_vel_divergence_r8<false, 2>), rg, w->rec8.p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->alpha.p, out, w->pk4.p, partial,
+                             w->dt, w->d_scal.p + 7, tk, w->errsum.p, (float4*)nullptr, 0.f, w->nrec8.p);
+                    w->nrec_valid = true;
+                } else {
+                    LAUNCH_R((k_vel_divergence_r8<false, 0>), rg, w->rec8.p, w->bpos[bc].p, w->bvel[bc].p, L, w->dens.p, w->alpha.p, out, w->pk4.p, partial,
+                             w->dt, w->d_scal.p + 7, tk, w->errsum.p, (float4*)nullptr, 0.f, (Rec8*)nullptr);
+                }
             } else if (predict) {
                 if (ptex) LAUNCH_R((k_vel_divergence_u<true, true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
                                    w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
@@ -1208,7 +1261,7 @@ sph_status launch_vel_update(sph_world* w, bool pressure, const int* gate = null
     return run_parts(w, w->unimass ? a : a1, w->unimass ? 3 : 1, nullptr, [&](Range rg, uint32_t) -> sph_status {
         if (w->unimass) {
             const bool ptex = w->uni_upd_mode == 1;
-            Rec8* rec = (pressure && w->use_rec8 && !w->slab.active && !gate) ? w->rec8.p : nullptr;
+            Rec8* rec = (!gate && ((pressure && rec8_predict(w)) || rec8_full(w))) ? w->rec8.p : nullptr;
             BOOL3(k_vel_update_u, bf, pressure, ptex, rg, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p,
                   rec, w->dens.p, w->bforce.p, w->inv_dt, gate);
         } else {
@@ -1379,6 +1432,11 @@ sph_status phase_forces(sph_world* w) {
                                    w->normals.p, w->acc.p, w->bforce.p, (uint32_t)f, p[0], p[1], coh_norm, h6_64, adh_norm);
                         break;
                     }
+                    if (w->nrec_valid && f == 0) {  // normals came with a divergence evaluation, in the one-gather record of the force pass
+                        if (bf) LAUNCH((k_akinci_force_r8<true>), N, PASS_T, w->nrec8.p, w->bpos[bc].p, L, w->acc.p, w->bforce.p, p[0], p[1], coh_norm, h6_64, adh_norm);
+                        else LAUNCH((k_akinci_force_r8<false>), N, PASS_T, w->nrec8.p, w->bpos[bc].p, L, w->acc.p, w->bforce.p, p[0], p[1], coh_norm, h6_64, adh_norm);
+                        break;
+                    }
                     DISPATCH1(k_akinci_normals, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->dens.p, w->normals.p, (uint32_t)f);
                     TRY(slab_refresh(w, w->normals.p, sizeof(float4)));
                     DISPATCH2(k_akinci_force, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->normals.p, w->acc.p,
@@ -1517,6 +1575,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     // divergence_solve :466-503 (uses the PREVIOUS step's inv_dt; 0 on the first step)
     w->stats.n_divergence_iter = w->stats.n_divergence_eval = 0;
     w->xs_valid = false;
+    w->nrec_valid = false;
     uint32_t maxit = w->force_div >= 0 ? (uint32_t)w->force_div + 1 : w->desc.max_divergence_iter;
     const bool dev_loops = w->device_loops && !w->tile;
     if (dev_loops && w->force_div < 0) {
@@ -1562,7 +1621,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     TRY(phase_forces(w));
     CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
     timestep_advance(w, dt_total);  // :702
-    const bool r8 = w->use_rec8 && w->unimass && !w->slab.active;
+    const bool r8 = rec8_predict(w);
     LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p, w->unimass ? w->pvx4.p : nullptr,
            w->unimass ? w->vyz2.p : nullptr, w->pos[c].p, r8 ? w->rec8.p : nullptr, w->dens.p);
     TRY(refresh_vstar(w));
@@ -1714,6 +1773,7 @@ sph_status world_step(sph_world* w, float dt, const float g[3], const sph_coupli
         w->stats.predict_density_ms = acc[SP_PRED];
         w->stats.pressure_update_ms = acc[SP_PUPD];
     }
+    if (flag & 2) return w->fail(SPH_ERR_NCCL, "peer-memory ghost exchange timed out (a neighbour rank never delivered its boundary column)");
     if (flag) return w->fail(SPH_ERR_ZERO_DENSITY, "zero density (reference asserts dfsph_solver.rs:92,145,662)");
     if (coupling && coupling->transmit_forces) coupling->transmit_forces(coupling->user, w, w->dt, w->inv_dt);  // liquid_world.rs:146
     return SPH_OK;
@@ -1820,7 +1880,7 @@ void sph_world_destroy(sph_world* w) {
         for (auto& fr : f.forces) elasticity_release(fr);
     for (cudaTextureObject_t t : {w->tex_pvx, w->tex_vyz, w->tex_pk})
         if (t) cudaDestroyTextureObject(t);
-    w->pvx4.release(); w->pk4.release(); w->vyz2.release(); w->rec8.release();
+    w->pvx4.release(); w->pk4.release(); w->vyz2.release(); w->rec8.release(); w->nrec8.release();
     if (w->tex_vs) cudaDestroyTextureObject(w->tex_vs);
     if (w->tex_kappa) cudaDestroyTextureObject(w->tex_kappa);
     for (auto& s : w->spans) {
@@ -2347,6 +2407,7 @@ static sph_status slab_attach(sph_world* w, void* comm, bool own, int rank, int 
         CU(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
     }
     if (const char* t = getenv("SALVA_B200_SLAB_OVERLAP")) S.overlap = atoi(t) != 0;
+    if (S.active) TRY(p2p_setup(w));
     return SPH_OK;
 }
 

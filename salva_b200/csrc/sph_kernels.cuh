@@ -683,13 +683,16 @@ __device__ __forceinline__ void st_rec8(Rec8* p, float x, float y, float z, floa
 
 // v* = vel + vc after the reorder (the divergence solve works on vel + vc carried over from the previous step, Appendix A.3.2)
 __global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __restrict__ vc, float4* __restrict__ vs, const float4* __restrict__ pos,
-                             float4* __restrict__ pvx, float2* __restrict__ vyz) {
+                             float4* __restrict__ pvx, float2* __restrict__ vyz, Rec8* __restrict__ rec) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C.n_fluid) return;
     float4 v = vel[i], c = vc[i];
     float sx = v.x + c.x, sy = v.y + c.y, sz = v.z + c.z;
     vs[i] = make_float4(sx, sy, sz, 0.f);
-    if (pvx) {  // uniform-mass packed records (sph_passes.cuh)
+    if (rec) {  // 256-bit gather records; rho is filled in by the first velocity update of the step
+        float4 p = pos[i];
+        st_rec8(rec + i, p.x, p.y, p.z, sx, sy, sz, 0.f);
+    } else if (pvx) {  // uniform-mass packed records (sph_passes.cuh)
         float4 p = pos[i];
         pvx[i] = make_float4(p.x, p.y, p.z, sx);
         vyz[i] = make_float2(sy, sz);
@@ -931,6 +934,127 @@ __global__ void k_export_u32(uint32_t n, const uint32_t* __restrict__ orig, cons
 __global__ void k_import_u32(uint32_t n, const uint32_t* __restrict__ orig, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n) dst[s] = src[orig[s]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ghost exchange over NVLink peer memory (sph_slab.inl).  Every rank maps its two neighbours' landing zones ("boxes",
+// cudaIpc) and the producer side WRITES its boundary columns straight into the neighbour's box with plain st.global
+// over NVLink, then publishes a sequence number (release, system scope); the consumer side spins on its own flag
+// (acquire, system scope) and copies box -> ghost slots.  No NCCL, no host involvement, ~10 us per exchange.
+// ------------------------------------------------------------------------------------------------
+struct P2PSeg {           // one contiguous array range travelling in a message
+    const char* src;      // sender: local source; receiver: unused
+    char* dst;            // receiver: local ghost range; sender: unused
+    uint32_t box_off;     // byte offset inside the box (16-byte aligned)
+    uint32_t bytes;       // multiple of 4
+};
+struct P2PMsg {           // one direction (to / from one neighbour)
+    char* box;            // sender: the NEIGHBOUR's box (peer pointer); receiver: my own box
+    uint32_t* flag;       // sender: the neighbour's flag (peer pointer); receiver: my own flag
+    P2PSeg seg[4];
+    int n_seg;
+    uint32_t total_words;  // sum of bytes / 4
+};
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// bounded spin (a peer that never arrives must not hang the GPU): ~4 s of SM clock, then the error flag
+__device__ __forceinline__ bool p2p_wait(const uint32_t* flag, uint32_t seq, int* err) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+        if (clock64() - t0 > 8000000000LL) {
+            atomicOr(err, 2);
+            return false;
+        }
+        __nanosleep(64);
+    }
+    return true;
+}
+// blockIdx.y = direction (0: left neighbour, 1: right neighbour)
+__global__ void k_p2p_push(P2PMsg m0, P2PMsg m1, uint32_t seq0, uint32_t seq1, uint32_t* __restrict__ tickets) {
+    const P2PMsg& m = blockIdx.y ? m1 : m0;
+    if (!m.box) return;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (int s = 0; s < m.n_seg; ++s) {
+        const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(m.seg[s].src);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(m.box + m.seg[s].box_off);
+        const uint32_t nw = m.seg[s].bytes >> 2;
+        const uint32_t n4 = nw >> 2;  // ranges start 16-byte aligned on both sides whenever the element size is a multiple of 16
+        if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) d4[k] = s4[k];
+            for (uint32_t k = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; k < nw; k += stride) dst[k] = src[k];
+        } else {
+            for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nw; k += stride) dst[k] = src[k];
+        }
+    }
+    __threadfence_system();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&tickets[blockIdx.y], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        tickets[blockIdx.y] = 0;
+        __threadfence_system();
+        st_release_sys(m.flag, blockIdx.y ? seq1 : seq0);
+    }
+}
+__global__ void k_p2p_pull(P2PMsg m0, P2PMsg m1, uint32_t seq0, uint32_t seq1, int* __restrict__ err) {
+    const P2PMsg& m = blockIdx.y ? m1 : m0;
+    if (!m.box) return;
+    __shared__ bool ok;
+    if (threadIdx.x == 0) ok = p2p_wait(m.flag, blockIdx.y ? seq1 : seq0, err);
+    __syncthreads();
+    if (!ok) return;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (int s = 0; s < m.n_seg; ++s) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(m.box + m.seg[s].box_off);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(m.seg[s].dst);
+        const uint32_t nw = m.seg[s].bytes >> 2;
+        const uint32_t n4 = nw >> 2;
+        if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) d4[k] = __ldcv(&s4[k]);  // written by a peer: bypass L1
+            for (uint32_t k = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; k < nw; k += stride) dst[k] = __ldcv(&src[k]);
+        } else {
+            for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nw; k += stride) dst[k] = __ldcv(&src[k]);
+        }
+    }
+}
+// All-ranks sum of a few floats (Jacobi error means) through peer memory: rank r writes its values into slot r of EVERY
+// rank's table, publishes, waits for all slots and sums them in rank order (deterministic, same result on every rank).
+struct P2PPeers {
+    float* red[8];         // red[p]: rank p's table  [buf][rank][MAX_FLUIDS]
+    uint32_t* red_flag[8]; // rank p's flags          [buf][rank]
+};
+__global__ void k_p2p_allreduce(float* __restrict__ vals, int n, int rank, int nranks, P2PPeers P, uint32_t seq, int* __restrict__ err) {
+    const int buf = (int)(seq & 1u);
+    const int t = threadIdx.x;
+    // thread (p, f): write vals[f] into rank p's table
+    for (int k = t; k < nranks * n; k += blockDim.x) {
+        const int p = k / n, f = k % n;
+        P.red[p][((size_t)buf * 8 + rank) * MAX_FLUIDS + f] = vals[f];
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int p = t; p < nranks; p += blockDim.x) st_release_sys(&P.red_flag[p][buf * 8 + rank], seq);
+    __shared__ int ok;
+    if (t == 0) ok = 1;
+    __syncthreads();
+    for (int p = t; p < nranks; p += blockDim.x)
+        if (!p2p_wait(&P.red_flag[rank][buf * 8 + p], seq, err)) ok = 0;
+    __syncthreads();
+    if (!ok) return;
+    for (int f = t; f < n; f += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < nranks; ++p) s += __ldcv(&P.red[rank][((size_t)buf * 8 + p) * MAX_FLUIDS + f]);
+        vals[f] = s;
+    }
 }
 
 // LiquidWorld::particles_intersecting_aabb liquid_world.rs:211-243 over HGrid::cells_intersecting_aabb hgrid.rs:122-133.

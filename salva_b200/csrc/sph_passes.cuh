@@ -533,11 +533,17 @@ k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, con
 // passes are bound by L1TEX wavefronts (one per distinct 128-byte line a warp-wide gather touches, ~8 per instruction,
 // profiles/r1_*), not by bytes: halving the gather instructions per contact is what moves them.
 // ------------------------------------------------------------------------------------------------
-template <bool PREDICT>
-__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
+// EXTRA selects what rides with a stand-alone divergence evaluation (PREDICT = false only):
+//   1: the fluid term of XSPHViscosity::solve (xsph_viscosity.rs:52-69; valid when this is the loop's LAST evaluation, see
+//      k_vel_divergence_xsph_u) -> xs;   2: Akinci2013 compute_normals (akinci2013_surface_tension.rs:43-68: positions and
+//      densities only, so ANY evaluation of the step may produce them) -> nrec = (x, y, z, n_x, n_y, n_z, rho, -), the
+//      one-gather record of the force pass.  rho_j comes with the record: no extra gather.
+template <bool PREDICT, int EXTRA>
+__global__ void __launch_bounds__(PASS_T, EXTRA ? SPH_FORCE_MINB : SPH_PASS_MINB)  // the extra sums spill at 56 registers
 k_vel_divergence_r8(const Rec8* __restrict__ rec, const float4* __restrict__ bpos, const float4* __restrict__ bvel, Lists L, const float* __restrict__ dens,
                     const float* __restrict__ alpha, float* __restrict__ out, float4* __restrict__ pk4, float* __restrict__ partial, float dt,
-                    int* __restrict__ err, uint32_t* __restrict__ ticket, float* __restrict__ errsum, Range rg) {
+                    int* __restrict__ err, uint32_t* __restrict__ ticket, float* __restrict__ errsum, float4* __restrict__ xs, float cf,
+                    Rec8* __restrict__ nrec, Range rg) {
     __shared__ float sm[32];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < rg.count;
@@ -549,8 +555,9 @@ k_vel_divergence_r8(const Rec8* __restrict__ rec, const float4* __restrict__ bpo
         const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
         const float vix = a.w, viy = b.x, viz = b.y;
         const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
-        float d = 0.f;
-        if (PREDICT || L.cnt_f[i] + L.cnt_b[i] >= 20u) {
+        float d = 0.f, ex = 0.f, ey = 0.f, ez = 0.f;
+        const bool gated = !PREDICT && L.cnt_f[i] + L.cnt_b[i] < 20u;  // dfsph_solver.rs:301-314
+        if (!gated || EXTRA) {
             const uint32_t n = min(L.cnt_f[i], C.cap_f);
             const uint32_t nq = (n + 3u) >> 2;
             const uint4* col = L.nbr_f + i;
@@ -563,23 +570,32 @@ k_vel_divergence_r8(const Rec8* __restrict__ rec, const float4* __restrict__ bpo
 #pragma unroll
                 for (int u = 0; u < 4; ++u) ld_rec8(rec + j[u], pj[u], wj[u]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {  // padded tail slots are self contacts: zero gradient
-                    Pair p = make_pair<false, true>(pi, pj[u]);
+                for (int u = 0; u < 4; ++u) {  // padded tail slots are self contacts: zero gradient, zero velocity difference
+                    Pair p = make_pair<EXTRA == 1, true>(pi, pj[u]);
                     float dv = (vix - pj[u].w) * p.dx + (viy - wj[u].x) * p.dy + (viz - wj[u].y) * p.dz;
                     d = fmaf(dv * p.g, mass, d);
+                    if (EXTRA == 1) {
+                        float c = cf * p.w * mass / wj[u].z;  // coeff * W * (vol_j * rho0) / rho_j
+                        ex = fmaf(c, pj[u].w - vix, ex); ey = fmaf(c, wj[u].x - viy, ey); ez = fmaf(c, wj[u].y - viz, ez);
+                    } else if (EXTRA == 2) {
+                        float c = p.g * (mass / wj[u].z);
+                        ex = fmaf(c, p.dx, ex); ey = fmaf(c, p.dy, ey); ez = fmaf(c, p.dz, ez);
+                    }
                 }
                 J = Jn;
             }
-            for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
-                float dv;
-                if (PREDICT) {
-                    float4 vj = __ldg(&bvel[j]);
-                    dv = (vix - vj.x) * p.dx + (viy - vj.y) * p.dy + (viz - vj.z) * p.dz;
-                } else {
-                    dv = vix * p.dx + viy * p.dy + viz * p.dz;
-                }
-                d = fmaf(dv * p.g, pj.w * rho0, d);
-            });
+            if (gated) d = 0.f;
+            else
+                for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+                    float dv;
+                    if (PREDICT) {
+                        float4 vj = __ldg(&bvel[j]);
+                        dv = (vix - vj.x) * p.dx + (viy - vj.y) * p.dy + (viz - vj.z) * p.dz;
+                    } else {
+                        dv = vix * p.dx + viy * p.dy + viz * p.dz;
+                    }
+                    d = fmaf(dv * p.g, pj.w * rho0, d);
+                });
         }
         float kap;
         if (PREDICT) {
@@ -595,8 +611,134 @@ k_vel_divergence_r8(const Rec8* __restrict__ rec, const float4* __restrict__ bpo
             e = d / rho0;
         }
         pk4[i] = make_float4(a.x, a.y, a.z, kap);
+        if (EXTRA == 1) xs[i] = make_float4(ex, ey, ez, 0.f);
+        if (EXTRA == 2) st_rec8(nrec + i, a.x, a.y, a.z, ex * C.h, ey * C.h, ez * C.h, b.z);
     }
     reduce_error<false>(e, 0u, valid, partial, sm, ticket, errsum);
+}
+
+// K3 + first K4a on the 256-bit records (k_density_alpha_div with ONE gather per contact).
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
+k_density_alpha_div_r8(const Rec8* __restrict__ rec, const float4* __restrict__ bpos, Lists L, float* __restrict__ dens, float* __restrict__ alpha,
+                       float* __restrict__ divv, float4* __restrict__ pk4, float* __restrict__ partial, int* __restrict__ err, uint32_t* __restrict__ ticket,
+                       float* __restrict__ errsum, Range rg) {
+    __shared__ float sm[32];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < rg.count;
+    i += rg.begin;
+    float e = 0.f;
+    if (valid) {
+        float4 a, b;
+        ld_rec8(rec + i, a, b);
+        const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
+        const float vix = a.w, viy = b.x, viz = b.y;
+        const float rho0 = C.fluids[0].density0, umass = C.fluids[0].mass;
+        float rho = 0.f, sq = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, d = 0.f;
+        const uint32_t n = min(L.cnt_f[i], C.cap_f);
+        const uint32_t nq = (n + 3u) >> 2;
+        const uint4* col = L.nbr_f + i;
+        uint4 J = nq ? ld_list(col) : make_uint4(i, i, i, i);
+        for (uint32_t q = 0; q < nq; ++q) {
+            uint4 Jn = J;
+            if (q + 1 < nq) Jn = ld_list(col + (size_t)(q + 1) * C.stride);
+            const uint32_t j[4] = {J.x, J.y, J.z, J.w};
+            float4 pj[4], wj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ld_rec8(rec + j[u], pj[u], wj[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (q * 4u + u < n) {  // tail slots point at i itself and would add W(0) again
+                    Pair p = make_pair<true, true>(pi, pj[u]);
+                    rho = fmaf(umass, p.w, rho);
+                    float s = p.g * umass;  // m_j * gradient
+                    float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
+                    sq += ax * ax + ay * ay + az * az;
+                    gx += ax; gy += ay; gz += az;
+                    float dv = (vix - pj[u].w) * p.dx + (viy - wj[u].x) * p.dy + (viz - wj[u].y) * p.dz;
+                    d = fmaf(dv * p.g, umass, d);
+                }
+            }
+            J = Jn;
+        }
+        for_boundary_contacts<true, true>(i, pi, L, bpos, [&](uint32_t, const Pair& p, const float4& pj) {
+            float mb = pj.w * rho0;  // boundary pseudo mass: vol_b * rho0_i
+            rho = fmaf(mb, p.w, rho);
+            float s = p.g * mb;
+            float ax = s * p.dx, ay = s * p.dy, az = s * p.dz;
+            sq += ax * ax + ay * ay + az * az;
+            gx += ax; gy += ay; gz += az;
+            float dv = vix * p.dx + viy * p.dy + viz * p.dz;  // boundary velocity ignored (dfsph_solver.rs:336-338)
+            d = fmaf(dv * p.g, mb, d);
+        });
+        if (rho == 0.f) atomicOr(err, 1);  // assert!(!density.is_zero()) dfsph_solver.rs:662
+        float den = sq + (gx * gx + gy * gy + gz * gz);
+        float al = den <= 1.0e-5f ? 0.f : 1.0f / den;  // dfsph_solver.rs:209-213
+        dens[i] = rho;
+        alpha[i] = al;
+        if (L.cnt_f[i] + L.cnt_b[i] < 20u) d = 0.f;  // min_neighbors_for_divergence_solve :62,301-314
+        d = fmaxf(d, 0.f);
+        divv[i] = d;
+        pk4[i] = make_float4(a.x, a.y, a.z, d * al);
+        e = d / rho0;
+    }
+    reduce_error<false>(e, 0u, valid, partial, sm, ticket, errsum);
+}
+
+// a14 pass 2 on the one-gather record nrec = (x, y, z, n_x, n_y, n_z, rho, -) written by k_vel_divergence_r8<false, 2>:
+// Akinci2013SurfaceTension::solve akinci2013_surface_tension.rs:113-192, single fluid.
+template <bool BFORCE>
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
+k_akinci_force_r8(const Rec8* __restrict__ nrec, const float4* __restrict__ bpos, Lists L, float4* __restrict__ acc, float* __restrict__ bforce, float gamma,
+                  float adh, float coh_norm, float h6_64, float adh_norm) {
+    SPH_OWNED_INDEX(i)
+    float4 a, b;
+    ld_rec8(nrec + i, a, b);
+    const float4 pi = make_float4(a.x, a.y, a.z, C.fluids[0].mass);
+    const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
+    const float nix = a.w, niy = b.x, niz = b.y, rho_i = b.z;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (gamma != 0.f) {
+        const uint32_t n = min(L.cnt_f[i], C.cap_f);
+        const uint32_t nq = (n + 3u) >> 2;
+        const uint4* col = L.nbr_f + i;
+        uint4 J = nq ? ld_list(col) : make_uint4(i, i, i, i);
+        for (uint32_t q = 0; q < nq; ++q) {
+            uint4 Jn = J;
+            if (q + 1 < nq) Jn = ld_list(col + (size_t)(q + 1) * C.stride);
+            const uint32_t j[4] = {J.x, J.y, J.z, J.w};
+            float4 pj[4], wj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ld_rec8(nrec + j[u], pj[u], wj[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (q * 4u + u < n) {
+                    Pair p = make_pair<false, false>(pi, pj[u]);
+                    // cohesion_vec = dir * C(dist) if |dpos|^2 > eps^2 (Unit::try_new_and_get)
+                    float coh = p.d2 > F32_EPS * F32_EPS ? cohesion_kernel(p.r, coh_norm, h6_64) / p.r : 0.f;
+                    float cm = coh * (-gamma * mass);
+                    float kij = 2.0f * rho0 / (rho_i + wj[u].z);
+                    ax += (-gamma * (nix - pj[u].w) + cm * p.dx) * kij;
+                    ay += (-gamma * (niy - wj[u].x) + cm * p.dy) * kij;
+                    az += (-gamma * (niz - wj[u].y) + cm * p.dz) * kij;
+                }
+            }
+            J = Jn;
+        }
+    }
+    if (adh != 0.f)
+        for_boundary_contacts<false, false>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+            float ad = p.d2 > F32_EPS * F32_EPS ? adhesion_kernel(p.r, adh_norm) / p.r : 0.f;
+            float c = ad * adh * (pj.w * rho0);
+            ax -= c * p.dx; ay -= c * p.dy; az -= c * p.dz;
+            if (BFORCE) {  // apply_force(c.j, adhesion_acc * m_i) :188
+                atomicAdd(&bforce[3 * (size_t)j + 0], c * p.dx * mass);
+                atomicAdd(&bforce[3 * (size_t)j + 1], c * p.dy * mass);
+                atomicAdd(&bforce[3 * (size_t)j + 2], c * p.dz * mass);
+            }
+        });
+    float4 o = acc[i];
+    o.x += ax; o.y += ay; o.z += az;
+    acc[i] = o;
 }
 
 // compute_divergences (a7) + the fluid term of XSPHViscosity::solve (a12, xsph_viscosity.rs:52-69) in ONE sweep.

@@ -25,12 +25,13 @@ struct NcclApi {
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
-constexpr int NCCL_CHAR = 0, NCCL_FLOAT = 7, NCCL_UINT64 = 5, NCCL_SUM = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+constexpr int NCCL_CHAR = 0, NCCL_INT = 2, NCCL_FLOAT = 7, NCCL_UINT64 = 5, NCCL_SUM = 0, NCCL_MIN = 3;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 bool nccl_load(std::string* err) {
     if (g_nccl.lib) return true;
@@ -54,6 +55,7 @@ bool nccl_load(std::string* err) {
     NSYM(Send, "ncclSend")
     NSYM(Recv, "ncclRecv")
     NSYM(AllReduce, "ncclAllReduce")
+    NSYM(AllGather, "ncclAllGather")
     NSYM(GroupStart, "ncclGroupStart")
     NSYM(GroupEnd, "ncclGroupEnd")
     NSYM(GetErrorString, "ncclGetErrorString")
@@ -68,8 +70,18 @@ bool nccl_load(std::string* err) {
         if (r_ != 0) return w->fail(SPH_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
     } while (0)
 
+void p2p_release(sph_world* w) {
+    P2PState& P = w->slab.p2p;
+    for (int p = 0; p < 8; ++p)
+        if (P.peer_base[p] && P.peer_base[p] != P.base) cudaIpcCloseMemHandle(P.peer_base[p]);
+    if (P.base) cudaFree(P.base);
+    P.tickets.release();
+    P = P2PState();
+}
+
 void slab_release(sph_world* w) {
     SlabState& S = w->slab;
+    p2p_release(w);
     if (S.comm && S.own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S.comm);
     S.comm = nullptr;
     if (S.comm_st) cudaStreamSynchronize(S.comm_st);
@@ -92,26 +104,175 @@ inline bool slab_on(const sph_world* w) { return w->slab.active; }
 inline int slab_left(const sph_world* w) { return w->slab.rank > 0 ? w->slab.rank - 1 : -1; }
 inline int slab_right(const sph_world* w) { return w->slab.rank + 1 < w->slab.nranks ? w->slab.rank + 1 : -1; }
 
-// Per-iteration ghost refresh of up to 4 per-particle arrays in ONE NCCL group (elem = bytes per particle): my boundary
-// columns go to the neighbours, their boundary columns land in my ghost ranges.  Contiguous ranges, no packing.
+// ---- NVLink peer-memory exchange (k_p2p_push / k_p2p_pull, sph_kernels.cuh) ---------------------------------------------
+// One device allocation per rank, exported with cudaIpc to every other rank of the node:
+//   [box L buf0 | box L buf1 | box R buf0 | box R buf1 | 16 flags | reduction table 2 x 8 x MAX_FLUIDS | reduction flags 2 x 8]
+// "box L" receives what my LEFT neighbour sends me.  Messages are double buffered by the parity of their sequence number
+// (a sender can run at most one exchange ahead of the receiver's copy-out).
+inline size_t p2p_off_flags(const P2PState& P) { return 4 * P.box_bytes; }
+inline size_t p2p_off_red(const P2PState& P) { return 4 * P.box_bytes + 256; }
+inline size_t p2p_off_redflag(const P2PState& P) { return p2p_off_red(P) + 2 * 8 * MAX_FLUIDS * sizeof(float); }
+inline size_t p2p_total(const P2PState& P) { return p2p_off_redflag(P) + 2 * 8 * sizeof(uint32_t) + 256; }
+
+// Collective over the slab communicator.  On any failure (IPC not permitted, > 8 ranks, ...) every rank keeps the NCCL path.
+sph_status p2p_setup(sph_world* w) {
+    SlabState& S = w->slab;
+    P2PState& P = S.p2p;
+    int want = 1;
+    if (const char* t = getenv("SALVA_B200_P2P")) want = atoi(t) != 0;
+    if (S.nranks > 8 || S.nranks < 2) want = 0;
+    size_t box_mb = 16;
+    if (const char* t = getenv("SALVA_B200_P2P_BOX_MB")) box_mb = (size_t)std::max(1, atoi(t));
+    P.box_bytes = box_mb << 20;
+    int ok = want;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok) {
+        ok = cudaMalloc(&P.base, p2p_total(P)) == cudaSuccess && cudaMemset(P.base, 0, p2p_total(P)) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine, P.base) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
+    // handles of all ranks (64 bytes each) + a "still fine" vote, both through NCCL (the plumbing that exists anyway)
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    char* d_h = nullptr;
+    int* d_ok = nullptr;
+    CU(cudaMalloc(&d_h, 64 * (size_t)(S.nranks + 1)));
+    CU(cudaMalloc(&d_ok, sizeof(int)));
+    CU(cudaMemcpyAsync(d_h, &mine, 64, cudaMemcpyHostToDevice, w->st));
+    NC(g_nccl.AllGather(d_h, d_h + 64, 64, NCCL_CHAR, S.comm, w->st));
+    std::vector<cudaIpcMemHandle_t> all(S.nranks);
+    CU(cudaMemcpyAsync(all.data(), d_h + 64, 64 * (size_t)S.nranks, cudaMemcpyDeviceToHost, w->st));
+    CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, w->st));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_INT, NCCL_MIN, S.comm, w->st));
+    CU(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    if (ok) {
+        for (int p = 0; p < S.nranks && ok; ++p) {
+            if (p == S.rank) {
+                P.peer_base[p] = P.base;
+                continue;
+            }
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+            }
+            P.peer_base[p] = static_cast<char*>(q);
+        }
+        CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, w->st));
+        NC(g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_INT, NCCL_MIN, S.comm, w->st));
+        CU(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, w->st));
+        CU(cudaStreamSynchronize(w->st));
+    }
+    cudaFree(d_h);
+    cudaFree(d_ok);
+    if (!ok) {
+        p2p_release(w);
+        return SPH_OK;  // NCCL path stays in charge
+    }
+    CU(P.tickets.ensure(4));
+    CU(cudaMemset(P.tickets.p, 0, 4 * sizeof(uint32_t)));
+    P.on = true;
+    return SPH_OK;
+}
+
+// Per-iteration ghost refresh of up to 4 per-particle arrays (elem = bytes per particle): my boundary columns go to the
+// neighbours, their boundary columns land in my ghost ranges.  Contiguous ranges, no packing.  Messages that fit the peer
+// boxes travel as direct NVLink stores (one push + one pull kernel for both directions); the rest (or everything, when the
+// peer mapping is unavailable) as ONE NCCL send/recv group.
 sph_status slab_refresh_n(sph_world* w, const SlabArray* arrays, int n_arrays, cudaStream_t st) {
     if (!slab_on(w)) return SPH_OK;
     SlabState& S = w->slab;
+    P2PState& P = S.p2p;
     if (!st) st = w->st;
-    NC(g_nccl.GroupStart());
-    for (int k = 0; k < n_arrays; ++k) {
-        char* a = static_cast<char*>(arrays[k].p);
-        const size_t elem = arrays[k].elem;
-        if (slab_left(w) >= 0) {
-            if (S.sl_count) NC(g_nccl.Send(a + (size_t)S.sl_begin * elem, (size_t)S.sl_count * elem, NCCL_CHAR, slab_left(w), S.comm, st));
-            if (S.gl_count) NC(g_nccl.Recv(a, (size_t)S.gl_count * elem, NCCL_CHAR, slab_left(w), S.comm, st));
-        }
-        if (slab_right(w) >= 0) {
-            if (S.sr_count) NC(g_nccl.Send(a + (size_t)S.sr_begin * elem, (size_t)S.sr_count * elem, NCCL_CHAR, slab_right(w), S.comm, st));
-            if (S.gr_count) NC(g_nccl.Recv(a + (size_t)S.gr_begin * elem, (size_t)S.gr_count * elem, NCCL_CHAR, slab_right(w), S.comm, st));
+    const int nb[2] = {slab_left(w), slab_right(w)};
+    const uint32_t send_begin[2] = {S.sl_begin, S.sr_begin}, send_count[2] = {S.sl_count, S.sr_count};
+    const uint32_t recv_begin[2] = {0u, S.gr_begin}, recv_count[2] = {S.gl_count, S.gr_count};
+    bool p2p_send[2] = {false, false}, p2p_recv[2] = {false, false};
+    if (P.on && n_arrays <= 4) {
+        for (int side = 0; side < 2; ++side) {
+            if (nb[side] < 0) continue;
+            size_t sb = 0, rb = 0;
+            for (int k = 0; k < n_arrays; ++k) {
+                sb += ((size_t)send_count[side] * arrays[k].elem + 15) & ~(size_t)15;
+                rb += ((size_t)recv_count[side] * arrays[k].elem + 15) & ~(size_t)15;
+            }
+            p2p_send[side] = send_count[side] && sb <= P.box_bytes;
+            p2p_recv[side] = recv_count[side] && rb <= P.box_bytes;
         }
     }
-    NC(g_nccl.GroupEnd());
+    // ---- NCCL for whatever does not go through the boxes ----------------------------------------------------------------
+    bool any_nccl = false;
+    for (int side = 0; side < 2; ++side)
+        if (nb[side] >= 0 && ((send_count[side] && !p2p_send[side]) || (recv_count[side] && !p2p_recv[side]))) any_nccl = true;
+    if (any_nccl) {
+        NC(g_nccl.GroupStart());
+        for (int k = 0; k < n_arrays; ++k) {
+            char* a = static_cast<char*>(arrays[k].p);
+            const size_t elem = arrays[k].elem;
+            for (int side = 0; side < 2; ++side) {
+                if (nb[side] < 0) continue;
+                if (send_count[side] && !p2p_send[side])
+                    NC(g_nccl.Send(a + (size_t)send_begin[side] * elem, (size_t)send_count[side] * elem, NCCL_CHAR, nb[side], S.comm, st));
+                if (recv_count[side] && !p2p_recv[side])
+                    NC(g_nccl.Recv(a + (size_t)recv_begin[side] * elem, (size_t)recv_count[side] * elem, NCCL_CHAR, nb[side], S.comm, st));
+            }
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    // ---- peer-memory path ------------------------------------------------------------------------------------------------
+    if (p2p_send[0] || p2p_send[1] || p2p_recv[0] || p2p_recv[1]) {
+        P2PMsg out[2], in[2];
+        memset(out, 0, sizeof out);
+        memset(in, 0, sizeof in);
+        uint32_t seq_out[2] = {0, 0}, seq_in[2] = {0, 0}, max_words = 0;
+        for (int side = 0; side < 2; ++side) {
+            if (p2p_send[side]) {
+                const uint32_t seq = ++P.seq_send[side];
+                const int buf = (int)(seq & 1u);
+                const int their_side = 1 - side;  // I am my left neighbour's RIGHT neighbour
+                char* peer = P.peer_base[nb[side]];
+                out[side].box = peer + ((size_t)their_side * 2 + buf) * P.box_bytes;
+                out[side].flag = reinterpret_cast<uint32_t*>(peer + p2p_off_flags(P)) + their_side * 2 + buf;
+                uint32_t off = 0;
+                for (int k = 0; k < n_arrays; ++k) {
+                    const uint32_t bytes = (uint32_t)((size_t)send_count[side] * arrays[k].elem);
+                    out[side].seg[k] = P2PSeg{static_cast<const char*>(arrays[k].p) + (size_t)send_begin[side] * arrays[k].elem, nullptr, off, bytes};
+                    off += (bytes + 15u) & ~15u;
+                    out[side].total_words += bytes >> 2;
+                }
+                out[side].n_seg = n_arrays;
+                seq_out[side] = seq;
+                max_words = std::max(max_words, out[side].total_words);
+            }
+            if (p2p_recv[side]) {
+                const uint32_t seq = ++P.seq_recv[side];
+                const int buf = (int)(seq & 1u);
+                in[side].box = P.base + ((size_t)side * 2 + buf) * P.box_bytes;
+                in[side].flag = reinterpret_cast<uint32_t*>(P.base + p2p_off_flags(P)) + side * 2 + buf;
+                uint32_t off = 0;
+                for (int k = 0; k < n_arrays; ++k) {
+                    const uint32_t bytes = (uint32_t)((size_t)recv_count[side] * arrays[k].elem);
+                    in[side].seg[k] = P2PSeg{nullptr, static_cast<char*>(arrays[k].p) + (size_t)recv_begin[side] * arrays[k].elem, off, bytes};
+                    off += (bytes + 15u) & ~15u;
+                    in[side].total_words += bytes >> 2;
+                }
+                in[side].n_seg = n_arrays;
+                seq_in[side] = seq;
+                max_words = std::max(max_words, in[side].total_words);
+            }
+        }
+        const uint32_t blocks = std::max(1u, std::min(64u, cdiv(max_words / 4 + 1, 1024)));
+        if (p2p_send[0] || p2p_send[1]) {
+            k_p2p_push<<<dim3(blocks, 2), 256, 0, st>>>(out[0], out[1], seq_out[0], seq_out[1], P.tickets.p);
+            w->launches++;
+        }
+        if (p2p_recv[0] || p2p_recv[1]) {
+            k_p2p_pull<<<dim3(blocks, 2), 256, 0, st>>>(in[0], in[1], seq_in[0], seq_in[1], w->d_scal.p + 7);
+            w->launches++;
+        }
+        CU(cudaGetLastError());
+    }
     w->stats_exchanges++;
     return SPH_OK;
 }
@@ -123,7 +284,20 @@ sph_status slab_refresh(sph_world* w, void* array, size_t elem) {
 // Sum a small device float buffer over all ranks (error means of the Jacobi loops: dfsph_solver.rs:153-158).
 sph_status slab_allreduce(sph_world* w, float* buf, size_t n) {
     if (!slab_on(w)) return SPH_OK;
-    NC(g_nccl.AllReduce(buf, buf, n, NCCL_FLOAT, NCCL_SUM, w->slab.comm, w->st));
+    SlabState& S = w->slab;
+    if (S.p2p.on && n <= (size_t)MAX_FLUIDS) {  // a handful of floats: one 1-block kernel writing into every rank's table over NVLink
+        P2PPeers peers;
+        memset(&peers, 0, sizeof peers);
+        for (int p = 0; p < S.nranks; ++p) {
+            peers.red[p] = reinterpret_cast<float*>(S.p2p.peer_base[p] + p2p_off_red(S.p2p));
+            peers.red_flag[p] = reinterpret_cast<uint32_t*>(S.p2p.peer_base[p] + p2p_off_redflag(S.p2p));
+        }
+        k_p2p_allreduce<<<1, 128, 0, w->st>>>(buf, (int)n, S.rank, S.nranks, peers, ++S.p2p.red_seq, w->d_scal.p + 7);
+        w->launches++;
+        CU(cudaGetLastError());
+        return SPH_OK;
+    }
+    NC(g_nccl.AllReduce(buf, buf, n, NCCL_FLOAT, NCCL_SUM, S.comm, w->st));
     return SPH_OK;
 }
 

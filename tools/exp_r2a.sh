@@ -11,6 +11,7 @@ for cfg in c2 c3; do
   timeout 1500 python tools/exp_variants.py $cfg 10 \
     base=$V/v_base.so \
     fast=$L \
+    new=salva_b200/libsalva_b200.so new_nogen=$V/v_nogen.so new_rec8=salva_b200/libsalva_b200.so,SALVA_B200_REC8=1 \
     fast_rec8=$L,SALVA_B200_REC8=1 \
     fast_gcache=$L,SALVA_B200_GCACHE=1 \
     fast_gcache_rec8=$L,SALVA_B200_GCACHE=1,SALVA_B200_REC8=1 \
