@@ -70,7 +70,9 @@ enum { SPH_FORCE_XSPH_VISCOSITY = 0,        /* p[0]=fluid coeff, p[1]=boundary c
 
 /* Kernel type parameters of the solver, DFSPHSolver<KernelDensity, KernelGradient> dfsph_solver.rs:17-20 /
  * IISPHSolver<..> iisph_solver.rs:17-20: contact.weight uses the density kernel, contact.gradient the gradient kernel
- * (helper.rs:24-25). */
+ * (helper.rs:24-25).  They are compile-time parameters in the reference and link-time ones here: libsalva_b200.so is
+ * monomorphised on the cubic spline (sph_world_create rejects anything else), libsalva_b200_kernels.so — same source,
+ * same ABI — serves every combination. */
 enum { SPH_KERNEL_CUBIC_SPLINE = 0,  /* kernel/cubic_spline_kernel.rs:12-80 (default) */
        SPH_KERNEL_POLY6 = 1,         /* kernel/poly6_kernel.rs:12-40 */
        SPH_KERNEL_SPIKY = 2,         /* kernel/spiky_kernel.rs:12-40 */

@@ -7,7 +7,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SALVA_B200_LIB") or os.path.join(_HERE, "libsalva_b200.so")  # env override: A/B builds
+KERNELS_LIB_PATH = os.path.join(_HERE, "libsalva_b200_kernels.so")  # same ABI, solver kernels other than the cubic spline
 _LIB = None
+_LIBS = {}
 
 SPH_OK = 0
 STATUS_NAMES = {0: "SPH_OK", 1: "SPH_ERR_INVALID", 2: "SPH_ERR_CUDA", 3: "SPH_ERR_OOM", 4: "SPH_ERR_NCCL",
@@ -127,20 +129,24 @@ SYMBOLS = {
 }
 
 
-def lib():
-    """Load libsalva_b200.so; raises (never falls back) when it is missing."""
+def lib(kernels=False):
+    """Load libsalva_b200.so (kernels=True: libsalva_b200_kernels.so, the build that carries the Poly6 / Spiky / Viscosity
+    solver kernels); raises (never falls back) when it is missing."""
     global _LIB
-    if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError("libsalva_b200.so is not built (run `python -c 'import __graft_entry__ as g; "
-                               "g.build()'`); there is no CPU fallback")
-        L = C.CDLL(LIB_PATH)
-        ab_build = bool(os.environ.get("SALVA_B200_LIB"))  # A/B experiment builds may predate the newest entry points
+    path = KERNELS_LIB_PATH if kernels else LIB_PATH
+    if path not in _LIBS:
+        if not os.path.exists(path):
+            raise RuntimeError("%s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback"
+                               % os.path.basename(path))
+        L = C.CDLL(path)
+        ab_build = bool(os.environ.get("SALVA_B200_LIB")) and not kernels  # A/B experiment builds may predate the newest entry points
         for name, (res, args) in SYMBOLS.items():
             if ab_build and not hasattr(L, name):
                 continue
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        _LIB = L
-    return _LIB
+        _LIBS[path] = L
+    if not kernels:
+        _LIB = _LIBS[path]
+    return _LIBS[path]

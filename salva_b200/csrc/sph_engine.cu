@@ -221,12 +221,13 @@ struct sph_world {
     // gather_backend 0: the second per-contact gather (v* / kappa) can go through the texture pipe
     // uniform-mass packed gather records (sph_passes.cuh): pvx4 = (x,y,z,v*x), vyz2 = (v*y,v*z), pk4 = (x,y,z,kappa)
     bool unimass = false;
-    int uni_eval_mode = 1, uni_upd_mode = 1;  // 1: position record through the texture pipe, 2: through the LSU pipe
+    int uni_eval_mode = 1, uni_upd_mode = 2;  // 1: position record through the texture pipe, 2: through the LSU pipe, 3 (update): alternate
     DBuf<float4> pvx4, pk4;
     DBuf<float2> vyz2;
     DBuf<Rec8> rec8, nrec8;  // 256-bit gather records: (pos, v*, rho) of the evaluations, (pos, normal, rho) of the Akinci force pass
     int use_rec8 = 0;        // 0: off, 1: pressure-loop evaluations, 2: every evaluation of the step (+ fused XSPH / Akinci normals)
     bool nrec_valid = false;
+    bool fuse_akinci = true, nr4_valid = false;  // Akinci normals ride with a divergence evaluation (k_vel_divergence_xsph_u<.., 2>)
     cudaTextureObject_t tex_pvx = 0, tex_vyz = 0, tex_pk = 0;
     const void* tex_pvx_ptr = nullptr;
     const void* tex_vyz_ptr = nullptr;
@@ -1153,6 +1154,14 @@ bool xsph_fusable(const sph_world* w) {
     const sph_force_desc& d = w->fluids[0].forces[0].d;
     return d.kind == SPH_FORCE_XSPH_VISCOSITY && d.p[0] != 0.f && (d.p[1] == 0.f || w->B == 0);
 }
+// ... and on the default records (k_vel_divergence_xsph_u<.., 2>, one extra 4-byte gather of rho_j): single uniform-mass fluid
+bool akinci_fusable_u(const sph_world* w) {
+    if (!w->fuse_akinci || w->desc.solver != SPH_SOLVER_DFSPH || w->tile || !w->unimass || w->use_gcache || w->slab.active || rec8_full(w)) return false;
+    if (w->fluids.size() != 1) return false;
+    for (const ForceRec& fr : w->fluids[0].forces)
+        if (fr.d.kind == SPH_FORCE_AKINCI2013_TENSION) return true;
+    return false;
+}
 // Akinci2013 normals (positions + densities only) can ride with any stand-alone divergence evaluation of the step when the
 // evaluations gather the 256-bit records (rho_j comes with them): k_vel_divergence_r8<false, 2>.
 bool akinci_fusable(const sph_world* w) {
@@ -1166,7 +1175,9 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1;
     const bool xsf = !predict && !gate && xsph_fusable(w);
+    const bool akf = !predict && !gate && !xsf && akinci_fusable_u(w);
     if (xsf) CU(w->xs.ensure(std::max(w->Ntot, w->N)));
+    if (akf) CU(w->normals.ensure(std::max(w->Ntot, w->N)));
     if (w->tile) {
         TileLists L{w->nbr16.p, w->nbr_b.p, w->cnt_f.p, w->cnt_b.p};
         uint32_t cap = tile_cap(w, 32);
@@ -1218,11 +1229,17 @@ sph_status launch_vel_divergence(sph_world* w, bool predict, uint32_t* nblk, con
                               w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
             } else if (xsf) {
                 const float cf = w->fluids[0].forces[0].d.p[0];
-                if (ptex) LAUNCH_R((k_vel_divergence_xsph_u<true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, L, w->dens.p,
+                if (ptex) LAUNCH_R((k_vel_divergence_xsph_u<true, 1>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, L, w->dens.p,
                                    w->alpha.p, out, w->pk4.p, partial, tk, w->errsum.p, w->xs.p, cf);
-                else LAUNCH_R((k_vel_divergence_xsph_u<false>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, L, w->dens.p,
+                else LAUNCH_R((k_vel_divergence_xsph_u<false, 1>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, L, w->dens.p,
                               w->alpha.p, out, w->pk4.p, partial, tk, w->errsum.p, w->xs.p, cf);
                 w->xs_valid = true;
+            } else if (akf) {  // Akinci normals ride along: nr4 = (n, rho) for k_akinci_force_u
+                if (ptex) LAUNCH_R((k_vel_divergence_xsph_u<true, 2>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, L, w->dens.p,
+                                   w->alpha.p, out, w->pk4.p, partial, tk, w->errsum.p, w->normals.p, 0.f);
+                else LAUNCH_R((k_vel_divergence_xsph_u<false, 2>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, L, w->dens.p,
+                              w->alpha.p, out, w->pk4.p, partial, tk, w->errsum.p, w->normals.p, 0.f);
+                w->nr4_valid = true;
             } else {
                 if (ptex) LAUNCH_R((k_vel_divergence_u<false, true>), rg, w->pvx4.p, w->tex_pvx, w->vyz2.p, w->tex_vyz, w->bpos[bc].p, w->bvel[bc].p, L,
                                    w->dens.p, w->alpha.p, out, w->pk4.p, partial, w->dt, w->d_scal.p + 7, gate, tk, w->errsum.p);
@@ -1262,6 +1279,16 @@ sph_status launch_vel_update(sph_world* w, bool pressure, const int* gate = null
         if (w->unimass) {
             const bool ptex = w->uni_upd_mode == 1;
             Rec8* rec = (!gate && ((pressure && rec8_predict(w)) || rec8_full(w))) ? w->rec8.p : nullptr;
+            if (w->uni_upd_mode == 3 && !rec && !gate) {
+                if (bf) {
+                    if (pressure) LAUNCH_R((k_vel_update_alt<true, true>), rg, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p, w->bforce.p, w->inv_dt);
+                    else LAUNCH_R((k_vel_update_alt<true, false>), rg, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p, w->bforce.p, w->inv_dt);
+                } else {
+                    if (pressure) LAUNCH_R((k_vel_update_alt<false, true>), rg, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p, w->bforce.p, w->inv_dt);
+                    else LAUNCH_R((k_vel_update_alt<false, false>), rg, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p, w->bforce.p, w->inv_dt);
+                }
+                return SPH_OK;
+            }
             BOOL3(k_vel_update_u, bf, pressure, ptex, rg, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p,
                   rec, w->dens.p, w->bforce.p, w->inv_dt, gate);
         } else {
@@ -1437,6 +1464,12 @@ sph_status phase_forces(sph_world* w) {
                         else LAUNCH((k_akinci_force_r8<false>), N, PASS_T, w->nrec8.p, w->bpos[bc].p, L, w->acc.p, w->bforce.p, p[0], p[1], coh_norm, h6_64, adh_norm);
                         break;
                     }
+                    if (w->nr4_valid && f == 0) {  // normals (and rho, in .w) came with a divergence evaluation
+                        TRY(ensure_tex(w, &w->tex_pvx, &w->tex_pvx_ptr, w->pvx4.p, w->pvx4.cap));
+                        if (bf) LAUNCH((k_akinci_force_u<true>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->normals.p, w->bpos[bc].p, L, w->acc.p, w->bforce.p, p[0], p[1], coh_norm, h6_64, adh_norm);
+                        else LAUNCH((k_akinci_force_u<false>), N, PASS_T, w->pvx4.p, w->tex_pvx, w->normals.p, w->bpos[bc].p, L, w->acc.p, w->bforce.p, p[0], p[1], coh_norm, h6_64, adh_norm);
+                        break;
+                    }
                     DISPATCH1(k_akinci_normals, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, L, w->dens.p, w->normals.p, (uint32_t)f);
                     TRY(slab_refresh(w, w->normals.p, sizeof(float4)));
                     DISPATCH2(k_akinci_force, multi, bf, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, w->normals.p, w->acc.p,
@@ -1576,6 +1609,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     w->stats.n_divergence_iter = w->stats.n_divergence_eval = 0;
     w->xs_valid = false;
     w->nrec_valid = false;
+    w->nr4_valid = false;
     uint32_t maxit = w->force_div >= 0 ? (uint32_t)w->force_div + 1 : w->desc.max_divergence_iter;
     const bool dev_loops = w->device_loops && !w->tile;
     if (dev_loops && w->force_div < 0) {
@@ -1817,6 +1851,10 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     if (desc->solver != SPH_SOLVER_DFSPH && desc->solver != SPH_SOLVER_IISPH) return SPH_ERR_INVALID;
     if (desc->kernel_density < 0 || desc->kernel_density > SPH_KERNEL_VISCOSITY || desc->kernel_gradient < 0 || desc->kernel_gradient > SPH_KERNEL_VISCOSITY)
         return SPH_ERR_INVALID;
+#if !SPH_GENERIC_KERNELS
+    // this build monomorphises the solver on CubicSplineKernel; libsalva_b200_kernels.so carries the other kernels
+    if (desc->kernel_density != SPH_KERNEL_CUBIC_SPLINE || desc->kernel_gradient != SPH_KERNEL_CUBIC_SPLINE) return SPH_ERR_INVALID;
+#endif
     std::lock_guard<std::recursive_mutex> lock(g_mutex);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || desc->device < 0 || desc->device >= ndev) return SPH_ERR_CUDA;
@@ -1831,6 +1869,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     if (const char* t = getenv("SALVA_B200_REC8")) w->use_rec8 = atoi(t);
     if (const char* t = getenv("SALVA_B200_FUSE_DIV")) w->fuse_div = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_FUSE_XSPH")) w->fuse_xsph = atoi(t) != 0;
+    if (const char* t = getenv("SALVA_B200_FUSE_AKINCI")) w->fuse_akinci = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_UNI_EVAL")) w->uni_eval_mode = atoi(t);
     if (const char* t = getenv("SALVA_B200_UNI_UPD")) w->uni_upd_mode = atoi(t);
     {
@@ -2373,7 +2412,13 @@ sph_status sph_debug_read(sph_world* w, uint32_t fluid_h, int what, float* out, 
 }
 
 const char* sph_last_error(const sph_world* w) { return w ? w->err.c_str() : "null world"; }
-const char* sph_version(void) { return "salva_b200 0.1 (sm_100a)"; }
+const char* sph_version(void) {
+#if SPH_GENERIC_KERNELS
+    return "salva_b200 0.2 (sm_100a, kernels: cubic-spline poly6 spiky viscosity)";
+#else
+    return "salva_b200 0.2 (sm_100a, kernels: cubic-spline)";
+#endif
+}
 
 sph_status sph_nccl_unique_id(char out[128]) {
     if (!out) return SPH_ERR_INVALID;

@@ -142,8 +142,13 @@ __device__ __forceinline__ float kernel_dw_kind(int kind, float r) {  // scalar_
     return __fdiv_rn(C.sigma * rhs, h);
 }
 
+// The solver's KernelDensity / KernelGradient are COMPILE-TIME type parameters in the reference (monomorphised per solver
+// type).  Here likewise: libsalva_b200.so is built with SPH_GENERIC_KERNELS = 0 (cubic spline only, no branch in the pair
+// evaluation: the uniform `if (C.kgen)` inside the 4-way unrolled contact loops cost 6-8 % of the whole step,
+// profiles/r2_exp_a_variants.md); libsalva_b200_kernels.so is the same source built with SPH_GENERIC_KERNELS = 1 and
+// serves worlds whose solver names Poly6 / Spiky / Viscosity kernels.  Same C ABI in both.
 #ifndef SPH_GENERIC_KERNELS
-#define SPH_GENERIC_KERNELS 1   // 0 compiles the non-default kernels out (A/B builds measuring what the uniform branch costs)
+#define SPH_GENERIC_KERNELS 0
 #endif
 __device__ __forceinline__ float2 pair_generic(float d2, int need_w, int need_g) {
     const float r = __fsqrt_rn(d2);

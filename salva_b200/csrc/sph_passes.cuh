@@ -751,7 +751,11 @@ struct VyzRho {
     float2 v;
     float rho;
 };
-template <bool POS_TEX>
+// EXTRA = 1: XSPH sums (above) -> xs.   EXTRA = 2: Akinci2013 compute_normals (akinci2013_surface_tension.rs:43-68) rides along
+// instead: n_i = h sum_j (m_j / rho_j) grad W_ij needs positions and densities only, so ANY stand-alone evaluation of the
+// step may produce it; the output record nr4 = (n_x, n_y, n_z, rho_i) is what k_akinci_force_u gathers (one float4 instead
+// of a normal and a density), and the separate normals pass is skipped.
+template <bool POS_TEX, int EXTRA>
 __global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)  // 64 registers: the extra sums spill at 56
 k_vel_divergence_xsph_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, const float2* __restrict__ vyz, cudaTextureObject_t tvyz,
                         const float4* __restrict__ bpos, Lists L, const float* __restrict__ dens, const float* __restrict__ alpha,
@@ -770,14 +774,19 @@ k_vel_divergence_xsph_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx
         const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
         const bool gated = L.cnt_f[i] + L.cnt_b[i] < 20u;  // dfsph_solver.rs:301-314
         float d = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
-        for_fluid_grads<false, true>(
+        for_fluid_grads<false, EXTRA == 1>(
             i, pi, L, [&](uint32_t j) { return POS_TEX ? tex1Dfetch<float4>(tpvx, (int)j) : __ldg(&pvx[j]); },
             [&](uint32_t j) { return VyzRho{POS_TEX ? __ldg(&vyz[j]) : tex1Dfetch<float2>(tvyz, (int)j), __ldg(&dens[j])}; },
             [&](uint32_t, const Pair& p, const float4& pj, const VyzRho& wj) {
                 float dv = (vix - pj.w) * p.dx + (viy - wj.v.x) * p.dy + (viz - wj.v.y) * p.dz;
                 d = fmaf(dv * p.g, mass, d);
-                float c = cf * p.w * mass / wj.rho;  // coeff * W * (vol_j * rho0) / rho_j
-                fx = fmaf(c, pj.w - vix, fx); fy = fmaf(c, wj.v.x - viy, fy); fz = fmaf(c, wj.v.y - viz, fz);
+                if (EXTRA == 1) {
+                    float c = cf * p.w * mass / wj.rho;  // coeff * W * (vol_j * rho0) / rho_j
+                    fx = fmaf(c, pj.w - vix, fx); fy = fmaf(c, wj.v.x - viy, fy); fz = fmaf(c, wj.v.y - viz, fz);
+                } else {
+                    float c = p.g * (mass / wj.rho);
+                    fx = fmaf(c, p.dx, fx); fy = fmaf(c, p.dy, fy); fz = fmaf(c, p.dz, fz);
+                }
             });
         if (gated) {
             d = 0.f;
@@ -791,11 +800,56 @@ k_vel_divergence_xsph_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx
         out[i] = d;
         e = d / rho0;
         pk4[i] = make_float4(a.x, a.y, a.z, d * alpha[i]);
-        xs[i] = make_float4(fx, fy, fz, 0.f);
+        if (EXTRA == 1) xs[i] = make_float4(fx, fy, fz, 0.f);
+        else xs[i] = make_float4(fx * C.h, fy * C.h, fz * C.h, dens[i]);
     }
     reduce_error<false>(e, 0u, valid, partial, sm, ticket, errsum);
 }
 
+// a14 pass 2 for a single uniform-mass fluid on the records of the fused pass: positions from pvx4 (texture pipe) and
+// nr4 = (n_x, n_y, n_z, rho) (LSU pipe): two gathers per contact instead of three.  Akinci2013SurfaceTension::solve
+// akinci2013_surface_tension.rs:113-192.
+template <bool BFORCE>
+__global__ void __launch_bounds__(PASS_T, SPH_FORCE_MINB)
+k_akinci_force_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, const float4* __restrict__ nr4, const float4* __restrict__ bpos, Lists L,
+                 float4* __restrict__ acc, float* __restrict__ bforce, float gamma, float adh, float coh_norm, float h6_64, float adh_norm) {
+    SPH_OWNED_INDEX(i)
+    const float4 a = pvx[i];
+    const float4 ni = nr4[i];
+    const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
+    const float4 pi = make_float4(a.x, a.y, a.z, mass);
+    const float rho_i = ni.w;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (gamma != 0.f)
+        for_fluid_contacts_g<false, false>(
+            i, pi, L, [&](uint32_t j) { return tex1Dfetch<float4>(tpvx, (int)j); }, [&](uint32_t j) { return __ldg(&nr4[j]); },
+            [&](uint32_t, const Pair& p, const float4&, const float4& nj) {
+                // cohesion_vec = dir * C(dist) if |dpos|^2 > eps^2 (Unit::try_new_and_get)
+                float coh = p.d2 > F32_EPS * F32_EPS ? cohesion_kernel(p.r, coh_norm, h6_64) / p.r : 0.f;
+                float cm = coh * (-gamma * mass);
+                float kij = 2.0f * rho0 / (rho_i + nj.w);
+                ax += (-gamma * (ni.x - nj.x) + cm * p.dx) * kij;
+                ay += (-gamma * (ni.y - nj.y) + cm * p.dy) * kij;
+                az += (-gamma * (ni.z - nj.z) + cm * p.dz) * kij;
+            });
+    if (adh != 0.f)
+        for_boundary_contacts<false, false>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+            float ad = p.d2 > F32_EPS * F32_EPS ? adhesion_kernel(p.r, adh_norm) / p.r : 0.f;
+            float c = ad * adh * (pj.w * rho0);
+            ax -= c * p.dx; ay -= c * p.dy; az -= c * p.dz;
+            if (BFORCE) {  // apply_force(c.j, adhesion_acc * m_i) :188
+                atomicAdd(&bforce[3 * (size_t)j + 0], c * p.dx * mass);
+                atomicAdd(&bforce[3 * (size_t)j + 1], c * p.dy * mass);
+                atomicAdd(&bforce[3 * (size_t)j + 2], c * p.dz * mass);
+            }
+        });
+    float4 o = acc[i];
+    o.x += ax; o.y += ay; o.z += az;
+    acc[i] = o;
+}
+
+// POS_TEX: the (x, y, z, kappa) gather goes through the texture pipe (true) or the LSU pipe (false).  ALT (runtime, uniform):
+// contacts 0 and 2 of every group of four through TEX, 1 and 3 through LSU, so both L1TEX front ends carry half the wavefronts.
 template <bool BFORCE, bool PRESSURE, bool POS_TEX>
 __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
 k_vel_update_u(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
@@ -842,6 +896,67 @@ k_vel_update_u(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const fl
         pvx[i] = make_float4(a.x, a.y, a.z, sx);
         vyz[i] = make_float2(sy, sz);
     }
+}
+
+// k_vel_update_u with the gathers of every group of four contacts split between the two L1TEX front ends: contacts 0 and 2
+// through the texture pipe, 1 and 3 through the LSU pipe (SALVA_B200_UNI_UPD=3).  Same arithmetic and summation order.
+template <bool BFORCE, bool PRESSURE>
+__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
+k_vel_update_alt(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
+                 float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ pvx, float2* __restrict__ vyz, float* __restrict__ bforce, float inv_dt,
+                 Range rg) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rg.count) return;
+    i += rg.begin;
+    const float4 a = pk4[i];
+    const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
+    const float ki = a.w;
+    const float4 v = vel[i];
+    const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
+    const float scale = (PRESSURE ? inv_dt : 1.0f) * mass;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    {
+        const uint32_t n = min(L.cnt_f[i], C.cap_f);
+        const uint32_t nq = (n + 3u) >> 2;
+        const uint4* col = L.nbr_f + i;
+        uint4 J = nq ? ld_list(col) : make_uint4(i, i, i, i);
+        for (uint32_t q = 0; q < nq; ++q) {
+            uint4 Jn = J;
+            if (q + 1 < nq) Jn = ld_list(col + (size_t)(q + 1) * C.stride);
+            float4 pj[4];
+            pj[0] = tex1Dfetch<float4>(tpk, (int)J.x);
+            pj[1] = __ldg(&pk4[J.y]);
+            pj[2] = tex1Dfetch<float4>(tpk, (int)J.z);
+            pj[3] = __ldg(&pk4[J.w]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // padded tail slots are self contacts: zero gradient
+                Pair p = make_pair<false, true>(pi, pj[u]);
+                float c = (ki + pj[u].w) * scale * p.g;
+                ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
+            }
+            J = Jn;
+        }
+    }
+    if (!PRESSURE || ki > 0.f) {
+        const float bscale = PRESSURE ? inv_dt : 1.0f;
+        for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
+            float c = ki * pj.w * rho0 * bscale * p.g;
+            ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
+            if (BFORCE) {
+                float s = c * inv_dt * mass;
+                atomicAdd(&bforce[3 * (size_t)j + 0], s * p.dx);
+                atomicAdd(&bforce[3 * (size_t)j + 1], s * p.dy);
+                atomicAdd(&bforce[3 * (size_t)j + 2], s * p.dz);
+            }
+        });
+    }
+    float4 c4 = vc[i];
+    c4.x -= ax; c4.y -= ay; c4.z -= az;
+    vc[i] = c4;
+    const float sx = v.x + c4.x, sy = v.y + c4.y, sz = v.z + c4.z;
+    vs[i] = make_float4(sx, sy, sz, 0.f);
+    pvx[i] = make_float4(a.x, a.y, a.z, sx);
+    vyz[i] = make_float2(sy, sz);
 }
 
 // ------------------------------------------------------------------------------------------------

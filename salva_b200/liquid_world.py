@@ -236,7 +236,8 @@ class LiquidWorld:
     def __init__(self, solver=None, particle_radius=0.05, smoothing_factor=2.0, device=0, deterministic=True,
                  slab_rank=0, slab_count=1, gather_backend=0):
         solver = solver or DFSPHSolver()
-        self._L = _lib.lib()
+        # the solver's kernels are compile-time parameters (dfsph_solver.rs:17-20): non-default ones live in the second library
+        self._L = _lib.lib(kernels=bool(getattr(solver, "kernel_density", 0) or getattr(solver, "kernel_gradient", 0)))
         d = WorldDesc()
         self._L.sph_world_desc_default(C.byref(d))
         d.solver = solver.kind
@@ -430,7 +431,7 @@ class LiquidWorld:
         addr = C.cast(ptr, C.c_void_p).value or 0
 
         class _View:
-            __cuda_array_interface__ = {"shape": (n.value, 3), "typestr": "<f4", "data": (addr, True), "version": 2, "strides": None}
+            __cuda_array_interface__ = {"shape": (n.value, 3), "typestr": "<f4", "data": (addr, False), "version": 2, "strides": None}
         return _View()
 
     def add_boundary(self, boundary_or_positions, velocities=None, memberships=1, filter=0xFFFFFFFF,

@@ -34,6 +34,7 @@ def make_scene(kind):
 def main():
     kind, steps, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
     free_running = len(sys.argv) > 4 and sys.argv[4] == "free"
+    do_rebalance = len(sys.argv) > 4 and sys.argv[4] == "rebalance"
     local_rank = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -41,13 +42,25 @@ def main():
     sc = make_scene(kind)
     uid = slab.broadcast_unique_id(nccl_unique_id, rank, device=torch.device("cuda", local_rank))
     w = LiquidWorld(particle_radius=sc["particle_radius"], device=local_rank)
-    fh, _ = slab.populate_slab(w, sc, rank, ws, uid)
+    planes = None
+    if do_rebalance:  # a deliberately bad split: rank 0 starts with a quarter of the cell columns
+        h = np.float32(sc["particle_radius"]) * np.float32(4.0)
+        cols = slab.cell_columns(sc["fluids"][0]["positions"], h)
+        lo, hi = int(cols.min()), int(cols.max()) + 1
+        step = max(2, (hi - lo) // (2 * ws))
+        planes = [slab.INT32_MIN] + [lo + step * r for r in range(1, ws)] + [slab.INT32_MAX]
+    fh, _ = slab.populate_slab(w, sc, rank, ws, uid, planes)
     if not free_running:
         w.force_iterations(2, 3)
     n0 = w.num_particles(fh[0])
     migrated = 0
     iters = []
-    for _ in range(steps):
+    rebalanced, imb_before, imb_after = 0, 0.0, 0.0
+    for k in range(steps):
+        if do_rebalance and k == steps // 2:
+            imb_before, did = slab.rebalance(w, fh[0], threshold=0.05)
+            rebalanced += int(did)
+            imb_after, _ = slab.imbalance(w.num_particles(fh[0]))
         w.step(sc["dt"])
         st = w.stats()
         migrated += st["n_migrated"]
@@ -78,7 +91,8 @@ def main():
                    h_over_dt=h / sc["dt"], migrated=int(sum(g["migrated"] for g in gathered)),
                    ghosts=[int(g["ghosts"]) for g in gathered], exchanges=[int(g["exchanges"]) for g in gathered],
                    n_per_rank=[int(len(g["ids"])) for g in gathered], n0_per_rank=[int(g["n0"]) for g in gathered],
-                   iters_match=iters == ref_iters, iters=iters[-1], ref_iters=ref_iters[-1])
+                   iters_match=iters == ref_iters, iters=iters[-1], ref_iters=ref_iters[-1], rebalanced=rebalanced,
+                   imbalance_before=imb_before, imbalance_after=imb_after)
         json.dump(res, open(out, "w"))
         print(json.dumps(res))
     dist.barrier()

@@ -20,10 +20,14 @@ def _declared_symbols():
 def test_header_symbols_are_all_bound_and_exported():
     names = _declared_symbols()
     assert len(names) >= 20
-    L = C.CDLL(_lib.LIB_PATH)
-    for n in names:
-        assert hasattr(L, n), "libsalva_b200.so does not export %s" % n
-        assert n in _lib.SYMBOLS, "python binding misses %s" % n
+    for path in (_lib.LIB_PATH, _lib.KERNELS_LIB_PATH):
+        L = C.CDLL(path)
+        for n in names:
+            assert hasattr(L, n), "%s does not export %s" % (os.path.basename(path), n)
+            assert n in _lib.SYMBOLS, "python binding misses %s" % n
+    lean, full = C.CDLL(_lib.LIB_PATH), C.CDLL(_lib.KERNELS_LIB_PATH)
+    lean.sph_version.restype = full.sph_version.restype = C.c_char_p
+    assert b"poly6" in full.sph_version() and b"poly6" not in lean.sph_version()
     assert set(_lib.SYMBOLS) == set(names)
 
 

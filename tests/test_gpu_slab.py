@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(nproc, kind, steps, tmp_path, mode="forced"):
+def _run(nproc, kind, steps, tmp_path, mode="forced", env=None):
     import torch
     if torch.cuda.device_count() < nproc:
         pytest.skip("needs %d GPUs" % nproc)
@@ -23,7 +23,7 @@ def _run(nproc, kind, steps, tmp_path, mode="forced"):
     out = str(tmp_path / "res.json")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py"), kind, str(steps), out, mode],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
     return json.load(open(out))
 
@@ -42,3 +42,23 @@ def test_two_slabs_free_running_iteration_counts(tmp_path):
     res = _run(2, "xsph", 8, tmp_path, mode="free")
     assert res["iters_match"], (res["iters"], res["ref_iters"])
     assert res["max_dx_over_h"] <= 1e-3
+
+
+@pytest.mark.parametrize("p2p", ["1", "0"], ids=["nvlink-peer-memory", "nccl-sendrecv"])
+def test_two_slabs_exchange_paths_agree(p2p, tmp_path):
+    """The ghost exchange over NVLink peer memory (cudaIpc boxes, k_p2p_push / k_p2p_pull, P2P allreduce) and the NCCL
+    send/recv fallback must both reproduce the 1-GPU trajectory; free-running loops so the error allreduce matters."""
+    res = _run(2, "akinci", 10, tmp_path, mode="free", env={"SALVA_B200_P2P": p2p})
+    assert res["n_total"] == res["n_expected"] and res["ids_unique"]
+    assert res["iters_match"], (res["iters"], res["ref_iters"])
+    assert res["max_dx_over_h"] <= 1e-3
+
+
+def test_rebalance_moves_the_planes_and_keeps_the_trajectory(tmp_path):
+    """SURVEY §8e plane re-balancing: start from a bad split (imbalance > 30 %), re-balance half way (positions, velocities,
+    velocity_changes and ids change rank wholesale), and still match the 1-GPU trajectory particle by particle."""
+    res = _run(2, "xsph", 10, tmp_path, mode="rebalance")
+    assert res["rebalanced"] == 1 and res["imbalance_before"] > 0.3 and res["imbalance_after"] <= 0.2
+    assert res["n_total"] == res["n_expected"] and res["ids_unique"]
+    assert res["max_dx_over_h"] <= 1e-3
+    assert res["max_dv"] <= 1e-3 * res["h_over_dt"]
