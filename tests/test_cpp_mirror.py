@@ -11,10 +11,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
-def _build(tmp_path, name="basic3"):
-    exe = str(tmp_path / name)
-    r = subprocess.run([GXX, "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", name + ".cpp"),
-                        "-L" + os.path.join(ROOT, "salva_b200"), "-lsalva_b200", "-Wl,-rpath," + os.path.join(ROOT, "salva_b200"), "-o", exe],
+def _build(tmp_path, name="basic3", lib="salva_b200", extra=()):
+    exe = str(tmp_path / (name + "_" + lib))
+    r = subprocess.run([GXX, "-std=c++17", "-Wall", *extra, "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", name + ".cpp"),
+                        "-L" + os.path.join(ROOT, "salva_b200"), "-l" + lib, "-Wl,-rpath," + os.path.join(ROOT, "salva_b200"), "-o", exe],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe
@@ -36,6 +36,22 @@ def test_cpp_custom_force_example_builds(tmp_path):
     if torch.cuda.is_available():
         r = subprocess.run([exe, "3"], capture_output=True, text=True)
         assert r.returncode == 0 and "custom_forces3: 1000 particles" in r.stdout, r.stderr
+    else:
+        r = subprocess.run([exe, "1"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.parametrize("lib,extra", [("salva_b200", ()), ("salva_b200_kernels", ("-DUSE_KERNELS",))], ids=["cubic-spline", "poly6+spiky"])
+def test_cpp_coupling_example_builds(tmp_path, lib, extra):
+    """examples/coupling3.cpp: a CouplingManager (coupling_manager.rs:9-28) that re-samples a ball collider's boundary every
+    step, on both library builds (the second one with DFSPHSolver<Poly6Kernel, SpikyKernel>)."""
+    import torch
+    exe = _build(tmp_path, "coupling3", lib, extra)
+    if torch.cuda.is_available():
+        r = subprocess.run([exe, "25"], capture_output=True, text=True)
+        assert r.returncode == 0 and "coupling3: 480 particles, 25 steps" in r.stdout, (r.stdout, r.stderr)
+        m = re.search(r"sampled boundary (\d+)\.\.(\d+) particles", r.stdout)
+        assert m and int(m.group(2)) > int(m.group(1)) >= 0
     else:
         r = subprocess.run([exe, "1"], capture_output=True, text=True)
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
