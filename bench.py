@@ -479,7 +479,7 @@ def native_arm(args, rank, world_size):
         k2 = max(3, min(args.steps, 10))
         acc2, _, iters2, _, _ = timed_steps(w2, sc2, k2, barrier)
         dev2 = allmax([acc2["step_ms"] * 1e-3])[0]
-        settled = {"what": "same workload started from a 0.90-compressed lattice (+10 % density), 3 warm-up + %d timed steps" % k2,
+        settled = {"what": "same workload started from a 0.90-compressed lattice (+10 %% density), 3 warm-up + %d timed steps" % k2,
                    "value": nf * k2 / dev2, "unit": UNIT, "ms_per_step": dev2 / k2 * 1e3,
                    "iterations_per_step_mean": [float(np.mean([i[0] for i in iters2])), float(np.mean([i[1] for i in iters2]))],
                    "pressure_pair_ms": (acc2["predict_density_ms"] / max(acc2["n_pressure_eval"], 1) +
@@ -488,9 +488,28 @@ def native_arm(args, rank, world_size):
                                           acc2["divergence_update_ms"] / max(acc2["n_divergence_iter"], 1))}
         w2.close()
 
+    # ---- N > 1: the same per-GPU slice on ONE GPU (rank 0, the others wait), so the line carries its own weak-scaling reference
+    slice_ref = None
+    if world_size > 1 and not args.no_slice_ref:
+        if rank == 0:
+            nx, ny, nz = scene_dims(cfg, args.n, world_size)
+            one = scene_fn(cfg)(nx // world_size, ny, nz)
+            w1 = LiquidWorld(DFSPHSolver(), particle_radius=one["particle_radius"], smoothing_factor=one["smoothing_factor"], device=local_rank,
+                             deterministic=not args.fast_sort)
+            scenes.populate(w1, one)
+            for _ in range(3):
+                w1.step(one["dt"], one["gravity"])
+            k1 = max(3, min(args.steps, 10))
+            ms1 = 0.0
+            for _ in range(k1):
+                w1.step(one["dt"], one["gravity"])
+                ms1 += w1.stats()["step_ms"]
+            n1 = len(one["fluids"][0]["positions"])
+            slice_ref = {"what": "the %d-particle slice one rank owns, stepped alone on one GPU (no slabs), %d steps" % (n1, k1),
+                         "value": n1 * k1 / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1 / k1}
+            w1.close()
+        barrier()
     if rank != 0:
-        if parity is not None and world_size > 1:
-            pass
         return 0
     peak, peak_src = peaks()
     # ---- roofline of the pressure iteration kernels (K8a + K8b), algorithmic bytes / CUDA-event time, PER GPU ------
@@ -533,7 +552,7 @@ def native_arm(args, rank, world_size):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "sph_fluid_write + sph_world_step + sph_fluid_read (pinned host buffers), all ranks"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "parity": parity, "settled": settled}
+            "parity": parity, "settled": settled, "single_gpu_slice": slice_ref}
     print(json.dumps(line), flush=True)
     if parity is not None and not parity.get("ok", False):
         sys.stderr.write("PARITY FAILED: %s\n" % json.dumps(parity))
@@ -556,6 +575,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-settled", action="store_true")
+    ap.add_argument("--no-slice-ref", action="store_true", help="N > 1: skip the 1-GPU run of one rank's slice")
     ap.add_argument("--fast-sort", action="store_true", help="skip the deterministic in-cell ordering")
     ap.add_argument("--force-iters", type=int, nargs=2, default=None)
     ap.add_argument("--backend", type=int, default=0, help="0 = L1 gathers (default), 1 = tile/TMA shared-memory gathers")

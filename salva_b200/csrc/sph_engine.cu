@@ -221,7 +221,8 @@ struct sph_world {
     // gather_backend 0: the second per-contact gather (v* / kappa) can go through the texture pipe
     // uniform-mass packed gather records (sph_passes.cuh): pvx4 = (x,y,z,v*x), vyz2 = (v*y,v*z), pk4 = (x,y,z,kappa)
     bool unimass = false;
-    int uni_eval_mode = 1, uni_upd_mode = 2;  // 1: position record through the texture pipe, 2: through the LSU pipe, 3 (update): alternate
+    int uni_eval_mode = 1, uni_upd_mode = 1;  // 1: gathers split evenly over the texture and LSU pipes (even / odd contacts), 2: the
+                                              // position record through the LSU pipe only (second record, if any, through TEX)
     DBuf<float4> pvx4, pk4;
     DBuf<float2> vyz2;
     DBuf<Rec8> rec8, nrec8;  // 256-bit gather records: (pos, v*, rho) of the evaluations, (pos, normal, rho) of the Akinci force pass
@@ -271,6 +272,10 @@ struct sph_world {
 
     uint32_t cap_f = 64, cap_b = 32, stride = 0;
     bool lists_valid = false;
+    // cell-coordinate AABB of the positions the last step wrote (k_update_positions): sizes the next grid without a bounds pass
+    bool nb_valid = false, nb_pending = false;
+    int nb[7] = {0, 0, 0, 0, 0, 0, 0};
+    DBuf<int> d_nb;
     bool grid_ready = false;    // cstart/bstart + sorted arrays describe the last step's cell grid (AABB queries)
     bool ever_stepped = false;
     sph_step_stats stats;
@@ -476,6 +481,7 @@ sph_status stage_down(sph_world* w) {
     w->staged = true;
     w->lists_valid = false;
     w->grid_ready = false;
+    w->nb_valid = false;
     return SPH_OK;
 }
 
@@ -512,7 +518,6 @@ sph_status ensure_fluid_buffers(sph_world* w) {
     CU(w->vyz2.ensure(N));
     if (w->use_rec8) CU(w->rec8.ensure(N));
     CU(w->acc.ensure(N));
-    CU(w->dbg_acc.ensure(N));
     CU(w->dens.ensure(N + 8));
     CU(w->alpha.ensure(N + 8));
     CU(w->kappa.ensure(N + 8));
@@ -692,13 +697,20 @@ sph_status phase_grid(sph_world* w) {
     int init[11] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(w->d_scal.p, init, sizeof init, cudaMemcpyHostToDevice, w->st));
     CU(cudaMemsetAsync(w->d_cnt.p, 0, 2 * sizeof(unsigned long long), w->st));
-    if (N) {
-        k_bounds<<<std::min<uint32_t>(cdiv(N, 256), 296), 256, 0, w->st>>>(w->pos[c].p, (uint32_t)N, w->d_scal.p);
-        w->launches++;
-    }
     int hb[7];
-    CU(cudaMemcpyAsync(hb, w->d_scal.p, sizeof hb, cudaMemcpyDeviceToHost, w->st));
-    CU(cudaStreamSynchronize(w->st));
+    if (w->nb_valid && !w->slab.active && N) {
+        // positions are exactly what the last step's k_update_positions wrote (no host edit since): its bounds came back with
+        // that step's final read-back, so this step starts without a bounds pass and without a host round trip
+        memcpy(hb, w->nb, sizeof hb);
+    } else {
+        if (N) {
+            k_bounds<<<std::min<uint32_t>(cdiv(N, 256), 296), 256, 0, w->st>>>(w->pos[c].p, (uint32_t)N, w->d_scal.p);
+            w->launches++;
+        }
+        CU(cudaMemcpyAsync(hb, w->d_scal.p, sizeof hb, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaStreamSynchronize(w->st));
+    }
+    w->nb_valid = false;
     if (hb[6] || w->b_bad) return w->fail(SPH_ERR_INVALID, "non-finite or out-of-range particle coordinates");
     for (int a = 0; a < 3; ++a) {  // boundary AABB: static, kept on the host
         hb[a] = std::min(hb[a], w->b_aabb[a]);
@@ -1119,8 +1131,12 @@ sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
     int c = w->cur, bc = w->bcur;
     const bool multi = w->fluids.size() > 1;
     Lists L{reinterpret_cast<const uint4*>(w->nbr_f.p), w->nbr_b.p, w->cnt_f.p, w->cnt_b.p, w->g_f.p};
-    if (w->unimass) TRY(ensure_tex(w, &w->tex_vyz, &w->tex_vyz_ptr, w->vyz2.p, w->vyz2.cap));
-    else TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
+    if (w->unimass) {
+        TRY(ensure_tex(w, &w->tex_vyz, &w->tex_vyz_ptr, w->vyz2.p, w->vyz2.cap));
+        TRY(ensure_tex(w, &w->tex_pvx, &w->tex_pvx_ptr, w->pvx4.p, w->pvx4.cap));
+    } else {
+        TRY(ensure_tex(w, &w->tex_vs, &w->tex_vs_ptr, w->vs.p, w->vs.cap));
+    }
     const size_t nf = std::max<size_t>(1, w->fluids.size());
     sph_status rs = run_parts(w, nullptr, 0, nblk, [&](Range rg, uint32_t blk) -> sph_status {
         float* partial = w->partial.p + (size_t)blk * nf;
@@ -1129,13 +1145,13 @@ sph_status launch_density_alpha_div(sph_world* w, uint32_t* nblk) {
             LAUNCH_R(k_density_alpha_div_r8, rg, w->rec8.p, w->bpos[bc].p, L, w->dens.p, w->alpha.p, w->divv.p, w->pk4.p, partial, w->d_scal.p + 7, tk,
                      w->errsum.p);
         else if (w->unimass)
-            LAUNCH_R((k_density_alpha_div<false, true>), rg, w->pvx4.p, w->vs.p, (cudaTextureObject_t)0, w->vyz2.p, w->tex_vyz, w->vel[c].p, w->bpos[bc].p, L,
+            LAUNCH_R((k_density_alpha_div<false, true>), rg, w->pvx4.p, w->tex_pvx, w->vs.p, (cudaTextureObject_t)0, w->vyz2.p, w->tex_vyz, w->vel[c].p, w->bpos[bc].p, L,
                      w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7, tk, w->errsum.p);
         else if (multi)
-            LAUNCH_R((k_density_alpha_div<true, false>), rg, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p, w->bpos[bc].p,
+            LAUNCH_R((k_density_alpha_div<true, false>), rg, w->pos[c].p, (cudaTextureObject_t)0, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p, w->bpos[bc].p,
                      L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7, tk, w->errsum.p);
         else
-            LAUNCH_R((k_density_alpha_div<false, false>), rg, w->pos[c].p, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p, w->bpos[bc].p,
+            LAUNCH_R((k_density_alpha_div<false, false>), rg, w->pos[c].p, (cudaTextureObject_t)0, w->vs.p, w->tex_vs, w->vyz2.p, (cudaTextureObject_t)0, w->vel[c].p, w->bpos[bc].p,
                      L, w->g_f.p, w->dens.p, w->alpha.p, w->divv.p, w->kappa.p, w->pk4.p, partial, w->d_scal.p + 7, tk, w->errsum.p);
         return SPH_OK;
     });
@@ -1656,7 +1672,7 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
     timestep_advance(w, dt_total);  // :702
     const bool r8 = rec8_predict(w);
-    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p, w->unimass ? w->pvx4.p : nullptr,
+    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->unimass ? w->pvx4.p : nullptr,
            w->unimass ? w->vyz2.p : nullptr, w->pos[c].p, r8 ? w->rec8.p : nullptr, w->dens.p);
     TRY(refresh_vstar(w));
     CU(cudaEventRecord(w->ev[EV_INTEG], w->st));
@@ -1691,7 +1707,13 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     }
     CU(cudaEventRecord(w->ev[EV_PRESS], w->st));
     TRY(slab_wait(w));  // a speculative exchange may still be in flight: it must land before the arrays are reused
-    LAUNCH(k_update_positions, N, 256, w->pos[c].p, w->vs.p, w->dt);  // :411-420
+    {
+        static const int init[7] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0};
+        CU(w->d_nb.ensure(8));
+        CU(cudaMemcpyAsync(w->d_nb.p, init, sizeof init, cudaMemcpyHostToDevice, w->st));
+        LAUNCH(k_update_positions, N, 256, w->pos[c].p, w->vs.p, w->dt, w->slab.active ? (int*)nullptr : w->d_nb.p);  // :411-420
+        w->nb_pending = !w->slab.active;
+    }
     CU(cudaGetLastError());
     return SPH_OK;
 }
@@ -1701,6 +1723,7 @@ sph_status world_step(sph_world* w, float dt, const float g[3], const sph_coupli
     w->launches = 0;
     w->stats_exchanges = 0;
     w->n_spans = 0;
+    w->nb_pending = false;
     memset(&w->stats, 0, sizeof w->stats);
     TRY(apply_pending_deletes(w));  // liquid_world.rs:79-81
     TRY(stage_up(w));
@@ -1768,7 +1791,10 @@ sph_status world_step(sph_world* w, float dt, const float g[3], const sph_coupli
     unsigned long long cnts[2] = {0, 0};
     CU(cudaMemcpyAsync(&flag, w->d_scal.p + 7, sizeof(int), cudaMemcpyDeviceToHost, w->st));
     CU(cudaMemcpyAsync(cnts, w->d_cnt.p, sizeof cnts, cudaMemcpyDeviceToHost, w->st));
+    if (w->nb_pending) CU(cudaMemcpyAsync(w->nb, w->d_nb.p, sizeof w->nb, cudaMemcpyDeviceToHost, w->st));
     CU(cudaStreamSynchronize(w->st));
+    w->nb_valid = w->nb_pending;
+    w->nb_pending = false;
     CU(cudaGetLastError());
     if (!w->b_reused) w->bb_contacts = cnts[0];
     w->stats.n_contacts = w->bb_contacts + cnts[1];
@@ -1930,6 +1956,7 @@ void sph_world_destroy(sph_world* w) {
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     w->d_ctl.release();
     w->d_ticket.release();
+    w->d_nb.release();
     w->xs.release(); w->he_colors.release(); w->he_gradc.release(); w->q_out.release(); w->q_count.release();
     for (auto& e : w->ev)
         if (e) cudaEventDestroy(e);
@@ -2095,6 +2122,7 @@ sph_status sph_fluid_write(sph_world* w, uint32_t fluid_h, const float* pos, con
     }
     CU(cudaStreamSynchronize(w->st));
     w->lists_valid = false;
+    if (pos) w->nb_valid = false;  // the cached bounds describe the positions the last step wrote
     return SPH_OK;
 }
 
@@ -2402,7 +2430,7 @@ sph_status sph_debug_read(sph_world* w, uint32_t fluid_h, int what, float* out, 
     const uint32_t* og = w->orig[c].p + ob;
     if (s1) LAUNCH(k_export1, N, 256, (uint32_t)N, og, s1 + ob, w->o_c.p);
     else if (what == SPH_DBG_VELOCITY_CHANGE) LAUNCH(k_export3, N, 256, (uint32_t)N, og, w->vc[c].p + ob, w->o_c.p);
-    else if (what == SPH_DBG_ACCELERATION) LAUNCH(k_export3, N, 256, (uint32_t)N, og, w->dbg_acc.p + ob, w->o_c.p);
+    else if (what == SPH_DBG_ACCELERATION) LAUNCH(k_export3, N, 256, (uint32_t)N, og, w->acc.p + ob, w->o_c.p);
     else if (what == SPH_DBG_NUM_FLUID_CONTACTS) LAUNCH(k_export1u, N, 256, (uint32_t)N, og, w->cnt_f.p + ob, w->o_c.p);
     else if (what == SPH_DBG_NUM_BOUNDARY_CONTACTS) LAUNCH(k_export1u, N, 256, (uint32_t)N, og, w->cnt_b.p + ob, w->o_c.p);
     else return w->fail(SPH_ERR_INVALID, "sph_debug_read: unknown selector %d", what);

@@ -50,7 +50,7 @@ sph_status iisph_step(sph_world* w, float dt_total, const float g[3]) {
     TRY(phase_forces(w));
     CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
     timestep_advance(w, dt_total);
-    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->dbg_acc.p, (float4*)nullptr, (float2*)nullptr, (const float4*)nullptr, (Rec8*)nullptr, (const float*)nullptr);  // :662
+    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, (float4*)nullptr, (float2*)nullptr, (const float4*)nullptr, (Rec8*)nullptr, (const float*)nullptr);  // :662
     CU(cudaEventRecord(w->ev[EV_INTEG], w->st));
     DISPATCH1(k_iisph_dii, multi, N, PASS_T, w->pos[c].p, w->vel[c].p, w->bpos[bc].p, L, w->dens.p, S.dii, w->dt);            // :665-671
     LAUNCH(k_iisph_warm_start, N, 256, w->press[c].p, w->dens.p, S.prho);                                                        // :673-677

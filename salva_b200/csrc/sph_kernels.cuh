@@ -733,13 +733,14 @@ __global__ void k_set_gravity(const float4* __restrict__ vel, float4* __restrict
     acc[i] = make_float4(gx, gy, gz, 0.f);
 }
 
-// a18: integrate_and_clear_accelerations dfsph_solver.rs:505-518 (+ v* = vel + vc)
-__global__ void k_integrate_acc(const float4* __restrict__ vel, float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ acc, float dt,
-                                float4* __restrict__ dbg_acc, float4* __restrict__ pvx, float2* __restrict__ vyz, const float4* __restrict__ pos,
-                                Rec8* __restrict__ rec, const float* __restrict__ dens) {
+// a18: integrate_and_clear_accelerations dfsph_solver.rs:505-518 (+ v* = vel + vc).  The accelerations are NOT cleared here:
+// the next step's k_fold_velocities / k_set_gravity overwrites them with gravity before any force adds to them, so the
+// array doubles as the SPH_DBG_ACCELERATION view and the pass saves 32 B per particle of stores.
+__global__ void k_integrate_acc(const float4* __restrict__ vel, float4* __restrict__ vc, float4* __restrict__ vs, const float4* __restrict__ acc, float dt,
+                                float4* __restrict__ pvx, float2* __restrict__ vyz, const float4* __restrict__ pos, Rec8* __restrict__ rec,
+                                const float* __restrict__ dens) {
     SPH_OWNED_INDEX(i)
     float4 a = acc[i], c = vc[i], v = vel[i];
-    if (dbg_acc) dbg_acc[i] = a;
     c.x += a.x * dt; c.y += a.y * dt; c.z += a.z * dt;
     vc[i] = c;
     float sx = v.x + c.x, sy = v.y + c.y, sz = v.z + c.z;
@@ -751,15 +752,65 @@ __global__ void k_integrate_acc(const float4* __restrict__ vel, float4* __restri
         pvx[i].w = sx;  // xyz already hold the position
         vyz[i] = make_float2(sy, sz);
     }
-    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// a22: update_positions dfsph_solver.rs:411-420: pos += (vel + vc) * dt
-__global__ void k_update_positions(float4* __restrict__ pos, const float4* __restrict__ vs, float dt) {
-    SPH_OWNED_INDEX(i)
-    float4 p = pos[i], v = vs[i];
-    p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
-    pos[i] = p;
+// a22: update_positions dfsph_solver.rs:411-420: pos += (vel + vc) * dt.  bounds_out (optional): the cell-coordinate AABB of
+// the NEW positions (what k_bounds computes), so the next step's grid is sized without a bounds pass and its host round trip.
+__global__ void k_update_positions(float4* __restrict__ pos, const float4* __restrict__ vs, float dt, int* __restrict__ bounds_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < C.n_owned;
+    i += C.i_begin;
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    int bad = 0;
+    if (valid) {
+        float4 p = pos[i], v = vs[i];
+        p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
+        pos[i] = p;
+        if (bounds_out) {
+            const float c[3] = {floorf(__fdiv_rn(p.x, C.h)), floorf(__fdiv_rn(p.y, C.h)), floorf(__fdiv_rn(p.z, C.h))};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (!(fabsf(c[a]) < 1.0e9f)) { bad = 1; continue; }  // NaN / inf / absurd coordinates
+                mn[a] = mx[a] = (int)c[a];
+            }
+        }
+    }
+    if (!bounds_out) return;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    bad = __any_sync(0xffffffffu, bad);
+    __shared__ int s_mn[3][8], s_mx[3][8], s_bad[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            s_mn[a][wid] = mn[a];
+            s_mx[a][wid] = mx[a];
+        }
+        s_bad[wid] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {  // one atomic pair per axis per block
+        const int a = threadIdx.x, nw = (blockDim.x + 31) >> 5;
+        int m0 = INT_MAX, m1 = INT_MIN;
+        for (int k = 0; k < nw; ++k) {
+            m0 = min(m0, s_mn[a][k]);
+            m1 = max(m1, s_mx[a][k]);
+        }
+        if (m0 <= m1) {
+            atomicMin(&bounds_out[a], m0);
+            atomicMax(&bounds_out[3 + a], m1);
+        }
+        if (a == 0) {
+            int b = 0;
+            for (int k = 0; k < nw; ++k) b |= s_bad[k];
+            if (b) atomicOr(&bounds_out[6], 1);
+        }
+    }
 }
 
 __device__ __forceinline__ float powi3(float x) { return x * x * x; }

@@ -7,6 +7,8 @@
 // prefetched before the current one is used), then 4 position gathers + 4 auxiliary gathers are issued back to back
 // and only then the 4 pair evaluations run, so 8+ independent loads are in flight per thread.
 #pragma once
+#include <type_traits>
+
 #include "sph_kernels.cuh"
 
 namespace sphk {
@@ -22,6 +24,16 @@ struct Lists {
 };
 
 struct NoAux {};
+
+// Gather lambdas may take the contact's position u in its group of four as a second argument: kernels use it to send the
+// gathers of even and odd contacts through DIFFERENT L1TEX front ends (texture pipe / LSU pipe).  ncu on the round-1 kernels
+// (profiles/r2_ncu_pair_c3.md): the update pass ran at 88 % of the LSU data-pipe wavefront peak with the texture pipe idle, the
+// evaluation at 60 % TEX / 44 % LSU; splitting every gather stream over both pipes is worth 10-15 % of those passes.
+template <class F>
+__device__ __forceinline__ auto call_gather(F& f, uint32_t j, int u) {
+    if constexpr (std::is_invocable_v<F, uint32_t, int>) return f(j, u);
+    else return f(j);
+}
 
 // Slot range a launch covers.  One launch normally covers all owned slots; a slab world splits the Jacobi-loop kernels
 // into [boundary columns] + [interior] so the ghost exchange of the boundary columns overlaps the interior launch.
@@ -65,10 +77,10 @@ __device__ __forceinline__ void for_fluid_contacts_g(uint32_t i, const float4& p
         }
         float4 pj[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) pj[u] = ldpos(j[u]);
-        decltype(ld(0u)) aux[4];
+        for (int u = 0; u < 4; ++u) pj[u] = call_gather(ldpos, j[u], u);
+        decltype(call_gather(ld, 0u, 0)) aux[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) aux[u] = ld(j[u]);
+        for (int u = 0; u < 4; ++u) aux[u] = call_gather(ld, j[u], u);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (ok[u]) {
@@ -109,10 +121,10 @@ __device__ __forceinline__ void for_fluid_grads(uint32_t i, const float4& pi, co
         const float g[4] = {Gq.x, Gq.y, Gq.z, Gq.w};
         float4 pj[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) pj[u] = ldpos(j[u]);
-        decltype(ld(0u)) aux[4];
+        for (int u = 0; u < 4; ++u) pj[u] = call_gather(ldpos, j[u], u);
+        decltype(call_gather(ld, 0u, 0)) aux[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) aux[u] = ld(j[u]);
+        for (int u = 0; u < 4; ++u) aux[u] = call_gather(ld, j[u], u);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             Pair p;
@@ -265,7 +277,7 @@ struct Vel3 {
 };
 template <bool MULTI, bool UNI>
 __global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
-k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, const float4* __restrict__ vs, cudaTextureObject_t tvs,
+k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, cudaTextureObject_t tposrec, const float4* __restrict__ vs, cudaTextureObject_t tvs,
                     const float2* __restrict__ vyz, cudaTextureObject_t tvyz, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
                     float4* __restrict__ g_out, float* __restrict__ dens, float* __restrict__ alpha, float* __restrict__ divv, float* __restrict__ kappa,
                     float4* __restrict__ pk4, float* __restrict__ partial, int* __restrict__ err, uint32_t* __restrict__ ticket,
@@ -303,11 +315,11 @@ k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, const 
             float4 pj[4];
             Vel3 vj[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) pj[u] = __ldg(&posrec[j[u]]);  // tail slots point at i itself
+            for (int u = 0; u < 4; ++u) pj[u] = (UNI && (u & 1)) ? tex1Dfetch<float4>(tposrec, (int)j[u]) : __ldg(&posrec[j[u]]);  // tail slots point at i itself
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (UNI) {
-                    float2 b = tex1Dfetch<float2>(tvyz, (int)j[u]);
+                if (UNI) {  // even contacts: (record via LSU, velocity via TEX), odd ones the other way round
+                    float2 b = (u & 1) ? __ldg(&vyz[j[u]]) : tex1Dfetch<float2>(tvyz, (int)j[u]);
                     vj[u] = Vel3{pj[u].w, b.x, b.y};
                 } else {
                     float4 s = tex1Dfetch<float4>(tvs, (int)j[u]);
@@ -491,9 +503,10 @@ k_vel_divergence_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx, con
         const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
         float d = 0.f;
         if (PREDICT || L.cnt_f[i] + L.cnt_b[i] >= 20u) {
+            // POS_TEX: even contacts fetch (pvx via TEX, vyz via LSU), odd ones the other way round, so both pipes carry the same load
             for_fluid_grads<false>(
-                i, pi, L, [&](uint32_t j) { return POS_TEX ? tex1Dfetch<float4>(tpvx, (int)j) : __ldg(&pvx[j]); },
-                [&](uint32_t j) { return POS_TEX ? __ldg(&vyz[j]) : tex1Dfetch<float2>(tvyz, (int)j); },
+                i, pi, L, [&](uint32_t j, int u) { return (POS_TEX && !(u & 1)) ? tex1Dfetch<float4>(tpvx, (int)j) : __ldg(&pvx[j]); },
+                [&](uint32_t j, int u) { return (POS_TEX && !(u & 1)) ? __ldg(&vyz[j]) : tex1Dfetch<float2>(tvyz, (int)j); },
                 [&](uint32_t, const Pair& p, const float4& pj, const float2& wj) {
                     float dv = (vix - pj.w) * p.dx + (viy - wj.x) * p.dy + (viz - wj.y) * p.dz;
                     d = fmaf(dv * p.g, mass, d);
@@ -775,8 +788,8 @@ k_vel_divergence_xsph_u(const float4* __restrict__ pvx, cudaTextureObject_t tpvx
         const bool gated = L.cnt_f[i] + L.cnt_b[i] < 20u;  // dfsph_solver.rs:301-314
         float d = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
         for_fluid_grads<false, EXTRA == 1>(
-            i, pi, L, [&](uint32_t j) { return POS_TEX ? tex1Dfetch<float4>(tpvx, (int)j) : __ldg(&pvx[j]); },
-            [&](uint32_t j) { return VyzRho{POS_TEX ? __ldg(&vyz[j]) : tex1Dfetch<float2>(tvyz, (int)j), __ldg(&dens[j])}; },
+            i, pi, L, [&](uint32_t j, int u) { return (POS_TEX && !(u & 1)) ? tex1Dfetch<float4>(tpvx, (int)j) : __ldg(&pvx[j]); },
+            [&](uint32_t j, int u) { return VyzRho{(POS_TEX && !(u & 1)) ? __ldg(&vyz[j]) : tex1Dfetch<float2>(tvyz, (int)j), __ldg(&dens[j])}; },
             [&](uint32_t, const Pair& p, const float4& pj, const VyzRho& wj) {
                 float dv = (vix - pj.w) * p.dx + (viy - wj.v.x) * p.dy + (viz - wj.v.y) * p.dz;
                 d = fmaf(dv * p.g, mass, d);
@@ -867,7 +880,7 @@ k_vel_update_u(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const fl
     const float scale = (PRESSURE ? inv_dt : 1.0f) * mass;
     float ax = 0.f, ay = 0.f, az = 0.f;
     for_fluid_grads<false>(
-        i, pi, L, [&](uint32_t j) { return POS_TEX ? tex1Dfetch<float4>(tpk, (int)j) : __ldg(&pk4[j]); }, [](uint32_t) { return NoAux{}; },
+        i, pi, L, [&](uint32_t j, int u) { return (POS_TEX && !(u & 1)) ? tex1Dfetch<float4>(tpk, (int)j) : __ldg(&pk4[j]); }, [](uint32_t) { return NoAux{}; },
         [&](uint32_t, const Pair& p, const float4& pj, NoAux) {
             float c = (ki + pj.w) * scale * p.g;
             ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
