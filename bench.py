@@ -282,16 +282,22 @@ def parity_vs_oracle(cfg, device, edge=64, steps=3):
     for w in (gpu, cpu):
         w.force_iterations(2, 3)
     t0 = time.perf_counter()
-    for _ in range(steps):
+    contacts_equal = None
+    for k in range(steps):
         gpu.step(sc["dt"], sc["gravity"])
         cpu.step(sc["dt"], sc["gravity"])
+        if k == 0:
+            # exact comparison on IDENTICAL inputs (the first step's positions); from the second step on the two trajectories
+            # differ by ~1e-6 h and a few of the 9M pairs sit that close to the cutoff, so later counts may differ legitimately
+            contacts_equal = bool(np.array_equal(gpu.debug(fg, "num_fluid_contacts"), cpu.debug(fc, "num_fluid_contacts")) and
+                                  np.array_equal(gpu.debug(fg, "num_boundary_contacts"), cpu.debug(fc, "num_boundary_contacts")))
     pg, vg = gpu.read_fluid(fg)
     pc, vc = cpu.read_fluid(fc)
     h = float(gpu.h)
     rg, rc = gpu.debug(fg, "density"), cpu.debug(fc, "density")
     res = {"n": int(len(pg)), "steps": steps, "forced_iterations": [2, 3], "scene": "%s generator, edge %d, lattice 0.93-compressed" % (cfg.upper(), edge),
-           "contacts_equal": bool(np.array_equal(gpu.debug(fg, "num_fluid_contacts"), cpu.debug(fc, "num_fluid_contacts")) and
-                                  np.array_equal(gpu.debug(fg, "num_boundary_contacts"), cpu.debug(fc, "num_boundary_contacts"))),
+           "contacts_equal": contacts_equal,
+           "contact_count_mismatches_last_step": int((gpu.debug(fg, "num_fluid_contacts") != cpu.debug(fc, "num_fluid_contacts")).sum()),
            "max_dx_over_h": float(np.abs(pg - pc).max() / h),
            "max_dv_over_h_dt": float(np.abs(vg - vc).max() / (h / sc["dt"])),
            "max_rel_rho": float(np.abs(rg - rc).max() / np.abs(rc).max()),

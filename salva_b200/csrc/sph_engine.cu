@@ -1891,7 +1891,9 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     w->tile = desc->gather_backend == 1 && desc->solver == SPH_SOLVER_DFSPH;  // the tile backend covers the DFSPH passes only
     if (desc->kernel_density || desc->kernel_gradient) w->use_gcache = 0;
     if (const char* t = getenv("SALVA_B200_DEVICE_LOOPS")) w->device_loops = atoi(t) != 0;
+#if SPH_GCACHE
     if (const char* t = getenv("SALVA_B200_GCACHE")) w->use_gcache = atoi(t);
+#endif
     if (const char* t = getenv("SALVA_B200_REC8")) w->use_rec8 = atoi(t);
     if (const char* t = getenv("SALVA_B200_FUSE_DIV")) w->fuse_div = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_FUSE_XSPH")) w->fuse_xsph = atoi(t) != 0;

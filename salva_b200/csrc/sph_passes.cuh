@@ -47,6 +47,12 @@ struct Range {
 #ifndef SPH_LIST_PREFETCH
 #define SPH_LIST_PREFETCH 0
 #endif
+// Cached gradient scalars (g_f): measured slower in rounds 1 and 2 (profiles/r2_exp_a_variants.md) and, worse, the runtime
+// switch between the cached and the recomputed path sits inside the 4-way unrolled contact loops, where a uniform branch
+// costs ~10 % (k_vel_update_u 0.0653 ms with it vs 0.0578 ms without, C2).  Compiled out unless -DSPH_GCACHE=1.
+#ifndef SPH_GCACHE
+#define SPH_GCACHE 0
+#endif
 __device__ __forceinline__ uint4 ld_list(const uint4* p) { return __ldcs(p); }
 __device__ __forceinline__ float4 ld_list(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ void prefetch_list(const void* p) {
@@ -104,7 +110,7 @@ __device__ __forceinline__ void for_fluid_grads(uint32_t i, const float4& pi, co
     const uint32_t n = min(L.cnt_f[i], C.cap_f);
     const uint32_t nq = (n + 3u) >> 2;
     if (nq == 0) return;
-    const bool cached = C.use_gcache != 0;
+    const bool cached = SPH_GCACHE && C.use_gcache != 0;  // compile-time off: the uniform branch inside the unrolled group costs ~10 % of a pass
     const uint4* col = L.nbr_f + i;
     const float4* gcol = L.g_f + i;
     uint4 J = ld_list(col);
@@ -247,7 +253,7 @@ k_density_alpha(const float4* __restrict__ pos, const float4* __restrict__ vel, 
                     gx += ax; gy += ay; gz += az;
                 }
             }
-            if (C.use_gcache) g_out[(size_t)q * C.stride + i] = make_float4(g[0], g[1], g[2], g[3]);  // helper.rs:24-25, cached for the step
+            if (SPH_GCACHE && C.use_gcache) g_out[(size_t)q * C.stride + i] = make_float4(g[0], g[1], g[2], g[3]);  // helper.rs:24-25, cached for the step
             J = Jn;
         }
     }
@@ -343,7 +349,7 @@ k_density_alpha_div(const float4* __restrict__ posrec /* pos4 or pvx4 */, cudaTe
                     d = fmaf(dv * p.g, mj, d);
                 }
             }
-            if (C.use_gcache) g_out[(size_t)q * C.stride + i] = make_float4(g[0], g[1], g[2], g[3]);
+            if (SPH_GCACHE && C.use_gcache) g_out[(size_t)q * C.stride + i] = make_float4(g[0], g[1], g[2], g[3]);
             J = Jn;
         }
         for_boundary_contacts<true, true>(i, pi, L, bpos, [&](uint32_t, const Pair& p, const float4& pj) {
