@@ -478,7 +478,7 @@ def native_arm(args, rank, world_size):
 
     # ---- second measurement: compressed start (lattice spacing 0.90 * 2r, +10 % density), Jacobi loops iterate ---------
     settled = None
-    if not args.no_settled:
+    if not args.no_settled and world_size == 1:   # one GPU only: the driver's scaling runs stay as short (and as safe) as possible
         sc2, w2, _ = make_world(compress=0.90)
         for _ in range(3):
             w2.step(sc2["dt"], sc2["gravity"])
@@ -591,11 +591,22 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank, world_size)
         return 0
-    rc = native_arm(args, rank, world_size)
+    try:
+        rc = native_arm(args, rank, world_size)
+    except BaseException:
+        # one rank failing must not leave its peers (or its own tear-down) waiting in a collective: report and leave at once;
+        # torchrun then stops the other ranks
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.stdout.flush()
+        os._exit(1)
     if world_size > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(rc)   # skip interpreter tear-down: destroying NCCL communicators of already-finished peers can block
     return rc
 
 

@@ -1017,11 +1017,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-// bounded spin (a peer that never arrives must not hang the GPU): ~4 s of SM clock, then the error flag
+// bounded spin (a peer that never arrives must not hang the GPU): ~2 s of SM clock, then the (sticky) error flag
 __device__ __forceinline__ bool p2p_wait(const uint32_t* flag, uint32_t seq, int* err) {
+    if (*reinterpret_cast<volatile int*>(err) & 2) return false;  // an earlier exchange of this step already timed out: do not wait again
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(flag) - seq) < 0) {
-        if (clock64() - t0 > 8000000000LL) {
+        if (clock64() - t0 > 4000000000LL) {
             atomicOr(err, 2);
             return false;
         }

@@ -241,17 +241,34 @@ def scene_c4(nx=512, ny=250, nz=250, **kw):
 
 def slab_scene(scene_fn, rank, nranks, nx, **kw):
     """Rank `rank`'s slab of a dam-break scene whose block is nx lattice planes long in x, generated WITHOUT building the
-    other ranks' particles: h = 4r, so lattice planes 2c and 2c+1 fall in cell column c and (jitter < r) never leave it;
-    rank r owns the cell columns [r*ncol/nranks, (r+1)*ncol/nranks).  Returns the partitioned scene dict that
-    salva_b200.slab.populate_slab() accepts (fluids carry global ids, `slab` = owned cell columns)."""
-    ncol = nx // 2
-    assert nx % 2 == 0 and ncol >= 2 * nranks, "block too short for %d slabs" % nranks
-    c0, c1 = rank * ncol // nranks, (rank + 1) * ncol // nranks
-    sc = scene_fn(x_range=(2 * c0, 2 * c1), **kw)
+    other ranks' particles.  Lattice plane i sits at x_i = (2 i + 1) r c (c = `compress`, jitter < amplitude * r on top); the
+    cut before plane i is legal when a cell boundary k*h (h = 4 r) separates planes i-1 and i with the jitter margin, so
+    that both sides own whole cell columns.  The cuts are the legal ones closest to an even split.  Returns the partitioned
+    scene dict that salva_b200.slab.populate_slab() accepts (fluids carry global ids, `slab` = owned cell columns)."""
+    probe = scene_fn(x_range=(0, 0), **kw)
+    r = float(probe["particle_radius"])
+    c = float(kw.get("compress", 1.0))
+    amp = float(kw.get("amplitude", 0.05)) * r
+    h = np.float32(r) * np.float32(probe["smoothing_factor"]) * np.float32(2.0)
+    rr = F32(r * c)
+    x = ((np.arange(nx, dtype=F32) * F32(2.0) + F32(1.0)) * rr).astype(np.float64)   # same f32 arithmetic as the generator
+    col_hi_prev = np.floor((x[:-1] + amp * 1.001) / float(h))   # largest column plane i-1 can reach
+    col_lo_next = np.floor((x[1:] - amp * 1.001) / float(h))    # smallest column plane i can reach
+    legal = np.nonzero(col_lo_next > col_hi_prev)[0] + 1        # cut before plane i
+    cuts = [0]
+    for k in range(1, nranks):
+        target = k * nx / nranks
+        cand = legal[legal > cuts[-1] + 3]
+        assert len(cand), "block too short for %d slabs" % nranks
+        cuts.append(int(cand[np.argmin(np.abs(cand - target))]))
+    cuts.append(nx)
+    assert all(b - a >= 4 for a, b in zip(cuts[:-1], cuts[1:])), "block too short for %d slabs" % nranks
+    i0, i1 = cuts[rank], cuts[rank + 1]
+    sc = scene_fn(x_range=(i0, i1), **kw)
     f = sc["fluids"][0]
-    ny_nz = len(f["positions"]) // (2 * (c1 - c0))
-    f["ids"] = (np.arange(len(f["positions"]), dtype=np.int64) + 2 * c0 * ny_nz).astype(np.uint32)
-    planes = [-2 ** 31] + [r * ncol // nranks for r in range(1, nranks)] + [2 ** 31 - 1]
+    ny_nz = len(f["positions"]) // (i1 - i0)
+    f["ids"] = (np.arange(len(f["positions"]), dtype=np.int64) + i0 * ny_nz).astype(np.uint32)
+    planes = [-2 ** 31] + [int(np.floor((x[k] - amp * 1.001) / float(h))) for k in cuts[1:-1]] + [2 ** 31 - 1]
     sc["slab"] = (planes[rank], planes[rank + 1])
     sc["planes"] = planes
     sc["partitioned"] = True
@@ -272,6 +289,7 @@ def scene_c5(n=100):
                 fluids=[dict(positions=lower, density0=1000.0, forces=list(forces)),
                         dict(positions=upper, density0=800.0, forces=list(forces))],
                 boundaries=[dict(positions=open_tank(lo, hi, r))])
+
 
 
 def populate(world, scene):

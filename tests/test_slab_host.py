@@ -126,3 +126,21 @@ def test_planes_from_histogram_matches_slab_planes():
     hist = np.bincount(cols - lo)
     for nranks in (2, 3, 4):
         assert slab.planes_from_histogram(hist, lo, nranks) == slab.slab_planes(pos, h, nranks)
+
+
+def test_slab_scene_generates_each_ranks_slab_without_the_others():
+    """scenes.slab_scene (what bench.py uses for the C4 slices): per-rank generation must reproduce the partition of the whole
+    scene bit for bit — also for compressed lattices, where cell boundaries no longer fall between fixed lattice planes."""
+    for comp, amp in ((1.0, 0.05), (0.9, 0.05), (0.93, 0.3)):
+        full = scenes.scene_c4(32, 6, 5, compress=comp, amplitude=amp)
+        h = np.float32(0.1)
+        for nranks in (2, 4):
+            total = 0
+            for r in range(nranks):
+                sc = scenes.slab_scene(lambda **kw: scenes.scene_c4(32, 6, 5, **kw), r, nranks, 32, compress=comp, amplitude=amp)
+                p = sc["fluids"][0]["positions"]
+                assert slab.owned_mask(p, h, sc["slab"][0], sc["slab"][1]).all()
+                ref = slab.partition_scene(full, r, nranks, planes=sc["planes"])
+                assert np.array_equal(ref["fluids"][0]["positions"], p) and np.array_equal(ref["fluids"][0]["ids"], sc["fluids"][0]["ids"])
+                total += len(p)
+            assert total == 32 * 6 * 5

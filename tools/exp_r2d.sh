@@ -7,23 +7,17 @@ mkdir -p gpurun_out
 O=gpurun_out
 nvidia-smi -L > $O/r2d_gpus_$N.txt
 nvidia-smi topo -m >> $O/r2d_gpus_$N.txt 2>&1
-if [ "$N" = "2" ]; then
-  (timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -25) > $O/pytest_gpu_2gpu.txt
-  echo "== 1-GPU check of the build (g-cache branch compiled out)" > $O/exp_r2d.txt
-  for cfg in c2 c3; do
-    echo "== $cfg" >> $O/exp_r2d.txt
-    timeout 600 python tools/exp_variants.py $cfg 10 default=salva_b200/libsalva_b200.so upd_alt_kernel=salva_b200/libsalva_b200.so,SALVA_B200_UNI_UPD=3 >> $O/exp_r2d.txt 2>&1
-  done
-  cat $O/exp_r2d.txt
+if [ "$N" = "2" ] && [ "$2" = "tests" ]; then
+  (timeout 600 python -m pytest tests/test_gpu_slab.py -q 2>&1 | tail -25) > $O/pytest_gpu_2gpu.txt
 fi
 run() {  # name, extra env
   local name=$1; shift
-  env "$@" timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
+  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
       bench.py --gpus $N --steps 10 --warmup 3 > $O/bench_${N}gpu_$name.json 2> $O/bench_${N}gpu_$name.err
   tail -c 400 $O/bench_${N}gpu_$name.err
 }
 run p2p SALVA_B200_P2P=1
-run nccl SALVA_B200_P2P=0 BENCH_DUMMY=1
+if [ "$3" != "p2ponly" ]; then run nccl SALVA_B200_P2P=0; fi
 python - <<PY
 import json
 for name in ("p2p", "nccl"):
