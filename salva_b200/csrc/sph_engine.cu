@@ -146,7 +146,9 @@ struct SlabState {
     int lo = INT_MIN, hi = INT_MAX;  // owned cell columns [lo, hi) in absolute cell coordinates floor(x / h)
     int has_left = 0, has_right = 0;
     void* comm = nullptr;
-    DBuf<uint32_t> d_cnt, flag, flag_o, gid_l, gid_r, gid_cl, gid_cr;
+    DBuf<uint32_t> d_cnt, flag, gid_l, gid_r, gid_cl, gid_cr;
+    uint32_t cap_out = 1u << 14, cap_col = 1u << 17;  // staging capacities (emigrants / boundary-column particles per side); grown on demand
+    uint32_t sort_off = 0, sort_n = 0, sort_dead_n = 0;  // what the step's counting sort reads (set by slab_begin_step)
     DBuf<unsigned long long> d_cnt64;
     DBuf<float4> out_l[3], out_r[3], col_l[3], col_r[3];
     bool global_valid = false;
@@ -695,6 +697,12 @@ sph_status apply_pending_deletes(sph_world* w) {
 sph_status phase_grid(sph_world* w) {
     size_t N = w->Ntot, B = w->B;  // the sort covers owned + ghost slots
     int c = w->cur, bc = w->bcur;
+    // slab worlds: the prologue appended immigrants / ghosts behind the owned range of the live arrays and flagged the
+    // particles that left; the sort reads [off, off + Nin) and drops the flagged slots.  Elsewhere: all N slots from 0.
+    const uint32_t off = w->slab.active ? w->slab.sort_off : 0u;
+    const size_t Nin = w->slab.active ? w->slab.sort_n : N;
+    const uint32_t* dead = w->slab.active ? w->slab.flag.p : nullptr;
+    const uint32_t n_dead = w->slab.active ? w->slab.sort_dead_n : 0u;
     int init[11] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(w->d_scal.p, init, sizeof init, cudaMemcpyHostToDevice, w->st));
     CU(cudaMemsetAsync(w->d_cnt.p, 0, 2 * sizeof(unsigned long long), w->st));
@@ -704,8 +712,8 @@ sph_status phase_grid(sph_world* w) {
         // that step's final read-back, so this step starts without a bounds pass and without a host round trip
         memcpy(hb, w->nb, sizeof hb);
     } else {
-        if (N) {
-            k_bounds<<<std::min<uint32_t>(cdiv(N, 256), 296), 256, 0, w->st>>>(w->pos[c].p, (uint32_t)N, w->d_scal.p);
+        if (Nin) {
+            k_bounds<<<std::min<uint32_t>(cdiv(Nin, 256), 296), 256, 0, w->st>>>(w->pos[c].p + off, (uint32_t)Nin, w->d_scal.p);
             w->launches++;
         }
         CU(cudaMemcpyAsync(hb, w->d_scal.p, sizeof hb, cudaMemcpyDeviceToHost, w->st));
@@ -742,21 +750,21 @@ sph_status phase_grid(sph_world* w) {
     w->stats.grid_dims[2] = (uint32_t)dims[2];
     // fluid: counting sort by cell, then reorder every persistent array
     CU(cudaMemsetAsync(w->cstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));
-    LAUNCH(k_cell_hist, N, 256, w->pos[c].p, (uint32_t)N, w->cid.p, w->rank.p, w->cstart.p);
+    LAUNCH(k_cell_hist, Nin, 256, w->pos[c].p + off, (uint32_t)Nin, w->cid.p, w->rank.p, w->cstart.p, dead, n_dead);
     TRY(scan_exclusive(w, w->cstart.p, ncell + 1));
-    LAUNCH(k_cell_scatter, N, 256, (uint32_t)N, w->cid.p, w->rank.p, w->cstart.p, w->perm.p);
+    LAUNCH(k_cell_scatter, Nin, 256, (uint32_t)Nin, w->cid.p, w->rank.p, w->cstart.p, w->perm.p);
     if (w->desc.deterministic)
-        LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->cstart.p, w->perm.p, (const uint32_t*)w->gid[c].p,
-               w->fluids.size() > 1 ? (const float4*)w->vel[c].p : (const float4*)nullptr);
+        LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->cstart.p, w->perm.p, (const uint32_t*)w->gid[c].p + off,
+               w->fluids.size() > 1 ? (const float4*)w->vel[c].p + off : (const float4*)nullptr);
     if (N) {
         GatherSet g;
         memset(&g, 0, sizeof g);
-        g.in4[0] = w->pos[c].p; g.out4[0] = w->pos[c ^ 1].p;
-        g.in4[1] = w->vel[c].p; g.out4[1] = w->vel[c ^ 1].p;
-        g.in4[2] = w->vc[c].p;  g.out4[2] = w->vc[c ^ 1].p;
+        g.in4[0] = w->pos[c].p + off; g.out4[0] = w->pos[c ^ 1].p;
+        g.in4[1] = w->vel[c].p + off; g.out4[1] = w->vel[c ^ 1].p;
+        g.in4[2] = w->vc[c].p + off;  g.out4[2] = w->vc[c ^ 1].p;
         g.n4 = 3;
-        g.in1[0] = w->orig[c].p; g.out1[0] = w->orig[c ^ 1].p;
-        g.in1[1] = w->gid[c].p; g.out1[1] = w->gid[c ^ 1].p;
+        g.in1[0] = w->orig[c].p + off; g.out1[0] = w->orig[c ^ 1].p;  // (slab worlds overwrite orig with the identity after the sort)
+        g.in1[1] = w->gid[c].p + off; g.out1[1] = w->gid[c ^ 1].p;
         g.n1 = 2;
         if (w->desc.solver == SPH_SOLVER_IISPH) {
             g.in1[2] = reinterpret_cast<const uint32_t*>(w->press[c].p);
@@ -774,7 +782,7 @@ sph_status phase_grid(sph_world* w) {
     w->b_reused = reuse_b;
     if (!reuse_b) CU(cudaMemsetAsync(w->bstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));
     if (B && !reuse_b) {
-        LAUNCH(k_cell_hist, B, 256, w->bpos[bc].p, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p);
+        LAUNCH(k_cell_hist, B, 256, w->bpos[bc].p, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p, (const uint32_t*)nullptr, 0u);
         TRY(scan_exclusive(w, w->bstart.p, ncell + 1));
         LAUNCH(k_cell_scatter, B, 256, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p, w->bperm.p);
         if (w->desc.deterministic) LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->bstart.p, w->bperm.p, (const uint32_t*)nullptr, (const float4*)nullptr);

@@ -306,10 +306,16 @@ __global__ void k_bounds(const float4* __restrict__ pos, uint32_t n, int* __rest
 // K1: counting sort by cell (replaces HGrid::insert hgrid.rs:60-63 / insert_*_to_grid contacts.rs:133-151
 // and the dead z_order.rs sort).
 // ------------------------------------------------------------------------------------------------
+// dead (optional): dead[i] != 0 for i < n_dead marks an input slot that must not enter the sorted arrays (a particle that left
+// this rank's slab, sph_slab.inl); such slots get cid = 0xFFFFFFFF and are skipped by the scatter.
 __global__ void k_cell_hist(const float4* __restrict__ pos, uint32_t n, uint32_t* __restrict__ cid, uint32_t* __restrict__ rank,
-                            uint32_t* __restrict__ count) {
+                            uint32_t* __restrict__ count, const uint32_t* __restrict__ dead, uint32_t n_dead) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (dead && i < n_dead && dead[i]) {
+        cid[i] = 0xFFFFFFFFu;
+        return;
+    }
     float4 p = pos[i];
     uint32_t id = (uint32_t)cell_id(cell_coord(p.x), cell_coord(p.y), cell_coord(p.z));
     cid[i] = id;
@@ -320,7 +326,9 @@ __global__ void k_cell_scatter(uint32_t n, const uint32_t* __restrict__ cid, con
                                const uint32_t* __restrict__ start, uint32_t* __restrict__ perm) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    perm[start[cid[i]] + rank[i]] = i;
+    const uint32_t c = cid[i];
+    if (c == 0xFFFFFFFFu) return;
+    perm[start[c] + rank[i]] = i;
 }
 
 // Deterministic mode: atomics hand out in-cell ranks in arbitrary order; sort each cell's slice of perm so the sorted
@@ -909,68 +917,52 @@ __global__ void k_iota(uint32_t n, uint32_t* __restrict__ a) {
 // ------------------------------------------------------------------------------------------------
 // Slab decomposition helpers (sph_slab.inl): classification by cell column, stream compaction.
 // ------------------------------------------------------------------------------------------------
-// Owned slots [ob, ob + on) are classified by their CURRENT cell column in ONE pass:
-//   keep / leaves-left / leaves-right (migration) and, for the kept ones, left / right boundary column (ghost source).
-// flag_o (indexed by the old original index) marks the particles that stay, so its exclusive scan is their new
-// original index.  counts[0..5] = #keep, #left, #right, #col-left, #col-right, #particles that jumped > 1 column.
-__global__ void k_slab_classify(const float4* __restrict__ pos, const uint32_t* __restrict__ orig, uint32_t ob, uint32_t on, int lo, int hi, int has_left,
-                                int has_right, uint32_t* __restrict__ fk, uint32_t* __restrict__ fl, uint32_t* __restrict__ fr, uint32_t* __restrict__ fcl,
-                                uint32_t* __restrict__ fcr, uint32_t* __restrict__ flag_o, uint32_t* __restrict__ counts) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t v[6] = {0, 0, 0, 0, 0, 0};
-    if (t < on) {
-        uint32_t s = ob + t;
-        int cx = cell_coord(pos[s].x);
-        bool left = has_left && cx < lo, right = has_right && cx >= hi;
-        bool keep = !left && !right;
-        v[0] = keep; v[1] = left; v[2] = right;
-        v[3] = keep && has_left && cx == lo;
-        v[4] = keep && has_right && cx == hi - 1;
-        v[5] = (left && cx < lo - 1) || (right && cx > hi);
-        fk[s] = v[0]; fl[s] = v[1]; fr[s] = v[2]; fcl[s] = v[3]; fcr[s] = v[4];
-        flag_o[orig[s]] = keep;
-    }
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        uint32_t x = v[a];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&counts[a], x);
-    }
-}
-struct SlabOut {  // destination arrays of k_slab_scatter
+// Owned slots [ob, ob + on) are classified by their CURRENT cell column in ONE pass.  Nothing is compacted: particles that
+// left the slab are only flagged `dead` (the counting sort that follows drops them), and the few particles the neighbours
+// need — emigrants and the kept particles of my two boundary columns — are appended to small staging buffers with one
+// atomic per warp.  Their order inside the buffers is arbitrary; the receiver's sort orders every cell by particle id.
+// counts[1..5] = #left, #right, #col-left, #col-right, #particles that jumped > 1 column.
+struct SlabOut {  // staging arrays of k_slab_classify
     float4 *pos, *vel, *vc;
     uint32_t* gid;
 };
-__global__ void k_slab_scatter(uint32_t n_slots, const uint32_t* __restrict__ fk, const uint32_t* __restrict__ fl, const uint32_t* __restrict__ fr,
-                               const uint32_t* __restrict__ fcl, const uint32_t* __restrict__ fcr, const uint32_t* __restrict__ sk,
-                               const uint32_t* __restrict__ sl, const uint32_t* __restrict__ sr, const uint32_t* __restrict__ scl,
-                               const uint32_t* __restrict__ scr, const uint32_t* __restrict__ scan_o, const float4* __restrict__ pos,
-                               const float4* __restrict__ vel, const float4* __restrict__ vc, const uint32_t* __restrict__ orig,
-                               const uint32_t* __restrict__ gid, SlabOut keep, uint32_t* __restrict__ keep_orig, SlabOut out_l, SlabOut out_r, SlabOut col_l,
-                               SlabOut col_r) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_slots) return;
-    if (fk[s]) {
-        float4 p = pos[s], v = vel[s], c = vc[s];
-        uint32_t d = sk[s];
-        keep.pos[d] = p; keep.vel[d] = v; keep.vc[d] = c;
-        keep.gid[d] = gid[s];
-        keep_orig[d] = scan_o[orig[s]];
-        if (fcl[s]) {
-            uint32_t e = scl[s];
-            col_l.pos[e] = p; col_l.vel[e] = v; col_l.vc[e] = c; col_l.gid[e] = gid[s];
-        }
-        if (fcr[s]) {
-            uint32_t e = scr[s];
-            col_r.pos[e] = p; col_r.vel[e] = v; col_r.vc[e] = c; col_r.gid[e] = gid[s];
-        }
-    } else if (fl[s]) {
-        uint32_t d = sl[s];
-        out_l.pos[d] = pos[s]; out_l.vel[d] = vel[s]; out_l.vc[d] = vc[s]; out_l.gid[d] = gid[s];
-    } else if (fr[s]) {
-        uint32_t d = sr[s];
-        out_r.pos[d] = pos[s]; out_r.vel[d] = vel[s]; out_r.vc[d] = vc[s]; out_r.gid[d] = gid[s];
+__device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t* counter) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (!m) return 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? base + (uint32_t)__popc(m & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
+}
+__global__ void k_slab_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ vc, const uint32_t* __restrict__ gid,
+                                uint32_t ob, uint32_t on, int lo, int hi, int has_left, int has_right, uint32_t* __restrict__ dead, SlabOut out_l, SlabOut out_r,
+                                SlabOut col_l, SlabOut col_r, uint32_t cap_out, uint32_t cap_col, uint32_t* __restrict__ counts) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = t < on;
+    const uint32_t s = ob + (in ? t : 0u);
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool left = false, right = false, cl = false, cr = false, jumped = false;
+    if (in) {
+        p = pos[s];
+        const int cx = cell_coord(p.x);
+        left = has_left && cx < lo;
+        right = has_right && cx >= hi;
+        cl = !left && !right && has_left && cx == lo;
+        cr = !left && !right && has_right && cx == hi - 1;
+        jumped = (left && cx < lo - 1) || (right && cx > hi);
+        dead[t] = (left || right) ? 1u : 0u;
     }
+    const uint32_t kl = warp_append(left, &counts[1]), kr = warp_append(right, &counts[2]);
+    const uint32_t kcl = warp_append(cl, &counts[3]), kcr = warp_append(cr, &counts[4]);
+    warp_append(jumped, &counts[5]);
+    if (!(left || right || cl || cr)) return;
+    const float4 v = vel[s], c = vc[s];
+    const uint32_t g = gid[s];
+    if (left && kl < cap_out) { out_l.pos[kl] = p; out_l.vel[kl] = v; out_l.vc[kl] = c; out_l.gid[kl] = g; }
+    if (right && kr < cap_out) { out_r.pos[kr] = p; out_r.vel[kr] = v; out_r.vc[kr] = c; out_r.gid[kr] = g; }
+    if (cl && kcl < cap_col) { col_l.pos[kcl] = p; col_l.vel[kcl] = v; col_l.vc[kcl] = c; col_l.gid[kcl] = g; }
+    if (cr && kcr < cap_col) { col_r.pos[kcr] = p; col_r.vel[kcr] = v; col_r.vc[kcr] = c; col_r.gid[kcr] = g; }
 }
 // counts[8..9] = {#emigrants left, #col-left}, counts[10..11] = {#emigrants right, #col-right}: the two 8-byte messages
 __global__ void k_slab_pack_counts(uint32_t* __restrict__ counts) {

@@ -89,7 +89,7 @@ void slab_release(sph_world* w) {
     if (S.ev_done) cudaEventDestroy(S.ev_done);
     if (S.comm_st) cudaStreamDestroy(S.comm_st);
     S.comm_st = nullptr; S.ev_ready = nullptr; S.ev_done = nullptr;
-    S.d_cnt.release(); S.flag.release(); S.flag_o.release(); S.gid_l.release(); S.gid_r.release(); S.gid_cl.release(); S.gid_cr.release();
+    S.d_cnt.release(); S.flag.release(); S.gid_l.release(); S.gid_r.release(); S.gid_cl.release(); S.gid_cr.release();
     S.d_cnt64.release();
     for (int a = 0; a < 3; ++a) {
         S.out_l[a].release();
@@ -301,130 +301,128 @@ sph_status slab_allreduce(sph_world* w, float* buf, size_t n) {
     return SPH_OK;
 }
 
-// Step prologue in slab mode — one classification pass, one count exchange, ONE host sync, one data exchange:
-//   * particles that left [lo, hi) migrate to the neighbour that now owns them (CFL: at most one cell column per step);
+// Step prologue in slab mode — one classification pass, one count exchange, ONE host sync, one data exchange, NO compaction:
+//   * particles that left [lo, hi) are flagged dead (the counting sort that follows simply does not pick them up) and go to
+//     the neighbour that now owns them (CFL: at most one cell column per step);
 //   * the kept particles of my boundary columns go to the neighbours as their ghosts;
-//   * my own emigrants stay here as ghosts (they now sit in the neighbour's boundary column), appended AFTER the
-//     neighbour's column so that both sides see that column in the same order: [neighbour's kept | my emigrants].
-// On exit the arrays hold [kept | immigrants left | immigrants right | left ghosts | right ghosts]; the counting sort
-// follows and leaves [left ghosts | owned | right ghosts] with the boundary columns at the ends of the owned range.
+//   * my own emigrants stay here as ghosts (they now sit in the neighbour's boundary column).
+// Immigrants and the new ghosts are appended behind the owned range of the LIVE arrays (over last step's right ghosts), so
+// the sort's input is the slot range [own_begin, own_begin + on + immigrants + ghosts); its output is
+// [left ghosts | owned | right ghosts] with the boundary columns at the ends of the owned range.  Only the handful of
+// particles that cross a rank boundary are ever copied by the prologue (round 1 compacted the whole state: 0.6 ms of a 4 ms
+// step at 4M particles per GPU, profiles/r2_multi_gpu.md).
+// Index order in a slab world: fluid.positions[i] of a slab world is the engine's sorted order of the moment (it changes
+// with every step); particles are tracked by their ids (sph_fluid_read_ids), which is what the migration preserves.
 sph_status slab_begin_step(sph_world* w) {
     SlabState& S = w->slab;
     if (w->fluids.size() != 1) return w->fail(SPH_ERR_INVALID, "slab decomposition supports one fluid per world");
     if (w->desc.solver != SPH_SOLVER_DFSPH || w->tile) return w->fail(SPH_ERR_INVALID, "slab decomposition supports DFSPH with gather_backend 0");
     for (auto& fr : w->fluids[0].forces)
         if (fr.d.kind == SPH_FORCE_BECKER2009_ELASTICITY) return w->fail(SPH_ERR_INVALID, "Becker2009 elasticity is not slab-decomposed");
-    const uint32_t n_slots = (uint32_t)w->Ntot;  // layout of the previous step: [ghosts | owned | ghosts] (or owned only)
     const uint32_t ob = w->own_begin, on = (uint32_t)w->N;
-    int c = w->cur;
+    const int c = w->cur;
     const int L = slab_left(w), R = slab_right(w);
-    // ---- classify + count ---------------------------------------------------------------------------------------------
-    CU(S.flag.ensure(10 * (size_t)n_slots + 16));
-    CU(S.flag_o.ensure((size_t)on + 8));
+    CU(S.flag.ensure((size_t)on + 16));
     CU(S.d_cnt.ensure(32));
-    uint32_t* f[5];   // keep, left, right, col-left, col-right flags
-    uint32_t* sc[5];  // their exclusive scans
-    for (int a = 0; a < 5; ++a) {
-        f[a] = S.flag.p + (size_t)a * n_slots;
-        sc[a] = S.flag.p + (size_t)(5 + a) * n_slots;
-    }
-    CU(cudaMemsetAsync(S.flag.p, 0, 5 * (size_t)n_slots * sizeof(uint32_t), w->st));
-    CU(cudaMemsetAsync(S.d_cnt.p, 0, 32 * sizeof(uint32_t), w->st));
-    LAUNCH(k_slab_classify, on, 256, w->pos[c].p, w->orig[c].p, ob, on, S.lo, S.hi, S.has_left, S.has_right, f[0], f[1], f[2], f[3], f[4], S.flag_o.p,
-           S.d_cnt.p);
-    // counts go to the neighbours straight from the device: [#emigrants to you, #particles of my column facing you]
-    LAUNCH(k_slab_pack_counts, 1, 32, S.d_cnt.p);  // d_cnt[8..9] = {nl, ncl}, d_cnt[10..11] = {nr, ncr}
-    NC(g_nccl.GroupStart());
-    if (L >= 0) {
-        NC(g_nccl.Send(S.d_cnt.p + 8, 8, NCCL_CHAR, L, S.comm, w->st));
-        NC(g_nccl.Recv(S.d_cnt.p + 12, 8, NCCL_CHAR, L, S.comm, w->st));
-    }
-    if (R >= 0) {
-        NC(g_nccl.Send(S.d_cnt.p + 10, 8, NCCL_CHAR, R, S.comm, w->st));
-        NC(g_nccl.Recv(S.d_cnt.p + 14, 8, NCCL_CHAR, R, S.comm, w->st));
-    }
-    NC(g_nccl.GroupEnd());
     uint32_t hc[16];
-    CU(cudaMemcpyAsync(hc, S.d_cnt.p, sizeof hc, cudaMemcpyDeviceToHost, w->st));
-    CU(cudaMemcpyAsync(sc[0], f[0], 5 * (size_t)n_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->st));
-    {
-        ScanSet<5> set;
-        for (int a = 0; a < 5; ++a) set.a[a] = sc[a];
-        TRY(scan_exclusive_k<5>(w, set, n_slots));  // one 3-launch scan for the five flag arrays
+    for (int attempt = 0;; ++attempt) {
+        for (int a = 0; a < 3; ++a) {
+            CU(S.out_l[a].ensure(S.cap_out));
+            CU(S.out_r[a].ensure(S.cap_out));
+            CU(S.col_l[a].ensure(S.cap_col));
+            CU(S.col_r[a].ensure(S.cap_col));
+        }
+        CU(S.gid_l.ensure(S.cap_out));
+        CU(S.gid_r.ensure(S.cap_out));
+        CU(S.gid_cl.ensure(S.cap_col));
+        CU(S.gid_cr.ensure(S.cap_col));
+        SlabOut ol{S.out_l[0].p, S.out_l[1].p, S.out_l[2].p, S.gid_l.p}, orr{S.out_r[0].p, S.out_r[1].p, S.out_r[2].p, S.gid_r.p};
+        SlabOut cl{S.col_l[0].p, S.col_l[1].p, S.col_l[2].p, S.gid_cl.p}, cr{S.col_r[0].p, S.col_r[1].p, S.col_r[2].p, S.gid_cr.p};
+        CU(cudaMemsetAsync(S.d_cnt.p, 0, 12 * sizeof(uint32_t), w->st));
+        LAUNCH(k_slab_classify, on, 256, w->pos[c].p, w->vel[c].p, w->vc[c].p, w->gid[c].p, ob, on, S.lo, S.hi, S.has_left, S.has_right, S.flag.p, ol, orr, cl,
+               cr, S.cap_out, S.cap_col, S.d_cnt.p);
+        if (attempt == 0) {
+            // counts go to the neighbours straight from the device: [#emigrants to you, #particles of my column facing you]
+            LAUNCH(k_slab_pack_counts, 1, 32, S.d_cnt.p);  // d_cnt[8..9] = {nl, ncl}, d_cnt[10..11] = {nr, ncr}
+            NC(g_nccl.GroupStart());
+            if (L >= 0) {
+                NC(g_nccl.Send(S.d_cnt.p + 8, 8, NCCL_CHAR, L, S.comm, w->st));
+                NC(g_nccl.Recv(S.d_cnt.p + 12, 8, NCCL_CHAR, L, S.comm, w->st));
+            }
+            if (R >= 0) {
+                NC(g_nccl.Send(S.d_cnt.p + 10, 8, NCCL_CHAR, R, S.comm, w->st));
+                NC(g_nccl.Recv(S.d_cnt.p + 14, 8, NCCL_CHAR, R, S.comm, w->st));
+            }
+            NC(g_nccl.GroupEnd());
+            CU(cudaMemcpyAsync(hc, S.d_cnt.p, sizeof hc, cudaMemcpyDeviceToHost, w->st));
+            CU(cudaStreamSynchronize(w->st));  // the only host sync of the prologue
+        }
+        if (hc[1] <= S.cap_out && hc[2] <= S.cap_out && hc[3] <= S.cap_col && hc[4] <= S.cap_col) break;
+        if (attempt) return w->fail(SPH_ERR_INVALID, "slab staging buffers did not grow");
+        // the staging buffers were too small (first step of a big scene): grow them and classify once more — the counts, and
+        // therefore what the neighbours were told, do not change
+        S.cap_out = std::max(S.cap_out, std::max(hc[1], hc[2]) + std::max(hc[1], hc[2]) / 2 + 1024);
+        S.cap_col = std::max(S.cap_col, std::max(hc[3], hc[4]) + std::max(hc[3], hc[4]) / 2 + 1024);
     }
-    TRY(scan_exclusive(w, S.flag_o.p, on));  // new original index of the kept particles (stable in the old order)
-    CU(cudaStreamSynchronize(w->st));        // the only host sync of the prologue
-    const uint32_t nk = hc[0], nl = hc[1], nr = hc[2], ncl = hc[3], ncr = hc[4];
+    const uint32_t nl = hc[1], nr = hc[2], ncl = hc[3], ncr = hc[4];
     if (hc[5]) return w->fail(SPH_ERR_INVALID, "%u particles crossed more than one cell column in a step (CFL violated)", hc[5]);
     const uint32_t im_l = L >= 0 ? hc[12] : 0, gcol_l = L >= 0 ? hc[13] : 0;  // from the left rank: its emigrants to me, its column
     const uint32_t im_r = R >= 0 ? hc[14] : 0, gcol_r = R >= 0 ? hc[15] : 0;
-    const uint32_t n_new = nk + im_l + im_r;
+    const uint32_t n_new = on - nl - nr + im_l + im_r;
     const uint32_t ghl = gcol_l + nl, ghr = gcol_r + nr;
-    // ---- buffers ------------------------------------------------------------------------------------------------------------
-    for (int a = 0; a < 3; ++a) {
-        CU(S.out_l[a].ensure(std::max<uint32_t>(nl, 1)));
-        CU(S.out_r[a].ensure(std::max<uint32_t>(nr, 1)));
-        CU(S.col_l[a].ensure(std::max<uint32_t>(ncl, 1)));
-        CU(S.col_r[a].ensure(std::max<uint32_t>(ncr, 1)));
-    }
-    CU(S.gid_l.ensure(std::max<uint32_t>(nl, 1)));
-    CU(S.gid_r.ensure(std::max<uint32_t>(nr, 1)));
-    CU(S.gid_cl.ensure(std::max<uint32_t>(ncl, 1)));
-    CU(S.gid_cr.ensure(std::max<uint32_t>(ncr, 1)));
-    w->N = n_new;
-    w->Ntot = (size_t)n_new + ghl + ghr;
-    w->fluids[0].n = n_new;
-    w->fluids[0].pending_delete.assign(n_new, 0);
-    recompute_offsets(w);
-    w->cur = c ^ 1;          // the compacted state is built in the other buffer ...
-    w->protect_buf = c;      // ... while the old one is still being read by the scatter
+    const uint32_t n_in = on + im_l + im_r + ghl + ghr;  // slots the sort reads: owned (incl. the dead ones) + appended
+    // ---- grow the live arrays behind the owned range if needed (contents kept) ----------------------------------------------
+    w->Ntot = (size_t)ob + n_in;  // sizing only; the real value follows below
     TRY(ensure_fluid_buffers(w));
-    const int d = c ^ 1;
-    SlabOut keep{w->pos[d].p, w->vel[d].p, w->vc[d].p, w->gid[d].p};
-    SlabOut ol{S.out_l[0].p, S.out_l[1].p, S.out_l[2].p, S.gid_l.p}, orr{S.out_r[0].p, S.out_r[1].p, S.out_r[2].p, S.gid_r.p};
-    SlabOut cl{S.col_l[0].p, S.col_l[1].p, S.col_l[2].p, S.gid_cl.p}, cr{S.col_r[0].p, S.col_r[1].p, S.col_r[2].p, S.gid_cr.p};
-    LAUNCH(k_slab_scatter, n_slots, 256, n_slots, f[0], f[1], f[2], f[3], f[4], sc[0], sc[1], sc[2], sc[3], sc[4], S.flag_o.p, w->pos[c].p, w->vel[c].p,
-           w->vc[c].p, w->orig[c].p, w->gid[c].p, keep, w->orig[d].p, ol, orr, cl, cr);
+    float4* dst4[3] = {w->pos[c].p, w->vel[c].p, w->vc[c].p};
+    const uint32_t a0 = ob + on;                    // first appended slot: immigrants from the left, then from the right,
+    const uint32_t g0 = a0 + im_l + im_r;           // then the left ghosts, then the right ghosts
+    const uint32_t g1 = g0 + ghl;
     // ---- one data exchange: emigrants + boundary columns out, immigrants + ghost columns in --------------------------------
-    float4* dst4[3] = {w->pos[d].p, w->vel[d].p, w->vc[d].p};
-    const uint32_t g0 = n_new, g1 = n_new + ghl;  // first left / right ghost slot
     NC(g_nccl.GroupStart());
     if (L >= 0) {
         for (int a = 0; a < 3; ++a) {
             if (nl) NC(g_nccl.Send(S.out_l[a].p, (size_t)nl * 16, NCCL_CHAR, L, S.comm, w->st));
             if (ncl) NC(g_nccl.Send(S.col_l[a].p, (size_t)ncl * 16, NCCL_CHAR, L, S.comm, w->st));
-            if (im_l) NC(g_nccl.Recv(dst4[a] + nk, (size_t)im_l * 16, NCCL_CHAR, L, S.comm, w->st));
+            if (im_l) NC(g_nccl.Recv(dst4[a] + a0, (size_t)im_l * 16, NCCL_CHAR, L, S.comm, w->st));
             if (gcol_l) NC(g_nccl.Recv(dst4[a] + g0, (size_t)gcol_l * 16, NCCL_CHAR, L, S.comm, w->st));
         }
         if (nl) NC(g_nccl.Send(S.gid_l.p, (size_t)nl * 4, NCCL_CHAR, L, S.comm, w->st));
         if (ncl) NC(g_nccl.Send(S.gid_cl.p, (size_t)ncl * 4, NCCL_CHAR, L, S.comm, w->st));
-        if (im_l) NC(g_nccl.Recv(w->gid[d].p + nk, (size_t)im_l * 4, NCCL_CHAR, L, S.comm, w->st));
-        if (gcol_l) NC(g_nccl.Recv(w->gid[d].p + g0, (size_t)gcol_l * 4, NCCL_CHAR, L, S.comm, w->st));
+        if (im_l) NC(g_nccl.Recv(w->gid[c].p + a0, (size_t)im_l * 4, NCCL_CHAR, L, S.comm, w->st));
+        if (gcol_l) NC(g_nccl.Recv(w->gid[c].p + g0, (size_t)gcol_l * 4, NCCL_CHAR, L, S.comm, w->st));
     }
     if (R >= 0) {
         for (int a = 0; a < 3; ++a) {
             if (nr) NC(g_nccl.Send(S.out_r[a].p, (size_t)nr * 16, NCCL_CHAR, R, S.comm, w->st));
             if (ncr) NC(g_nccl.Send(S.col_r[a].p, (size_t)ncr * 16, NCCL_CHAR, R, S.comm, w->st));
-            if (im_r) NC(g_nccl.Recv(dst4[a] + nk + im_l, (size_t)im_r * 16, NCCL_CHAR, R, S.comm, w->st));
+            if (im_r) NC(g_nccl.Recv(dst4[a] + a0 + im_l, (size_t)im_r * 16, NCCL_CHAR, R, S.comm, w->st));
             if (gcol_r) NC(g_nccl.Recv(dst4[a] + g1, (size_t)gcol_r * 16, NCCL_CHAR, R, S.comm, w->st));
         }
         if (nr) NC(g_nccl.Send(S.gid_r.p, (size_t)nr * 4, NCCL_CHAR, R, S.comm, w->st));
         if (ncr) NC(g_nccl.Send(S.gid_cr.p, (size_t)ncr * 4, NCCL_CHAR, R, S.comm, w->st));
-        if (im_r) NC(g_nccl.Recv(w->gid[d].p + nk + im_l, (size_t)im_r * 4, NCCL_CHAR, R, S.comm, w->st));
-        if (gcol_r) NC(g_nccl.Recv(w->gid[d].p + g1, (size_t)gcol_r * 4, NCCL_CHAR, R, S.comm, w->st));
+        if (im_r) NC(g_nccl.Recv(w->gid[c].p + a0 + im_l, (size_t)im_r * 4, NCCL_CHAR, R, S.comm, w->st));
+        if (gcol_r) NC(g_nccl.Recv(w->gid[c].p + g1, (size_t)gcol_r * 4, NCCL_CHAR, R, S.comm, w->st));
     }
     NC(g_nccl.GroupEnd());
-    // my own emigrants are my ghosts now (after the neighbour's column, see the header comment)
+    // my own emigrants are my ghosts now (they sit in the neighbour's boundary column)
     for (int a = 0; a < 3; ++a) {
         if (nl) CU(cudaMemcpyAsync(dst4[a] + g0 + gcol_l, S.out_l[a].p, (size_t)nl * 16, cudaMemcpyDeviceToDevice, w->st));
         if (nr) CU(cudaMemcpyAsync(dst4[a] + g1 + gcol_r, S.out_r[a].p, (size_t)nr * 16, cudaMemcpyDeviceToDevice, w->st));
     }
-    if (im_l + im_r) LAUNCH(k_iota_from, im_l + im_r, 256, im_l + im_r, nk, w->orig[d].p + nk);
-    if (nl) CU(cudaMemcpyAsync(w->gid[d].p + g0 + gcol_l, S.gid_l.p, (size_t)nl * 4, cudaMemcpyDeviceToDevice, w->st));
-    if (nr) CU(cudaMemcpyAsync(w->gid[d].p + g1 + gcol_r, S.gid_r.p, (size_t)nr * 4, cudaMemcpyDeviceToDevice, w->st));
-    if (ghl + ghr) CU(cudaMemsetAsync(w->orig[d].p + n_new, 0xFF, (size_t)(ghl + ghr) * 4, w->st));  // ghosts carry no original index (ids they do: the sort key)
+    if (nl) CU(cudaMemcpyAsync(w->gid[c].p + g0 + gcol_l, S.gid_l.p, (size_t)nl * 4, cudaMemcpyDeviceToDevice, w->st));
+    if (nr) CU(cudaMemcpyAsync(w->gid[c].p + g1 + gcol_r, S.gid_r.p, (size_t)nr * 4, cudaMemcpyDeviceToDevice, w->st));
     S.migrated_out = nl + nr;
     S.migrated_in = im_l + im_r;
+    // what the sort reads, and which of its first `on` input slots it must drop
+    S.sort_off = ob;
+    S.sort_n = n_in;
+    S.sort_dead_n = on;
+    w->N = n_new;
+    w->Ntot = (size_t)n_new + ghl + ghr;
+    w->fluids[0].n = n_new;
+    w->fluids[0].pending_delete.assign(n_new, 0);
+    recompute_offsets(w);
     // slot ranges after the sort follow from the counts alone (CFL: immigrants land in my boundary columns)
     S.gl_count = ghl;
     S.sl_begin = ghl;
@@ -442,9 +440,6 @@ sph_status slab_begin_step(sph_world* w) {
         S.global_n = cnt;
         S.global_valid = true;
     }
-    w->own_begin = 0;  // until the sort
-    w->protect_buf = -1;
-    TRY(ensure_fluid_buffers(w));  // now the old buffer may grow too (it is the sort's destination)
     return SPH_OK;
 }
 
@@ -453,6 +448,12 @@ sph_status slab_begin_step(sph_world* w) {
 sph_status slab_after_sort(sph_world* w) {
     SlabState& S = w->slab;
     w->own_begin = S.gl_count;
+    {   // index order of a slab world = sorted order of the moment: orig is the identity over the owned range
+        const int c = w->cur;
+        if (w->N) LAUNCH(k_iota_from, w->N, 256, (uint32_t)w->N, 0u, w->orig[c].p + w->own_begin);
+        if (S.gl_count) CU(cudaMemsetAsync(w->orig[c].p, 0xFF, (size_t)S.gl_count * 4, w->st));
+        if (S.gr_count) CU(cudaMemsetAsync(w->orig[c].p + S.gr_begin, 0xFF, (size_t)S.gr_count * 4, w->st));
+    }
     static const bool check = getenv("SALVA_B200_SLAB_CHECK") && atoi(getenv("SALVA_B200_SLAB_CHECK")) != 0;
     if (!check) return SPH_OK;
     const Consts& c = w->hc;
