@@ -316,7 +316,9 @@ sph_status sph_fluid_read_ids(sph_world* w, uint32_t fluid, uint32_t* ids, size_
  * the world of rank r owns the particles whose cell column floor(x / h) lies in [cell_lo, cell_hi) (INT32_MIN / INT32_MAX
  * = open end), the host adds only those to it (plus ALL boundary particles), and every step the library exchanges
  * one-cell ghost columns with ranks r-1 / r+1 (ncclSend/ncclRecv over NVLink) and migrates particles that crossed a
- * plane.  Either hand over an initialised ncclComm_t (attach) or let the library create one from a unique id that
+ * plane.  In a slab world the index order of a fluid (sph_fluid_read / _write / _delete) is the engine's sorted order of the moment
+ * and changes with every step: track particles by id (sph_fluid_set_ids / sph_fluid_read_ids), which migration preserves.
+ * Either hand over an initialised ncclComm_t (attach) or let the library create one from a unique id that
  * rank 0 obtained with sph_nccl_unique_id() and the host's own plumbing (torch.distributed) broadcast. */
 sph_status sph_nccl_unique_id(char out_id[128]);
 sph_status sph_world_create_nccl(sph_world* w, const char unique_id[128], int rank, int nranks);
