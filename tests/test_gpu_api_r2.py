@@ -325,3 +325,29 @@ def test_non_default_solver_kernels_match_oracle(kd, kg, solver):
     h = float(gpu.h)
     assert np.abs(pg - pc).max() <= 1e-3 * h
     assert np.abs(vg - vc).max() <= 1e-3 * h / sc["dt"]
+
+
+def test_replace_particles_in_a_different_order_keeps_the_trajectory_bit_exact():
+    """sph_fluid_replace_particles (what the slab re-balancing uses): hand the engine the same particles — positions,
+    velocities, velocity_changes, ids — in a shuffled index order; the canonical in-cell order (ascending id) makes the
+    continued run bit-identical to the undisturbed one, particle by particle."""
+    sc = _scene(41, forces=(scenes.xsph_viscosity(0.5, 0.2),))
+    a, fa, _ = _world(sc)
+    b, fb, _ = _world(sc)
+    for _ in range(4):
+        a.step(sc["dt"])
+        b.step(sc["dt"])
+    p, v = b.read_fluid(fb[0])
+    vc = b.debug(fb[0], "velocity_change")
+    ids = b.read_ids(fb[0])
+    perm = np.random.default_rng(0).permutation(len(p))
+    b.replace_particles(fb[0], p[perm], v[perm], vc[perm], ids[perm])
+    for _ in range(4):
+        a.step(sc["dt"])
+        b.step(sc["dt"])
+    pa, va = a.read_fluid(fa[0])
+    pb, vb = b.read_fluid(fb[0])
+    ia, ib = a.read_ids(fa[0]), b.read_ids(fb[0])
+    assert np.array_equal(ib, ids[perm])
+    oa, ob_ = np.argsort(ia), np.argsort(ib)
+    assert np.array_equal(pa[oa], pb[ob_]) and np.array_equal(va[oa], vb[ob_])
