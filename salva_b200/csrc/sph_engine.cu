@@ -243,7 +243,6 @@ struct sph_world {
     // ParticlesContacts materialised for host plugins (original order CSR)
     DBuf<uint32_t> ct_cnt[2], ct_j[2], ct_model[2];
     DBuf<float> ct_w[2], ct_g[2];
-    DBuf<uint32_t> sm_next;       // per-SM chunk counters of the persistent-kernel experiment
     DBuf<uint32_t> d_ticket;      // last-block ticket of the in-kernel error reduction (kept at 0 between launches)
     bool errsum_ready = false;    // the last evaluation launch already reduced its partials into errsum
     DBuf<LoopCtl> d_ctl;          // device-side Jacobi loop control (sph_kernels.cuh LoopCtl)
@@ -1304,18 +1303,6 @@ sph_status launch_vel_update(sph_world* w, bool pressure, const int* gate = null
         if (w->unimass) {
             const bool ptex = w->uni_upd_mode == 1;
             Rec8* rec = (!gate && ((pressure && rec8_predict(w)) || rec8_full(w))) ? w->rec8.p : nullptr;
-            if (w->uni_upd_mode == 4 && !rec && !gate && !bf && !w->slab.active) {  // experiment: persistent CTAs, contiguous chunk ranges per SM
-                int n_sm = 148;
-                cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, w->desc.device);
-                const uint32_t n_chunks = cdiv(rg.count, PASS_T), cps = cdiv(n_chunks, (size_t)n_sm);
-                CU(w->sm_next.ensure(256));
-                CU(cudaMemsetAsync(w->sm_next.p, 0, 256 * sizeof(uint32_t), w->st));
-                const uint32_t grid = std::min<uint32_t>(n_chunks, (uint32_t)n_sm * SPH_PASS_MINB);
-                if (pressure) k_vel_update_persist<false, true><<<grid, PASS_T, 0, w->st>>>(w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p, w->bforce.p, w->inv_dt, rg, w->sm_next.p, (uint32_t)n_sm, cps, n_chunks);
-                else k_vel_update_persist<false, false><<<grid, PASS_T, 0, w->st>>>(w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p, w->bforce.p, w->inv_dt, rg, w->sm_next.p, (uint32_t)n_sm, cps, n_chunks);
-                w->launches++;
-                return SPH_OK;
-            }
             if (w->uni_upd_mode == 3 && !rec && !gate) {
                 if (bf) {
                     if (pressure) LAUNCH_R((k_vel_update_alt<true, true>), rg, w->pk4.p, w->tex_pk, w->vel[c].p, w->bpos[bc].p, L, w->vc[c].p, w->vs.p, w->pvx4.p, w->vyz2.p, w->bforce.p, w->inv_dt);
@@ -1979,7 +1966,6 @@ void sph_world_destroy(sph_world* w) {
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     w->d_ctl.release();
     w->d_ticket.release();
-    w->sm_next.release();
     w->d_nb.release();
     w->xs.release(); w->he_colors.release(); w->he_gradc.release(); w->q_out.release(); w->q_count.release();
     for (auto& e : w->ev)

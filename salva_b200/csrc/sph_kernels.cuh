@@ -538,8 +538,6 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
         float4 pi = pos[i];
         uint32_t fi = MULTI ? fid_of(vel[i]) : 0u;
         int cx = cell_coord(pi.x), cy = cell_coord(pi.y), cz = cell_coord(pi.z);
-        uint4 grp = make_uint4(i, i, i, i);
-        uint4* __restrict__ nbr_f4 = reinterpret_cast<uint4*>(nbr_f);
         for (int ax = -1; ax <= 1; ++ax)
             for (int ay = -1; ay <= 1; ++ay) {
                 int base = cell_id(cx + ax, cy + ay, cz);
@@ -551,11 +549,9 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
                         return fi == fj || groups_test(C.fluids[fi].memberships, C.fluids[fi].filter, C.fluids[fj].memberships, C.fluids[fj].filter);
                     },
                     [&](uint32_t j) {
-                        // collect four hits in registers and store the group as ONE coalesced 16-byte word per thread (the
-                        // lists are laid out in groups of four for exactly this width); single 4-byte stores would touch a
-                        // quarter of every sector they hit
-                        grp.x = grp.y; grp.y = grp.z; grp.z = grp.w; grp.w = j;
-                        if ((nf & 3u) == 3u && nf < C.cap_f) nbr_f4[(size_t)(nf >> 2) * C.stride + i] = grp;
+                        // (one 4-byte store per hit: collecting four hits in registers and storing 16-byte groups was measured
+                        //  SLOWER, 1.66 -> 1.80 ms at C3 — the shift-in costs more issue slots than the stores save)
+                        if (nf < C.cap_f) nbr_f[((size_t)(nf >> 2) * C.stride + i) * 4 + (nf & 3)] = j;
                         ++nf;
                     });
                 if (C.n_bound)
@@ -570,10 +566,7 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
                             ++nb;
                         });
             }
-        if (nf & 3u) {  // pad the last group with i itself (a self contact has zero gradient) and flush it
-            for (uint32_t t = nf & 3u; t < 4u; ++t) { grp.x = grp.y; grp.y = grp.z; grp.z = grp.w; grp.w = i; }
-            if (nf < C.cap_f) nbr_f4[(size_t)(nf >> 2) * C.stride + i] = grp;
-        }
+        for (uint32_t t = nf; t < ((nf + 3u) & ~3u) && t < C.cap_f; ++t) nbr_f[((size_t)(t >> 2) * C.stride + i) * 4 + (t & 3)] = i;  // pad the last group
         cnt_f[i] = nf;
         cnt_b[i] = nb;
     }

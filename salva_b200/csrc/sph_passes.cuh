@@ -917,92 +917,6 @@ k_vel_update_u(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const fl
     }
 }
 
-// Persistent variant of the pressure / divergence velocity update (SALVA_B200_UNI_UPD=4, experiment): one CTA slot per
-// resident block, and every SM works through a CONTIGUOUS range of 128-particle chunks (x-major order: z-strips that are
-// y-neighbours), so the chunks resident on an SM at any time share most of their 27-cell stencils and the L1 hit rate of
-// the gathers rises.  Chunks are handed out per SM by an atomic counter (sm_next[smid]); results do not depend on the order.
-template <bool BFORCE, bool PRESSURE>
-__global__ void __launch_bounds__(PASS_T, SPH_PASS_MINB)
-k_vel_update_persist(const float4* __restrict__ pk4, cudaTextureObject_t tpk, const float4* __restrict__ vel, const float4* __restrict__ bpos, Lists L,
-                     float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ pvx, float2* __restrict__ vyz, float* __restrict__ bforce,
-                     float inv_dt, Range rg, uint32_t* __restrict__ sm_next, uint32_t n_sm, uint32_t chunks_per_sm, uint32_t n_chunks) {
-    uint32_t smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    if (smid >= n_sm) smid %= n_sm;
-    __shared__ uint32_t s_chunk;
-    for (;;) {
-        if (threadIdx.x == 0) {
-            // own range first, then help the other SMs (work stealing keeps the tail short)
-            uint32_t c = 0xffffffffu;
-            for (uint32_t k = 0; k < n_sm && c == 0xffffffffu; ++k) {
-                const uint32_t s = (smid + k) % n_sm;
-                const uint32_t lo = s * chunks_per_sm, hi = min(lo + chunks_per_sm, n_chunks);
-                if (lo >= hi) continue;
-                if (k && sm_next[s] >= hi - lo) continue;  // cheap look before the atomic
-                const uint32_t t = atomicAdd(&sm_next[s], 1u);
-                if (t < hi - lo) c = lo + t;
-            }
-            s_chunk = c;
-        }
-        __syncthreads();
-        const uint32_t chunk = s_chunk;
-        __syncthreads();
-        if (chunk == 0xffffffffu) return;
-        uint32_t i = chunk * PASS_T + threadIdx.x;
-        if (i >= rg.count) continue;
-        i += rg.begin;
-        const float4 a = pk4[i];
-        const float4 pi = make_float4(a.x, a.y, a.z, 0.f);
-        const float ki = a.w;
-        const float4 v = vel[i];
-        const float rho0 = C.fluids[0].density0, mass = C.fluids[0].mass;
-        const float scale = (PRESSURE ? inv_dt : 1.0f) * mass;
-        float ax = 0.f, ay = 0.f, az = 0.f;
-        {
-            const uint32_t n = min(L.cnt_f[i], C.cap_f);
-            const uint32_t nq = (n + 3u) >> 2;
-            const uint4* col = L.nbr_f + i;
-            uint4 J = nq ? ld_list(col) : make_uint4(i, i, i, i);
-            for (uint32_t q = 0; q < nq; ++q) {
-                uint4 Jn = J;
-                if (q + 1 < nq) Jn = ld_list(col + (size_t)(q + 1) * C.stride);
-                float4 pj[4];
-                pj[0] = tex1Dfetch<float4>(tpk, (int)J.x);
-                pj[1] = __ldg(&pk4[J.y]);
-                pj[2] = tex1Dfetch<float4>(tpk, (int)J.z);
-                pj[3] = __ldg(&pk4[J.w]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    Pair p = make_pair<false, true>(pi, pj[u]);
-                    float c = (ki + pj[u].w) * scale * p.g;
-                    ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
-                }
-                J = Jn;
-            }
-        }
-        if (!PRESSURE || ki > 0.f) {
-            const float bscale = PRESSURE ? inv_dt : 1.0f;
-            for_boundary_contacts<false, true>(i, pi, L, bpos, [&](uint32_t j, const Pair& p, const float4& pj) {
-                float c = ki * pj.w * rho0 * bscale * p.g;
-                ax = fmaf(c, p.dx, ax); ay = fmaf(c, p.dy, ay); az = fmaf(c, p.dz, az);
-                if (BFORCE) {
-                    float s = c * inv_dt * mass;
-                    atomicAdd(&bforce[3 * (size_t)j + 0], s * p.dx);
-                    atomicAdd(&bforce[3 * (size_t)j + 1], s * p.dy);
-                    atomicAdd(&bforce[3 * (size_t)j + 2], s * p.dz);
-                }
-            });
-        }
-        float4 c4 = vc[i];
-        c4.x -= ax; c4.y -= ay; c4.z -= az;
-        vc[i] = c4;
-        const float sx = v.x + c4.x, sy = v.y + c4.y, sz = v.z + c4.z;
-        vs[i] = make_float4(sx, sy, sz, 0.f);
-        pvx[i] = make_float4(a.x, a.y, a.z, sx);
-        vyz[i] = make_float2(sy, sz);
-    }
-}
-
 // k_vel_update_u with the gathers of every group of four contacts split between the two L1TEX front ends: contacts 0 and 2
 // through the texture pipe, 1 and 3 through the LSU pipe (SALVA_B200_UNI_UPD=3).  Same arithmetic and summation order.
 template <bool BFORCE, bool PRESSURE>
