@@ -54,6 +54,8 @@ def test_single_pass_quantities_match_oracle():
     assert np.array_equal(gpu.debug(f, "num_boundary_contacts"), cpu.debug(o, "num_boundary_contacts"))  # exact
     assert _rel(gpu.debug(f, "density"), cpu.debug(o, "density")) <= 1e-5
     assert _rel(gpu.debug(f, "alpha"), cpu.debug(o, "alpha")) <= 1e-5
+    # 1e-4, not the 1e-5 of rho / alpha / rho*: sum_j m (v_i - v_j) . grad W cancels to ~1 % of its terms, so the one-ulp
+    # difference per term (g * x_ij here, dir * W' in the reference) is amplified ~100x relative to max|div|
     assert _rel(gpu.debug(f, "divergence"), cpu.debug(o, "divergence")) <= 1e-4
     assert _rel(gpu.debug(f, "predicted_density"), cpu.debug(o, "predicted_density")) <= 1e-5
     volg, _ = gpu.read_boundary(bg[0])
