@@ -230,6 +230,7 @@ struct sph_world {
     DBuf<Rec8> rec8, nrec8;  // 256-bit gather records: (pos, v*, rho) of the evaluations, (pos, normal, rho) of the Akinci force pass
     int use_rec8 = 0;        // 0: off, 1: pressure-loop evaluations, 2: every evaluation of the step (+ fused XSPH / Akinci normals)
     bool nrec_valid = false;
+    bool nbr_tex = false;  // experiment: odd neighbour-search candidates through the texture pipe (SALVA_B200_NBR_TEX)
     bool fuse_akinci = true, nr4_valid = false;  // Akinci normals ride with a divergence evaluation (k_vel_divergence_xsph_u<.., 2>)
     cudaTextureObject_t tex_pvx = 0, tex_vyz = 0, tex_pk = 0;
     const void* tex_pvx_ptr = nullptr;
@@ -862,6 +863,25 @@ cudaError_t tile_prepare(K kern) {
         }                                                                                                 \
     } while (0)
 
+template <class T>
+sph_status ensure_tex(sph_world* w, cudaTextureObject_t* tex, const void** cur, const T* ptr, size_t n) {
+    if (*cur == ptr && *tex) return SPH_OK;
+    if (*tex) cudaDestroyTextureObject(*tex);
+    *tex = 0;
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = const_cast<T*>(ptr);
+    rd.res.linear.desc = cudaCreateChannelDesc<T>();
+    rd.res.linear.sizeInBytes = n * sizeof(T);
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.readMode = cudaReadModeElementType;
+    CU(cudaCreateTextureObject(tex, &rd, &td, nullptr));
+    *cur = ptr;
+    return SPH_OK;
+}
+
 // `speculative` (optional) enqueues the work that follows the neighbour search and only writes scratch (the density
 // pass): it is launched BEFORE the host learns whether the lists overflowed, so the GPU is busy during that round trip;
 // on overflow the lists are rebuilt with a larger capacity and the speculative work is simply enqueued again.
@@ -890,11 +910,16 @@ sph_status phase_neighbors(sph_world* w, sph_status (*speculative)(sph_world*) =
             uint32_t cap = tile_cap(w, sb);
             TDISPATCH1(k_tile_neighbors, multi, sb, cap, w->pos[c].p, w->vel[c].p, w->cstart.p, cap, w->nbr16.p, w->cnt_f.p, maxcnt);
         } else if (multi) {
-            LAUNCH((k_neighbors<true>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
-                   w->cnt_f.p, w->cnt_b.p, maxcnt);
+            LAUNCH((k_neighbors<true, false>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
+                   w->cnt_f.p, w->cnt_b.p, maxcnt, (cudaTextureObject_t)0);
+        } else if (w->nbr_tex && w->unimass) {
+            // candidates from pvx4 (same x, y, z as pos4, fixed address => one texture object for the world's lifetime), odd ones via TEX
+            TRY(ensure_tex(w, &w->tex_pvx, &w->tex_pvx_ptr, w->pvx4.p, w->pvx4.cap));
+            LAUNCH((k_neighbors<false, true>), N, 128, w->pvx4.p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
+                   w->cnt_f.p, w->cnt_b.p, maxcnt, w->tex_pvx);
         } else {
-            LAUNCH((k_neighbors<false>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
-                   w->cnt_f.p, w->cnt_b.p, maxcnt);
+            LAUNCH((k_neighbors<false, false>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
+                   w->cnt_f.p, w->cnt_b.p, maxcnt, (cudaTextureObject_t)0);
         }
         int* hs = reinterpret_cast<int*>(w->h_pinned + 32);  // pinned: the copy is truly asynchronous
         CU(cudaMemcpyAsync(hs, w->d_scal.p + 7, 4 * sizeof(int), cudaMemcpyDeviceToHost, w->st));
@@ -991,24 +1016,6 @@ bool any_bforce(const sph_world* w) {
     } while (0)
 
 // ---- gather passes: one wrapper per reference function, two backends ------------------------------------
-template <class T>
-sph_status ensure_tex(sph_world* w, cudaTextureObject_t* tex, const void** cur, const T* ptr, size_t n) {
-    if (*cur == ptr && *tex) return SPH_OK;
-    if (*tex) cudaDestroyTextureObject(*tex);
-    *tex = 0;
-    cudaResourceDesc rd;
-    memset(&rd, 0, sizeof rd);
-    rd.resType = cudaResourceTypeLinear;
-    rd.res.linear.devPtr = const_cast<T*>(ptr);
-    rd.res.linear.desc = cudaCreateChannelDesc<T>();
-    rd.res.linear.sizeInBytes = n * sizeof(T);
-    cudaTextureDesc td;
-    memset(&td, 0, sizeof td);
-    td.readMode = cudaReadModeElementType;
-    CU(cudaCreateTextureObject(tex, &rd, &td, nullptr));
-    *cur = ptr;
-    return SPH_OK;
-}
 
 // ghost refresh of v* in whichever representation the evaluations gather (one NCCL group); vs itself is included
 // because the velocity fold reads vel = v* for ghosts too
@@ -1906,6 +1913,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     if (const char* t = getenv("SALVA_B200_FUSE_DIV")) w->fuse_div = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_FUSE_XSPH")) w->fuse_xsph = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_FUSE_AKINCI")) w->fuse_akinci = atoi(t) != 0;
+    if (const char* t = getenv("SALVA_B200_NBR_TEX")) w->nbr_tex = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_UNI_EVAL")) w->uni_eval_mode = atoi(t);
     if (const char* t = getenv("SALVA_B200_UNI_UPD")) w->uni_upd_mode = atoi(t);
     {

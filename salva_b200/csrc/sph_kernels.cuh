@@ -500,15 +500,18 @@ __global__ void k_scanK_add(ScanSet<K> io, uint32_t n, ScanSet<K> block_offsets)
 // only records hits in a 32-bit mask per chunk of 32 candidates; the (short) emit loop then walks the set bits in
 // ascending order, which keeps every list in the same order as a plain scan.
 // ------------------------------------------------------------------------------------------------
-template <class Accept, class Emit>
-__device__ __forceinline__ void scan_run(const float4& pi, const float4* __restrict__ P, uint32_t s, uint32_t e, Accept accept, Emit emit) {
+// TEX (optional): a texture over the same array P; odd candidates are then fetched through the texture pipe, so the candidate
+// stream (243 loads per particle) is split over both L1TEX front ends like the gather passes' (SALVA_B200_NBR_TEX).
+template <bool NTEX = false, class Accept, class Emit>
+__device__ __forceinline__ void scan_run(const float4& pi, const float4* __restrict__ P, uint32_t s, uint32_t e, Accept accept, Emit emit,
+                                         cudaTextureObject_t TEX = 0) {
     for (uint32_t base = s; base < e; base += 32u) {
         const uint32_t n = min(32u, e - base);
         const float4* __restrict__ q = P + base;
         uint32_t rej = 0u;  // candidate t of the chunk ends up in bit n - 1 - t; set = rejected
 #pragma unroll 4
         for (uint32_t t = 0; t < n; ++t) {
-            const float4 pj = __ldg(&q[t]);
+            const float4 pj = (NTEX && (t & 1u)) ? tex1Dfetch<float4>(TEX, (int)(base + t)) : __ldg(&q[t]);
             const float d2 = dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
             // d2 <= h*h  <=>  the sign bit of (h*h - d2) is clear (a float difference is zero only for equal operands;
             // NaN positions never get here, k_bounds rejects them): shift that bit into the mask with one funnel shift
@@ -524,12 +527,12 @@ __device__ __forceinline__ void scan_run(const float4& pi, const float4* __restr
     }
 }
 
-template <bool MULTI>
+template <bool MULTI, bool NTEX>
 __global__ void __launch_bounds__(128)
 k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, const uint32_t* __restrict__ cstart,
             const float4* __restrict__ bpos, const float4* __restrict__ bvel, const uint32_t* __restrict__ bstart,
             uint32_t* __restrict__ nbr_f, uint32_t* __restrict__ nbr_b, uint32_t* __restrict__ cnt_f, uint32_t* __restrict__ cnt_b,
-            uint32_t* __restrict__ maxcnt /* [0]=fluid,[1]=boundary */) {
+            uint32_t* __restrict__ maxcnt /* [0]=fluid,[1]=boundary */, cudaTextureObject_t tpos) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nf = 0, nb = 0;
     const bool owned = i < C.n_owned;
@@ -541,7 +544,7 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
         for (int ax = -1; ax <= 1; ++ax)
             for (int ay = -1; ay <= 1; ++ay) {
                 int base = cell_id(cx + ax, cy + ay, cz);
-                scan_run(
+                scan_run<NTEX>(
                     pi, pos, cstart[base - 1], cstart[base + 2],
                     [&](uint32_t j) {
                         if (!MULTI) return true;
@@ -553,7 +556,8 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
                         //  SLOWER, 1.66 -> 1.80 ms at C3 — the shift-in costs more issue slots than the stores save)
                         if (nf < C.cap_f) nbr_f[((size_t)(nf >> 2) * C.stride + i) * 4 + (nf & 3)] = j;
                         ++nf;
-                    });
+                    },
+                    tpos);
                 if (C.n_bound)
                     scan_run(
                         pi, bpos, bstart[base - 1], bstart[base + 2],
