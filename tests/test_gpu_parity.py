@@ -507,3 +507,13 @@ def test_error_paths():
     assert e.value.status == 1
     with pytest.raises(SphError):
         gpu.read_fluid(f + 7)
+
+
+def test_parity_at_110k_particles_through_the_bench_block():
+    """The same GPU-vs-oracle block every bench line carries (bench.py parity_vs_oracle), at 48^3 = 110 592 particles of the
+    C3 generator: contact counts exact on identical inputs, 3-step trajectory within the SURVEY 8(c) tolerances."""
+    import bench
+    res = bench.parity_vs_oracle("c3", 0, edge=48, steps=3)
+    assert res["n"] == 48 ** 3 and res["contacts_equal"] is True
+    assert res["max_dx_over_h"] <= 1e-3 and res["max_rel_rho"] <= 1e-5 and res["max_dv_over_h_dt"] <= 1e-3
+    assert res["ok"]
