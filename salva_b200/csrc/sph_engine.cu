@@ -230,6 +230,7 @@ struct sph_world {
     DBuf<Rec8> rec8, nrec8;  // 256-bit gather records: (pos, v*, rho) of the evaluations, (pos, normal, rho) of the Akinci force pass
     int use_rec8 = 0;        // 0: off, 1: pressure-loop evaluations, 2: every evaluation of the step (+ fused XSPH / Akinci normals)
     bool nrec_valid = false;
+    bool fuse_fold = true;  // fold + gravity + integrate in one pass when the force phase has nothing to launch
     bool nbr_tex = false;  // experiment: odd neighbour-search candidates through the texture pipe (SALVA_B200_NBR_TEX)
     bool fuse_akinci = true, nr4_valid = false;  // Akinci normals ride with a divergence evaluation (k_vel_divergence_xsph_u<.., 2>)
     cudaTextureObject_t tex_pvx = 0, tex_vyz = 0, tex_pk = 0;
@@ -771,10 +772,10 @@ sph_status phase_grid(sph_world* w) {
             g.out1[2] = reinterpret_cast<uint32_t*>(w->press[c ^ 1].p);
             g.n1 = 3;
         }
-        LAUNCH(k_gather, N, 256, (uint32_t)N, w->perm.p, g);
+        // reorder + v* = vel + vc (the divergence solve works on vel + vc carried over from the previous step, Appendix A.3.2) in one pass
+        LAUNCH(k_gather_vstar, N, 256, (uint32_t)N, w->perm.p, g, w->vs.p, w->unimass ? w->pvx4.p : nullptr, w->unimass ? w->vyz2.p : nullptr,
+               rec8_full(w) ? w->rec8.p : nullptr);
         w->cur = c ^ 1;
-        LAUNCH(k_make_vstar, N, 256, w->vel[w->cur].p, w->vc[w->cur].p, w->vs.p, w->pos[w->cur].p, w->unimass ? w->pvx4.p : nullptr,
-               w->unimass ? w->vyz2.p : nullptr, rec8_full(w) ? w->rec8.p : nullptr);
     }
     // boundaries: same sort — reused while neither the boundaries nor the cell mapping changed (static tanks)
     const int gridkey[6] = {w->hc.ox, w->hc.oy, w->hc.oz, w->hc.nx, w->hc.ny, w->hc.nz};
@@ -1680,15 +1681,31 @@ sph_status dfsph_step(sph_world* w, float dt_total, const float g[3]) {
     CU(cudaEventRecord(w->ev[EV_DIV], w->st));
     // update_velocities :422-430, zero vc :689-691, acc += gravity :574-578
     TRY(slab_wait(w));
-    LAUNCH(k_fold_velocities, w->Ntot, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2],  // ghosts too (vel = v*)
-           w->xs_valid ? (const float4*)w->xs.p : (const float4*)nullptr, w->inv_dt);
-    CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
-    TRY(phase_forces(w));
-    CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
-    timestep_advance(w, dt_total);  // :702
     const bool r8 = rec8_predict(w);
-    LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->unimass ? w->pvx4.p : nullptr,
-           w->unimass ? w->vyz2.p : nullptr, w->pos[c].p, r8 ? w->rec8.p : nullptr, w->dens.p);
+    // nothing to launch in the force phase (no plugin at all, or only the XSPH whose sums rode with the divergence loop)?  Then
+    // fold, acceleration and integration are one streaming pass (SALVA_B200_FUSE_FOLD=0 keeps them apart)
+    bool quiet_forces = w->fuse_fold && !r8;
+    for (size_t f = 0; f < w->fluids.size() && quiet_forces; ++f)
+        for (const ForceRec& fr : w->fluids[f].forces)
+            if (!(w->xs_valid && f == 0 && &fr == &w->fluids[0].forces[0] && fr.d.kind == SPH_FORCE_XSPH_VISCOSITY)) quiet_forces = false;
+    if (quiet_forces) {
+        const float inv_dt_old = w->inv_dt;
+        CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
+        CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
+        timestep_advance(w, dt_total);  // :702
+        LAUNCH(k_fold_integrate, w->Ntot, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2],
+               w->xs_valid ? (const float4*)w->xs.p : (const float4*)nullptr, inv_dt_old, w->dt, w->unimass ? w->pvx4.p : nullptr,
+               w->unimass ? w->vyz2.p : nullptr);
+    } else {
+        LAUNCH(k_fold_velocities, w->Ntot, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, g[0], g[1], g[2],  // ghosts too (vel = v*)
+               w->xs_valid ? (const float4*)w->xs.p : (const float4*)nullptr, w->inv_dt);
+        CU(cudaEventRecord(w->ev[EV_FOLD], w->st));
+        TRY(phase_forces(w));
+        CU(cudaEventRecord(w->ev[EV_FORCES], w->st));
+        timestep_advance(w, dt_total);  // :702
+        LAUNCH(k_integrate_acc, N, 256, w->vel[c].p, w->vc[c].p, w->vs.p, w->acc.p, w->dt, w->unimass ? w->pvx4.p : nullptr,
+               w->unimass ? w->vyz2.p : nullptr, w->pos[c].p, r8 ? w->rec8.p : nullptr, w->dens.p);
+    }
     TRY(refresh_vstar(w));
     CU(cudaEventRecord(w->ev[EV_INTEG], w->st));
     // pressure_solve :432-464
@@ -1914,6 +1931,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     if (const char* t = getenv("SALVA_B200_FUSE_XSPH")) w->fuse_xsph = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_FUSE_AKINCI")) w->fuse_akinci = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_NBR_TEX")) w->nbr_tex = atoi(t) != 0;
+    if (const char* t = getenv("SALVA_B200_FUSE_FOLD")) w->fuse_fold = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_UNI_EVAL")) w->uni_eval_mode = atoi(t);
     if (const char* t = getenv("SALVA_B200_UNI_UPD")) w->uni_upd_mode = atoi(t);
     {

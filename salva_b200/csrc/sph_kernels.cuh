@@ -700,6 +700,30 @@ __device__ __forceinline__ void st_rec8(Rec8* p, float x, float y, float z, floa
                  : "memory");
 }
 
+// The fluid reorder fused with k_make_vstar: the sorted pos / vel / vc are in registers anyway, so v* = vel + vc and the packed
+// gather records are written by the same pass (saves re-reading 48 B per particle and a launch).  g.in4 / out4 [0..2] = pos, vel, vc.
+__global__ void k_gather_vstar(uint32_t n, const uint32_t* __restrict__ perm, GatherSet g, float4* __restrict__ vs, float4* __restrict__ pvx,
+                               float2* __restrict__ vyz, Rec8* __restrict__ rec) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t src = perm[s];
+    const float4 p = g.in4[0][src], v = g.in4[1][src], c = g.in4[2][src];
+    g.out4[0][s] = p;
+    g.out4[1][s] = v;
+    g.out4[2][s] = c;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+        if (a < g.n1) g.out1[a][s] = g.in1[a][src];
+    const float sx = v.x + c.x, sy = v.y + c.y, sz = v.z + c.z;
+    vs[s] = make_float4(sx, sy, sz, 0.f);
+    if (rec) {
+        st_rec8(rec + s, p.x, p.y, p.z, sx, sy, sz, 0.f);
+    } else if (pvx) {
+        pvx[s] = make_float4(p.x, p.y, p.z, sx);
+        vyz[s] = make_float2(sy, sz);
+    }
+}
+
 // v* = vel + vc after the reorder (the divergence solve works on vel + vc carried over from the previous step, Appendix A.3.2)
 __global__ void k_make_vstar(const float4* __restrict__ vel, const float4* __restrict__ vc, float4* __restrict__ vs, const float4* __restrict__ pos,
                              float4* __restrict__ pvx, float2* __restrict__ vyz, Rec8* __restrict__ rec) {
@@ -738,6 +762,38 @@ __global__ void k_fold_velocities(float4* __restrict__ vel, float4* __restrict__
         az = __fadd_rn(gz, __fmul_rn(f.z, inv_dt));
     }
     acc[i] = make_float4(ax, ay, az, 0.f);
+}
+// update_velocities + the gravity / folded-XSPH acceleration + integrate_and_clear_accelerations in ONE pass, for steps whose force
+// phase launches nothing (no plugin, or only the XSPH whose sums rode with the divergence loop): same arithmetic, in the same
+// order, as k_fold_velocities followed by k_integrate_acc.  Ghost slots (multi-GPU) only take the fold part.
+__global__ void k_fold_integrate(float4* __restrict__ vel, float4* __restrict__ vc, float4* __restrict__ vs, float4* __restrict__ acc, float gx, float gy,
+                                 float gz, const float4* __restrict__ xs, float inv_dt_old, float dt_new, float4* __restrict__ pvx, float2* __restrict__ vyz) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_fluid) return;
+    const float4 v = vel[i], s = vs[i];
+    const float4 nv = make_float4(s.x, s.y, s.z, v.w);
+    vel[i] = nv;
+    const bool owned = i >= C.i_begin && i < C.i_begin + C.n_owned;
+    float ax = gx, ay = gy, az = gz;
+    if (xs) {
+        const float4 f = xs[i];
+        ax = __fadd_rn(gx, __fmul_rn(f.x, inv_dt_old));
+        ay = __fadd_rn(gy, __fmul_rn(f.y, inv_dt_old));
+        az = __fadd_rn(gz, __fmul_rn(f.z, inv_dt_old));
+    }
+    acc[i] = make_float4(ax, ay, az, 0.f);
+    if (!owned) {
+        vc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float cx = __fmul_rn(ax, dt_new), cy = __fmul_rn(ay, dt_new), cz = __fmul_rn(az, dt_new);  // vc = 0 + acc * dt
+    vc[i] = make_float4(cx, cy, cz, 0.f);
+    const float sx = nv.x + cx, sy = nv.y + cy, sz = nv.z + cz;
+    vs[i] = make_float4(sx, sy, sz, 0.f);
+    if (pvx) {
+        pvx[i].w = sx;
+        vyz[i] = make_float2(sy, sz);
+    }
 }
 // IISPH variant: accelerations += gravity only (vc is already zero, velocities untouched).
 __global__ void k_set_gravity(const float4* __restrict__ vel, float4* __restrict__ vs, float4* __restrict__ acc, float gx, float gy, float gz) {
