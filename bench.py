@@ -476,23 +476,25 @@ def native_arm(args, rank, world_size):
     world.close()
     del hp_all, hv_all
 
-    # ---- second measurement: compressed start (lattice spacing 0.90 * 2r, +10 % density), Jacobi loops iterate ---------
+    # ---- second measurement: the Jacobi loops iterate.  Start from a 0.92-compressed lattice (+2.7 % density): for the next
+    # ~8 steps the divergence loop runs 4-6 updates per step while the block relaxes (probed on the oracle; a stronger
+    # compression, 0.90, blows the block apart at 100 m/s through the tank walls, which is neither a meaningful regime nor kind
+    # to a dense cell grid).  One GPU only: the driver's scaling runs stay as short (and as safe) as possible.
     settled = None
-    if not args.no_settled and world_size == 1:   # one GPU only: the driver's scaling runs stay as short (and as safe) as possible
-        sc2, w2, _ = make_world(compress=0.90)
-        for _ in range(5):   # the over-dense start widens the contact lists: let the capacity settle before timing
-            w2.step(sc2["dt"], sc2["gravity"])
-        k2 = max(3, min(args.steps, 10))
+    if not args.no_settled and world_size == 1:
+        sc2, w2, _ = make_world(compress=0.92)
+        w2.step(sc2["dt"], sc2["gravity"])   # the first step only sees dt = 0 quantities (timestep_manager.rs:29-30)
+        k2 = 8
         acc2, _, iters2, wall2, st2 = timed_steps(w2, sc2, k2, barrier)
         dev2 = allmax([acc2["step_ms"] * 1e-3])[0]
-        settled = {"what": "same workload started from a 0.90-compressed lattice (+10 %% density), 5 warm-up + %d timed steps" % k2,
+        settled = {"what": "same workload started from a 0.92-compressed lattice (+2.7 %% density): 1 warm-up + %d timed steps while the block relaxes" % k2,
                    "value": nf * k2 / dev2, "unit": UNIT, "ms_per_step": dev2 / k2 * 1e3,
                    "iterations_per_step_mean": [float(np.mean([i[0] for i in iters2])), float(np.mean([i[1] for i in iters2]))],
                    "pressure_pair_ms": (acc2["predict_density_ms"] / max(acc2["n_pressure_eval"], 1) +
                                         acc2["pressure_update_ms"] / max(acc2["n_pressure_iter"], 1)),
                    "divergence_pair_ms": (acc2["divergence_eval_ms"] / max(acc2["n_divergence_eval"] - k2, 1) +
                                           acc2["divergence_update_ms"] / max(acc2["n_divergence_iter"], 1)),
-                   "wall_ms_per_step": wall2 / k2 * 1e3, "max_neighbors": st2.get("max_neighbors"),
+                   "wall_ms_per_step": wall2 / k2 * 1e3, "max_neighbors": st2.get("max_neighbors"), "grid_dims": st2.get("grid_dims"),
                    "phases": {k: acc2[k] / k2 for k in sorted(acc2) if k.endswith("_ms")}}
         w2.close()
 
