@@ -224,7 +224,34 @@ def run_oracle(sc, steps, warmup, threads=0):
         iters.append((st["n_divergence_iter"], st["n_pressure_iter"]))
     dt = time.perf_counter() - t0
     nf = sum(len(f["positions"]) for f in sc["fluids"])
-    return nf * steps / dt, dt / steps * 1e3, w.stats()["threads"], iters
+    st = w.stats()
+    run_oracle.last_stages = {k: st[k] for k in st if k.endswith("_ms")}  # stage times of the LAST step (Counters-like)
+    return nf * steps / dt, dt / steps * 1e3, st["threads"], iters
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"nproc": os.cpu_count() or 1, "cpu_model": model}
+
+
+def cpu_extras(cfg):
+    """Host description, per-stage ms of the last timed step of the port, and the same port on ONE thread (64^3 probe block)."""
+    out = dict(host_info())
+    out["stages_ms_last_step"] = {k: round(v, 3) for k, v in getattr(run_oracle, "last_stages", {}).items()}
+    try:
+        probe = build_scene(cfg, 64, 1) if cfg in ("c2", "c3", "c4") else build_scene(cfg, 0, 1)
+        v1, ms1, _, _ = run_oracle(probe, 1, 1, 1)
+        out["single_thread"] = {"value": v1, "unit": UNIT, "particles": sum(len(f["positions"]) for f in probe["fluids"]), "ms_per_step": ms1}
+    except Exception as e:  # the extras never break the line
+        out["single_thread"] = {"error": str(e)[:100]}
+    return out
 
 
 def cpu_sample_edge(cfg, n, ref_n):
@@ -251,6 +278,7 @@ def reference_arm(args, rank, world_size):
     probe = build_scene(cfg, min(edge or 64, 64), 1) if cfg in ("c2", "c3", "c4") else sc
     threads = best_oracle_threads(probe)
     value, ms, threads, iters = run_oracle(sc, args.steps, args.warmup, threads)
+    extras = cpu_extras(cfg)
     conf = static_config(cfg, args.n, world_size)
     sample = ("%s generator at %d fluid particles (%s), %d host threads (fastest of 8..nproc on a 64^3 probe), %d+%d steps, %.0f ms/step"
               % (cfg.upper(), nf, "the whole workload" if nf == conf["fluid_particles_total"] else "bounded sample of the workload", threads,
@@ -259,7 +287,7 @@ def reference_arm(args, rank, world_size):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": conf,
             "sample_particles": nf, "iterations_last_step": list(iters[-1]) if iters else None,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}, **extras),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -550,6 +578,7 @@ def native_arm(args, rank, world_size):
         cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%s generator at %d fluid particles (%s), 1+%d steps, %.0f ms/step" %
                          (cfg.upper(), cnf, "the whole workload" if cnf == nf else "bounded sample", args.cpu_steps, cms)}
+        cpu.update(cpu_extras(cfg))
     phases = {k: acc[k] / args.steps for k in sorted(acc) if k.endswith("_ms")}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": warm,
             "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
