@@ -40,8 +40,13 @@ struct Consts {
     // (default, the lean path), 1 = Poly6, 2 = Spiky, 3 = Viscosity; kgen != 0 <=> any of the two is not the cubic spline
     int kw, kg, kgen;
     float poly6_n, spiky_n, visc_n;  // 315/(64 pi h^9), 15/(pi h^6), 15/(2 pi h^3)
-    int ox, oy, oz;              // grid origin in cell coordinates (one padding cell each side)
+    int ox, oy, oz;              // grid origin in cell coordinates (one padding cell each side); oz and nz count z-BINS
     int nx, ny, nz;
+    // z-bins: the counting sort splits every cell of width h into `zsub` slices along z (the run direction of the sorted
+    // order), so the neighbour search can cut each of its 9 z-runs down to the slices within reach of the particle
+    // (2h + h/zsub instead of 3h of candidates).  x and y keep the reference's cells; zsub = 1 is the plain h-cell grid.
+    int zsub;
+    float zsub_f, h_reach;       // (float)zsub; h * (1 + 1e-5): covers every |dz| the f32 test d^2 <= h^2 can accept
     int ntx, nty, ntz;           // tile grid (sph_tile.cuh): 2 x 2 cell columns x TILE_Z cells per tile
     uint32_t n_fluid, n_bound;   // particle totals (n_fluid counts owned + ghost slots of the sorted arrays)
     uint32_t i_begin, n_owned;   // owned slots [i_begin, i_begin + n_owned): everything on one GPU; the slab between the
@@ -63,6 +68,27 @@ __constant__ Consts C;
 __device__ __forceinline__ int cell_coord(float x) { return (int)floorf(__fdiv_rn(x, C.h)); }
 
 __device__ __forceinline__ int cell_id(int cx, int cy, int cz) { return ((cx - C.ox) * C.ny + (cy - C.oy)) * C.nz + (cz - C.oz); }
+// z-bin of a coordinate: reference cell floor(z / h) (same IEEE division) times zsub plus the slice inside the cell.  Monotone
+// non-decreasing in z (correctly rounded division, exact q - floor(q)), and every bin lies inside ONE reference cell.
+__device__ __forceinline__ int zbin(float z) {
+    const float q = __fdiv_rn(z, C.h), fl = floorf(q);
+    const int cz = (int)fl;
+    if (C.zsub == 1) return cz;
+    return cz * C.zsub + min(C.zsub - 1, (int)((q - fl) * C.zsub_f));
+}
+// Bins [lo, hi] of the z-run a particle at z (reference cell cz) has to scan: everything within h_reach of z, clipped to the
+// three reference cells cz-1..cz+1 the reference's 27-cell stencil looks at.  A pair that passes the f32 test
+// (dx^2 + dy^2) + dz^2 <= h^2 has |z_i - z_j| <= h (1 + 2^-22) < h_reach; the bounds are rounded outwards, and zbin is
+// monotone, so no accepted pair of adjacent reference cells is ever cut off: the contact sets stay exactly the reference's.
+__device__ __forceinline__ void zrun(float z, int cz, int& lo, int& hi) {
+    if (C.zsub == 1) {
+        lo = cz - 1;
+        hi = cz + 1;
+        return;
+    }
+    lo = max(zbin(__fsub_rd(z, C.h_reach)), (cz - 1) * C.zsub);
+    hi = min(zbin(__fadd_ru(z, C.h_reach)), (cz + 2) * C.zsub - 1);
+}
 
 // contacts.rs:285,322,366: (dx*dx + dy*dy) + dz*dz <= h*h with no contraction (rustc never fuses).
 __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
@@ -317,7 +343,7 @@ __global__ void k_cell_hist(const float4* __restrict__ pos, uint32_t n, uint32_t
         return;
     }
     float4 p = pos[i];
-    uint32_t id = (uint32_t)cell_id(cell_coord(p.x), cell_coord(p.y), cell_coord(p.z));
+    uint32_t id = (uint32_t)cell_id(cell_coord(p.x), cell_coord(p.y), zbin(p.z));
     cid[i] = id;
     rank[i] = atomicAdd(&count[id], 1u);
 }
@@ -527,6 +553,9 @@ __device__ __forceinline__ void scan_run(const float4& pi, const float4* __restr
     }
 }
 
+#ifndef SPH_NBR_RUNPTR
+#define SPH_NBR_RUNPTR 1  // list entries addressed with a running pointer instead of recomputing ((k >> 2) * stride + i) * 4 + (k & 3)
+#endif
 template <bool MULTI, bool NTEX>
 __global__ void __launch_bounds__(128)
 k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, const uint32_t* __restrict__ cstart,
@@ -541,11 +570,15 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
         float4 pi = pos[i];
         uint32_t fi = MULTI ? fid_of(vel[i]) : 0u;
         int cx = cell_coord(pi.x), cy = cell_coord(pi.y), cz = cell_coord(pi.z);
+        int zlo, zhi;
+        zrun(pi.z, cz, zlo, zhi);
+        uint32_t* wp = nbr_f + (size_t)i * 4;                  // slot 0 of group 0 of this particle's column
+        const size_t gstep = (size_t)C.stride * 4 - 4;         // from behind slot 3 of a group to slot 0 of the next one
         for (int ax = -1; ax <= 1; ++ax)
             for (int ay = -1; ay <= 1; ++ay) {
-                int base = cell_id(cx + ax, cy + ay, cz);
+                const int lo = cell_id(cx + ax, cy + ay, zlo), hi = lo + (zhi - zlo) + 1;
                 scan_run<NTEX>(
-                    pi, pos, cstart[base - 1], cstart[base + 2],
+                    pi, pos, cstart[lo], cstart[hi],
                     [&](uint32_t j) {
                         if (!MULTI) return true;
                         uint32_t fj = fid_of(__ldg(&vel[j]));  // contacts.rs:355-362: different fluids need the groups test
@@ -554,13 +587,21 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
                     [&](uint32_t j) {
                         // (one 4-byte store per hit: collecting four hits in registers and storing 16-byte groups was measured
                         //  SLOWER, 1.66 -> 1.80 ms at C3 — the shift-in costs more issue slots than the stores save)
+                        //  entry k of particle i lives at ((k >> 2) * stride + i) * 4 + (k & 3): walked with a running pointer)
+#if SPH_NBR_RUNPTR
+                        if (nf < C.cap_f) *wp = j;
+                        ++nf;
+                        ++wp;
+                        if ((nf & 3u) == 0u) wp += gstep;
+#else
                         if (nf < C.cap_f) nbr_f[((size_t)(nf >> 2) * C.stride + i) * 4 + (nf & 3)] = j;
                         ++nf;
+#endif
                     },
                     tpos);
                 if (C.n_bound)
                     scan_run(
-                        pi, bpos, bstart[base - 1], bstart[base + 2],
+                        pi, bpos, bstart[lo], bstart[hi],
                         [&](uint32_t j) {  // contacts.rs:347-352
                             uint32_t bj = fid_of(__ldg(&bvel[j]));
                             return groups_test(C.fluids[fi].memberships, C.fluids[fi].filter, C.bounds[bj].memberships, C.bounds[bj].filter);
@@ -570,7 +611,11 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
                             ++nb;
                         });
             }
-        for (uint32_t t = nf; t < ((nf + 3u) & ~3u) && t < C.cap_f; ++t) nbr_f[((size_t)(t >> 2) * C.stride + i) * 4 + (t & 3)] = i;  // pad the last group
+#if SPH_NBR_RUNPTR
+        for (uint32_t t = nf; t < ((nf + 3u) & ~3u) && t < C.cap_f; ++t) *wp++ = i;  // pad the last group
+#else
+        for (uint32_t t = nf; t < ((nf + 3u) & ~3u) && t < C.cap_f; ++t) nbr_f[((size_t)(t >> 2) * C.stride + i) * 4 + (t & 3)] = i;
+#endif
         cnt_f[i] = nf;
         cnt_b[i] = nb;
     }
@@ -599,8 +644,8 @@ k_boundary_volumes(const float4* __restrict__ bpos, const float4* __restrict__ b
         float den = 0.f;
         for (int ax = -1; ax <= 1; ++ax)
             for (int ay = -1; ay <= 1; ++ay) {
-                int base = cell_id(cx + ax, cy + ay, cz);
-                uint32_t s = bstart[base - 1], e = bstart[base + 2];
+                int base = cell_id(cx + ax, cy + ay, (cz - 1) * C.zsub);  // all bins of the three reference cells cz-1..cz+1
+                uint32_t s = bstart[base], e = bstart[base + 3 * C.zsub];
                 for (uint32_t j = s; j < e; ++j) {
                     float4 pj = __ldg(&bpos[j]);
                     float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
