@@ -94,6 +94,24 @@ __device__ __forceinline__ void zrun(float z, int cz, int& lo, int& hi) {
 __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
+// The same value, bit for bit, with the x and y lanes done by Blackwell's packed-f32 instructions (FADD2 / FMUL2: two IEEE
+// round-to-nearest operations per issue slot; sm_100+).  Only subtract and multiply are packed: ptxas contracts a packed
+// multiply feeding a packed add into FFMA2 even with explicit .rn, which would change the rounding; the adds stay scalar.
+// The neighbour search is issue-bound (81 % of its issue slots, profiles/r2_ncu_neighbors_c3.md): 9 instead of 11 slots per candidate.
+__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float dist2_exact_packed(unsigned long long pi_xy, float pi_z, const float4& pj) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pi_xy), "l"(pack_f32x2(pj.x, pj.y)));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(d) : "l"(d));
+    float sx, sy;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(sx), "=f"(sy) : "l"(d));
+    const float dz = __fsub_rn(pi_z, pj.z);
+    return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
+}
 
 // cubic_spline_kernel.rs:12-33: W(r) for q = r/h.
 __device__ __forceinline__ float kernel_w(float r) {
@@ -528,6 +546,9 @@ __global__ void k_scanK_add(ScanSet<K> io, uint32_t n, ScanSet<K> block_offsets)
 // ------------------------------------------------------------------------------------------------
 // TEX (optional): a texture over the same array P; odd candidates are then fetched through the texture pipe, so the candidate
 // stream (243 loads per particle) is split over both L1TEX front ends like the gather passes' (SALVA_B200_NBR_TEX).
+#ifndef SPH_PACKED_F32
+#define SPH_PACKED_F32 1
+#endif
 template <bool NTEX = false, class Accept, class Emit>
 __device__ __forceinline__ void scan_run(const float4& pi, const float4* __restrict__ P, uint32_t s, uint32_t e, Accept accept, Emit emit,
                                          cudaTextureObject_t TEX = 0) {
@@ -535,8 +556,36 @@ __device__ __forceinline__ void scan_run(const float4& pi, const float4* __restr
         const uint32_t n = min(32u, e - base);
         const float4* __restrict__ q = P + base;
         uint32_t rej = 0u;  // candidate t of the chunk ends up in bit n - 1 - t; set = rejected
+        uint32_t t = 0;
+#if SPH_PACKED_F32
+        if (!NTEX) {
+            // two candidates per trip: x/y differences and squares, the two z squares and the two (h^2 - d^2) as packed pairs;
+            // 9.5 issue slots per candidate instead of 12.75 (SASS: 2 FADD2 + 3 FMUL2 + 1 FADD2 + 6 FADD + 2 SHF + 2 LDG per pair)
+            const unsigned long long pi_xy = pack_f32x2(pi.x, pi.y), hh = pack_f32x2(C.h2, C.h2);
+#pragma unroll 2
+            for (; t + 1 < n; t += 2) {
+                const float4 pa = __ldg(&q[t]), pb = __ldg(&q[t + 1]);
+                unsigned long long da, db, dz, r;
+                asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(da) : "l"(pi_xy), "l"(pack_f32x2(pa.x, pa.y)));
+                asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(db) : "l"(pi_xy), "l"(pack_f32x2(pb.x, pb.y)));
+                asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(da) : "l"(da));
+                asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(db) : "l"(db));
+                dz = pack_f32x2(__fsub_rn(pi.z, pa.z), __fsub_rn(pi.z, pb.z));
+                asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(dz) : "l"(dz));
+                float ax, ay, bx, by, za, zb, r0, r1;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(ax), "=f"(ay) : "l"(da));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(bx), "=f"(by) : "l"(db));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(za), "=f"(zb) : "l"(dz));
+                const float d2a = __fadd_rn(__fadd_rn(ax, ay), za), d2b = __fadd_rn(__fadd_rn(bx, by), zb);  // scalar adds: see dist2_exact_packed
+                asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(hh), "l"(pack_f32x2(d2a, d2b)));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+                rej = __funnelshift_l(__float_as_uint(r0), rej, 1);
+                rej = __funnelshift_l(__float_as_uint(r1), rej, 1);
+            }
+        }
+#endif
 #pragma unroll 4
-        for (uint32_t t = 0; t < n; ++t) {
+        for (; t < n; ++t) {
             const float4 pj = (NTEX && (t & 1u)) ? tex1Dfetch<float4>(TEX, (int)(base + t)) : __ldg(&q[t]);
             const float d2 = dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
             // d2 <= h*h  <=>  the sign bit of (h*h - d2) is clear (a float difference is zero only for equal operands;
