@@ -97,7 +97,7 @@ __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
 // The same value, bit for bit, with the x and y lanes done by Blackwell's packed-f32 instructions (FADD2 / FMUL2: two IEEE
 // round-to-nearest operations per issue slot; sm_100+).  Only subtract and multiply are packed: ptxas contracts a packed
 // multiply feeding a packed add into FFMA2 even with explicit .rn, which would change the rounding; the adds stay scalar.
-// The neighbour search is issue-bound (81 % of its issue slots, profiles/r2_ncu_neighbors_c3.md): 9 instead of 11 slots per candidate.
+// (Experiment only, see SPH_PACKED_F32 at scan_run: fewer issue slots, but not faster.)
 __device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
@@ -546,8 +546,12 @@ __global__ void k_scanK_add(ScanSet<K> io, uint32_t n, ScanSet<K> block_offsets)
 // ------------------------------------------------------------------------------------------------
 // TEX (optional): a texture over the same array P; odd candidates are then fetched through the texture pipe, so the candidate
 // stream (243 loads per particle) is split over both L1TEX front ends like the gather passes' (SALVA_B200_NBR_TEX).
+// Packed-f32 candidate test (FADD2 / FMUL2, below): bit-identical contact sets (all GPU tests pass with it) and 9.75 instead of
+// 12.75 issue slots per candidate in SASS, but measured SLOWER (k_neighbors 1.637 -> 1.669 ms at C3, 0.662 -> 0.683 ms on the C4
+// slice, profiles/r2_exp_m_raw.txt): the packed instructions do not issue at the scalar rate and the LSU data pipe (78 %) is the
+// co-limiter anyway.  Kept behind -DSPH_PACKED_F32=1.
 #ifndef SPH_PACKED_F32
-#define SPH_PACKED_F32 1
+#define SPH_PACKED_F32 0
 #endif
 template <bool NTEX = false, class Accept, class Emit>
 __device__ __forceinline__ void scan_run(const float4& pi, const float4* __restrict__ P, uint32_t s, uint32_t e, Accept accept, Emit emit,
