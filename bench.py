@@ -396,9 +396,13 @@ def timed_steps(world, sc, steps, barrier):
             acc[k] = acc.get(k, 0) + st[k]
         launches += st["kernel_launches"]
         iters.append((st["n_divergence_iter"], st["n_pressure_iter"]))
+        timed_steps.per_step.append((round(st["step_ms"], 3), round(st["grid_ms"], 3)))
     barrier()
     wall = time.perf_counter() - t0
     return acc, launches, iters, wall, st
+
+
+timed_steps.per_step = []   # (step_ms, grid_ms) of every timed step on this rank: a one-off stall shows up here, not in the mean
 
 
 def native_arm(args, rank, world_size):
@@ -474,7 +478,9 @@ def native_arm(args, rank, world_size):
 
     # ---- timed region: device-resident inputs, CUDA-event time of every step -------------------------------------
     sampler.mark()
+    timed_steps.per_step = []
     acc, launches, iters, wall, st = timed_steps(world, sc, args.steps, barrier)
+    per_step = list(timed_steps.per_step)
     clocks = sampler.stop()
     dev_s, wall = allmax([acc["step_ms"] * 1e-3, wall])
     value = nf * args.steps / dev_s
@@ -588,6 +594,7 @@ def native_arm(args, rank, world_size):
             "fluid_particles_per_gpu": nf // world_size,
             "iterations_per_step_mean": [float(np.mean([i[0] for i in iters])), float(np.mean([i[1] for i in iters]))],
             "phases": phases, "wall_ms_per_step": wall / args.steps * 1e3,
+            "per_step_ms_rank0": {"step": [p[0] for p in per_step[:64]], "grid": [p[1] for p in per_step[:64]]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "sph_fluid_write + sph_world_step + sph_fluid_read (pinned host buffers), all ranks"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
