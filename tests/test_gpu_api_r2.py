@@ -351,3 +351,26 @@ def test_replace_particles_in_a_different_order_keeps_the_trajectory_bit_exact()
     assert np.array_equal(ib, ids[perm])
     oa, ob_ = np.argsort(ia), np.argsort(ib)
     assert np.array_equal(pa[oa], pb[ob_]) and np.array_equal(va[oa], vb[ob_])
+
+
+def test_handle_arena_follows_the_reference_unit_test():
+    """The one unit test the reference holds for this boundary: ContiguousArena `smoke` (src/object/contiguous_arena.rs:172-184) —
+    three inserts, every handle removes its own value exactly once, a second removal finds nothing.  Fluids and boundaries live in
+    that arena (liquid_world.rs:161-178); the value is checked through the particle count stored under the handle."""
+    r = 0.05
+    w = LiquidWorld(particle_radius=r)
+    sizes = (123, 456, 789)
+    pts = [scenes.block_lattice(n, 1, 1, r, origin=(0.0, 3.0 * k, 0.0)) for k, n in enumerate(sizes)]
+    fh = [w.add_fluid(p, density0=1000.0) for p in pts]
+    bh = [w.add_boundary(p + np.float32(20.0)) for p in pts]
+    assert len(set(fh)) == 3 and len(set(bh)) == 3
+    for h, n in zip(fh, sizes):
+        assert w.num_particles(h) == n
+        w.remove_fluid(h)                       # Some(value)
+        with pytest.raises(Exception):
+            w.remove_fluid(h)                   # None
+    for h in bh:
+        w.remove_boundary(h)
+        with pytest.raises(Exception):
+            w.remove_boundary(h)
+    w.close()
