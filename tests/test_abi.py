@@ -78,3 +78,13 @@ def test_no_cpu_fallback_without_cuda():
     with pytest.raises(SphError) as e:
         LiquidWorld(particle_radius=0.05)
     assert e.value.status == 2  # SPH_ERR_CUDA
+
+
+def test_every_entry_point_cites_the_reference_and_is_in_the_integration_guide():
+    """include/sph.h declares the drop-in boundary: every entry point must appear in INTEGRATION.md (what it replaces in the
+    reference), and the header itself must cite reference files (file.rs:line) next to the declarations."""
+    header = open(os.path.join(ROOT, "include", "sph.h")).read()
+    guide = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in _declared_symbols() if s not in guide]
+    assert not missing, missing
+    assert len(re.findall(r"[a-z_0-9]+\.rs:\d+", header)) >= 30
