@@ -405,6 +405,53 @@ def timed_steps(world, sc, steps, barrier):
 timed_steps.per_step = []   # (step_ms, grid_ms) of every timed step on this rank: a one-off stall shows up here, not in the mean
 
 
+def pick_grid_order(args, cfg, world_size):
+    """Engine option Consts::xysub (SALVA_B200_XYSUB): 'rows' sorts the particles into (h/2 x h/2) columns with z running fastest, so
+    that the lanes of a warp gather consecutive records (profiles/r2_l1tex_wavefront_model.md).  It changes the order of every f32 sum
+    (not the contact sets), so it is only ever used after THIS run has checked it: both orders run as short subprocess probes that
+    carry the same parity block as the real line, and 'rows' is kept only if its parity passes and it is faster in the timed
+    free-fall steps without being slower in the settled block.  Anything going wrong in a probe => the default order."""
+    info = {"chosen": "h", "mode": args.grid_order}
+    if args.grid_order in ("h", "rows"):
+        info["chosen"] = args.grid_order
+        return info
+    if world_size != 1 or args.backend != 0 or cfg not in ("c2", "c3", "c4") or args.probe:
+        info["mode"] = "fixed (auto applies to one-GPU DFSPH dam-break configs)"
+        return info
+    import subprocess
+    probes = {}
+    for name in ("h", "rows"):
+        cmd = [sys.executable, os.path.abspath(__file__), "--config", cfg, "--gpus", "1", "--steps", "5", "--warmup", "3", "--no-cpu", "--probe",
+               "--grid-order", name, "--parity-n", str(args.parity_n)]
+        if args.n:
+            cmd += ["--n", str(args.n)]
+        if args.no_settled:
+            cmd += ["--no-settled"]
+        try:
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            d = json.loads(line[-1]) if line else None
+            if r.returncode != 0 or d is None:
+                probes[name] = {"error": "rc %d: %s" % (r.returncode, (r.stderr or "")[-200:].replace("\n", " | "))}
+            else:
+                probes[name] = {"ms_per_step": d["ms_per_step"], "parity_ok": bool((d.get("parity") or {}).get("ok")),
+                                "pair_ms": d["roofline"]["ms_per_launch_pair"], "neighbors_ms": d["phases"].get("neighbors_ms"),
+                                "grid_ms": d["phases"].get("grid_ms"),
+                                "settled_ms_per_step": (d.get("settled") or {}).get("ms_per_step"),
+                                "settled_error": (d.get("settled") or {}).get("error"), "seconds": round(time.perf_counter() - t0, 1)}
+        except Exception as e:  # timeout, unparsable output, ...
+            probes[name] = {"error": str(e)[:200]}
+    info["probes"] = probes
+    h, rows = probes.get("h", {}), probes.get("rows", {})
+    ok = ("error" not in h and "error" not in rows and rows.get("parity_ok") and h.get("parity_ok") and
+          not rows.get("settled_error") and rows["ms_per_step"] < 0.97 * h["ms_per_step"] and
+          (rows.get("settled_ms_per_step") is None or h.get("settled_ms_per_step") is None or
+           rows["settled_ms_per_step"] <= 1.02 * h["settled_ms_per_step"]))
+    info["chosen"] = "rows" if ok else "h"
+    return info
+
+
 def native_arm(args, rank, world_size):
     import torch
     import torch.distributed as dist
@@ -440,6 +487,8 @@ def native_arm(args, rank, world_size):
     if world_size > 1 and cfg not in ("c2", "c3", "c4"):
         raise SystemExit("multi-GPU runs need a dam-break config (c2, c3 or c4)")
     uid_fn = (lambda: slab.broadcast_unique_id(nccl_unique_id, rank, device=dev)) if world_size > 1 else None
+    grid_order = pick_grid_order(args, cfg, world_size)
+    os.environ["SALVA_B200_XYSUB"] = "2" if grid_order["chosen"] == "rows" else "1"   # read by every world this process creates
 
     # ---- parity before anything is timed -----------------------------------------------------------------------------
     parity = None
@@ -492,7 +541,7 @@ def native_arm(args, rank, world_size):
     hp_all = torch.empty((cap0, 3), dtype=torch.float32, pin_memory=True).numpy()
     hv_all = torch.empty((cap0, 3), dtype=torch.float32, pin_memory=True).numpy()
     world.read_fluid(f0, hp_all[:n0], hv_all[:n0])
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = 1 if args.probe else max(3, min(args.steps, 10))
     h2d = d2h = 0
     barrier()
     t0 = time.perf_counter()
@@ -516,6 +565,7 @@ def native_arm(args, rank, world_size):
     # to a dense cell grid).  One GPU only: the driver's scaling runs stay as short (and as safe) as possible.
     settled = None
     if not args.no_settled and world_size == 1:
+      try:
         sc2, w2, _ = make_world(compress=0.92)
         w2.step(sc2["dt"], sc2["gravity"])   # the first step only sees dt = 0 quantities (timestep_manager.rs:29-30)
         k2 = 8
@@ -531,6 +581,8 @@ def native_arm(args, rank, world_size):
                    "wall_ms_per_step": wall2 / k2 * 1e3, "max_neighbors": st2.get("max_neighbors"), "grid_dims": st2.get("grid_dims"),
                    "phases": {k: acc2[k] / k2 for k in sorted(acc2) if k.endswith("_ms")}}
         w2.close()
+      except Exception as e:   # the second measurement never costs the line
+        settled = {"error": str(e)[:300]}
 
     # ---- N > 1: the same per-GPU slice on ONE GPU (rank 0, the others wait), so the line carries its own weak-scaling reference
     slice_ref = None
@@ -595,6 +647,7 @@ def native_arm(args, rank, world_size):
             "iterations_per_step_mean": [float(np.mean([i[0] for i in iters])), float(np.mean([i[1] for i in iters]))],
             "phases": phases, "wall_ms_per_step": wall / args.steps * 1e3,
             "per_step_ms_rank0": {"step": [p[0] for p in per_step[:64]], "grid": [p[1] for p in per_step[:64]]},
+            "grid_order": grid_order,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "sph_fluid_write + sph_world_step + sph_fluid_read (pinned host buffers), all ranks"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
@@ -625,6 +678,10 @@ def main():
     ap.add_argument("--fast-sort", action="store_true", help="skip the deterministic in-cell ordering")
     ap.add_argument("--force-iters", type=int, nargs=2, default=None)
     ap.add_argument("--backend", type=int, default=0, help="0 = L1 gathers (default), 1 = tile/TMA shared-memory gathers")
+    ap.add_argument("--grid-order", default="auto", choices=["auto", "h", "rows"],
+                    help="particle order of the counting sort: h = cells of width h (z fastest), rows = x / y binned at h / 2 (SALVA_B200_XYSUB=2); "
+                         "auto (one GPU, DFSPH dam-break configs) = run both as short parity-checked probes and keep the faster one")
+    ap.add_argument("--probe", action="store_true", help="internal: short run of one grid order (no CPU arm, no e2e loop)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world_size = int(os.environ.get("WORLD_SIZE", 1))

@@ -280,6 +280,7 @@ struct sph_world {
     bool nb_valid = false, nb_pending = false;
     int nb[7] = {0, 0, 0, 0, 0, 0, 0};
     DBuf<int> d_nb;
+    int xysub = 1;              // row order (Consts::xysub, SALVA_B200_XYSUB): x / y bins per cell; one GPU, gather backend 0 only
     int zsub = 1;               // z-bins per cell of the counting sort (Consts::zsub, SALVA_B200_ZSUB).  Measured: 2..4 bins cut
                                 // the candidates by 17-25 % but k_neighbors does not get faster (-1 %) and the finer z order
                                 // costs the gather passes 10 % of their coalescing (profiles/r2_exp_k_zbins.md) => 1
@@ -384,6 +385,8 @@ void fill_static_consts(sph_world* w) {
     c.h2 = w->h * w->h;
     c.zsub = w->tile ? 1 : w->zsub;
     c.zsub_f = (float)c.zsub;
+    c.xysub = (w->tile || w->slab.active) ? 1 : w->xysub;  // slab worlds cut x into cell columns of width h: plain cells there
+    c.xysub_f = (float)c.xysub;
     c.h_reach = std::nextafter(w->h * 1.00001f, INFINITY);
     c.sigma = 8.0f / (3.14159265358979323846f * w->h * w->h * w->h);
     c.dsigma = c.sigma / w->h;
@@ -738,13 +741,14 @@ sph_status phase_grid(sph_world* w) {
     double ncell_d = (double)dims[0] * (double)dims[1] * (double)dims[2];
     if (ncell_d > 1.0e9) return w->fail(SPH_ERR_OOM, "dense cell grid too large: %lld x %lld x %lld cells of width h", dims[0], dims[1], dims[2]);
     const int zsub = w->tile ? 1 : w->zsub;  // z-bins per cell (sph_kernels.cuh Consts::zsub)
-    if (ncell_d * zsub > 2.0e9) return w->fail(SPH_ERR_OOM, "dense cell grid too large: %lld x %lld x %lld cells of width h", dims[0], dims[1], dims[2]);
-    size_t ncell = (size_t)dims[0] * dims[1] * dims[2] * zsub;
-    w->hc.ox = hb[0] - 1;
-    w->hc.oy = hb[1] - 1;
+    const int xys = (w->tile || w->slab.active) ? 1 : w->xysub;  // x / y bins per cell (row order, Consts::xysub)
+    if (ncell_d * zsub * xys * xys > 2.0e9) return w->fail(SPH_ERR_OOM, "dense cell grid too large: %lld x %lld x %lld cells of width h", dims[0], dims[1], dims[2]);
+    size_t ncell = (size_t)dims[0] * dims[1] * dims[2] * zsub * xys * xys;
+    w->hc.ox = (hb[0] - 1) * xys;
+    w->hc.oy = (hb[1] - 1) * xys;
     w->hc.oz = (hb[2] - 1) * zsub;
-    w->hc.nx = (int)dims[0];
-    w->hc.ny = (int)dims[1];
+    w->hc.nx = (int)dims[0] * xys;
+    w->hc.ny = (int)dims[1] * xys;
     w->hc.nz = (int)dims[2] * zsub;
     w->hc.ntx = (int)((dims[0] - 2 + TILE_X - 1) / TILE_X);
     w->hc.nty = (int)((dims[1] - 2 + TILE_Y - 1) / TILE_Y);
@@ -760,7 +764,8 @@ sph_status phase_grid(sph_world* w) {
     w->stats.grid_dims[2] = (uint32_t)dims[2];
     // fluid: counting sort by cell, then reorder every persistent array
     CU(cudaMemsetAsync(w->cstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));
-    LAUNCH(k_cell_hist, Nin, 256, w->pos[c].p + off, (uint32_t)Nin, w->cid.p, w->rank.p, w->cstart.p, dead, n_dead);
+    if (xys > 1) LAUNCH(k_cell_hist_xy, Nin, 256, w->pos[c].p + off, (uint32_t)Nin, w->cid.p, w->rank.p, w->cstart.p);  // (never a slab world: no dead slots)
+    else LAUNCH(k_cell_hist, Nin, 256, w->pos[c].p + off, (uint32_t)Nin, w->cid.p, w->rank.p, w->cstart.p, dead, n_dead);
     TRY(scan_exclusive(w, w->cstart.p, ncell + 1));
     LAUNCH(k_cell_scatter, Nin, 256, (uint32_t)Nin, w->cid.p, w->rank.p, w->cstart.p, w->perm.p);
     if (w->desc.deterministic)
@@ -792,7 +797,8 @@ sph_status phase_grid(sph_world* w) {
     w->b_reused = reuse_b;
     if (!reuse_b) CU(cudaMemsetAsync(w->bstart.p, 0, (ncell + 1) * sizeof(uint32_t), w->st));
     if (B && !reuse_b) {
-        LAUNCH(k_cell_hist, B, 256, w->bpos[bc].p, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p, (const uint32_t*)nullptr, 0u);
+        if (xys > 1) LAUNCH(k_cell_hist_xy, B, 256, w->bpos[bc].p, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p);
+        else LAUNCH(k_cell_hist, B, 256, w->bpos[bc].p, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p, (const uint32_t*)nullptr, 0u);
         TRY(scan_exclusive(w, w->bstart.p, ncell + 1));
         LAUNCH(k_cell_scatter, B, 256, (uint32_t)B, w->bcid.p, w->brank.p, w->bstart.p, w->bperm.p);
         if (w->desc.deterministic) LAUNCH(k_cell_sort, ncell, 256, (uint32_t)ncell, w->bstart.p, w->bperm.p, (const uint32_t*)nullptr, (const float4*)nullptr);
@@ -902,7 +908,8 @@ sph_status phase_neighbors(sph_world* w, sph_status (*speculative)(sph_world*) =
     if (B) {  // compute_boundary_volumes dfsph_solver.rs:72-96: the reference recomputes them every substep; they only
               // depend on the boundary positions, so they are reused while the boundaries are unchanged
         if (!w->b_reused) {
-            LAUNCH(k_boundary_volumes, B, 128, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->bvol.p, w->d_cnt.p, w->d_scal.p + 7);
+            if (w->hc.xysub > 1) LAUNCH(k_boundary_volumes_xy, B, 128, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->bvol.p, w->d_cnt.p, w->d_scal.p + 7);
+            else LAUNCH(k_boundary_volumes, B, 128, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->bvol.p, w->d_cnt.p, w->d_scal.p + 7);
             LAUNCH(k_set_w, B, 256, (uint32_t)B, w->bpos[bc].p, w->bvol.p);
         }
         for (auto& b : w->bounds)
@@ -919,6 +926,13 @@ sph_status phase_neighbors(sph_world* w, sph_status (*speculative)(sph_world*) =
             uint32_t sb = multi ? 32u : 16u;
             uint32_t cap = tile_cap(w, sb);
             TDISPATCH1(k_tile_neighbors, multi, sb, cap, w->pos[c].p, w->vel[c].p, w->cstart.p, cap, w->nbr16.p, w->cnt_f.p, maxcnt);
+        } else if (w->hc.xysub > 1) {  // row order
+            if (multi)
+                LAUNCH((k_neighbors_xy<true>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
+                       w->cnt_f.p, w->cnt_b.p, maxcnt);
+            else
+                LAUNCH((k_neighbors_xy<false>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
+                       w->cnt_f.p, w->cnt_b.p, maxcnt);
         } else if (multi) {
             LAUNCH((k_neighbors<true, false>), N, 128, w->pos[c].p, w->vel[c].p, w->cstart.p, w->bpos[bc].p, w->bvel[bc].p, w->bstart.p, w->nbr_f.p, w->nbr_b.p,
                    w->cnt_f.p, w->cnt_b.p, maxcnt, (cudaTextureObject_t)0);
@@ -1942,6 +1956,7 @@ sph_status sph_world_create(const sph_world_desc* desc, sph_world** out) {
     if (const char* t = getenv("SALVA_B200_NBR_TEX")) w->nbr_tex = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_FUSE_FOLD")) w->fuse_fold = atoi(t) != 0;
     if (const char* t = getenv("SALVA_B200_ZSUB")) w->zsub = std::min(8, std::max(1, atoi(t)));
+    if (const char* t = getenv("SALVA_B200_XYSUB")) w->xysub = std::min(4, std::max(1, atoi(t)));
     if (const char* t = getenv("SALVA_B200_UNI_EVAL")) w->uni_eval_mode = atoi(t);
     if (const char* t = getenv("SALVA_B200_UNI_UPD")) w->uni_upd_mode = atoi(t);
     {
@@ -2294,8 +2309,9 @@ static sph_status run_query(sph_world* w, AabbQuery q, const float mins[3], cons
     TRY(enter(w));
     const Consts& hc = w->hc;
     int lo[3], hi[3];
-    const int zs = hc.zsub > 0 ? hc.zsub : 1;  // the grid counts z in bins of h / zsub; the query box is in cells
-    const int go[3] = {hc.ox, hc.oy, hc.oz / zs}, gn[3] = {hc.nx, hc.ny, hc.nz / zs};
+    const int zs = hc.zsub > 0 ? hc.zsub : 1;  // the grid counts z in bins of h / zsub (and x, y in bins of h / xysub); the query box is in cells
+    const int xs = hc.xysub > 0 ? hc.xysub : 1;
+    const int go[3] = {hc.ox / xs, hc.oy / xs, hc.oz / zs}, gn[3] = {hc.nx / xs, hc.ny / xs, hc.nz / zs};
     for (int a = 0; a < 3; ++a) {  // hgrid.rs:41-52 keys, clipped IN FLOAT to the dense grid (cells outside hold nothing; +-inf / FLT_MAX bounds are legal)
         const float flo = std::floor(mins[a] / w->h), fhi = std::floor(maxs[a] / w->h);
         if (fhi < (float)go[a] || flo > (float)(go[a] + gn[a] - 1)) return SPH_OK;
@@ -2303,8 +2319,8 @@ static sph_status run_query(sph_world* w, AabbQuery q, const float mins[3], cons
         hi[a] = (int)std::fmin(fhi, (float)(go[a] + gn[a] - 1));
         if (hi[a] < lo[a]) return SPH_OK;
     }
-    q.lx = lo[0]; q.ly = lo[1]; q.lz = lo[2] * zs;
-    q.dx = hi[0] - lo[0] + 1; q.dy = hi[1] - lo[1] + 1; q.dz = (hi[2] - lo[2] + 1) * zs;
+    q.lx = lo[0] * xs; q.ly = lo[1] * xs; q.lz = lo[2] * zs;
+    q.dx = (hi[0] - lo[0] + 1) * xs; q.dy = (hi[1] - lo[1] + 1) * xs; q.dz = (hi[2] - lo[2] + 1) * zs;
     for (int a = 0; a < 3; ++a) { q.mins[a] = mins[a]; q.maxs[a] = maxs[a]; }
     q.radius = w->desc.particle_radius;
     q.slot_lo = w->own_begin;

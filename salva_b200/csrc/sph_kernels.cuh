@@ -47,6 +47,13 @@ struct Consts {
     // (2h + h/zsub instead of 3h of candidates).  x and y keep the reference's cells; zsub = 1 is the plain h-cell grid.
     int zsub;
     float zsub_f, h_reach;       // (float)zsub; h * (1 + 1e-5): covers every |dz| the f32 test d^2 <= h^2 can accept
+    // "row order" (SALVA_B200_XYSUB, one GPU, gather backend 0): x and y are binned `xysub` times finer than h (ox, oy, nx, ny then
+    // count BINS), z stays the run direction.  With xysub = 2 and the usual spacing h/2 every (x, y) bin column holds ONE line of
+    // particles along z, so the 32 lanes of a warp are 32 consecutive particles of a line and their k-th contacts are consecutive
+    // particles of a neighbouring line: a warp-wide gather touches ~4 cache lines instead of ~17 data-pipe wavefronts
+    // (profiles/r2_l1tex_wavefront_model.md).  Contact SETS are unchanged (k_neighbors_xy clips its rows like zrun does).
+    int xysub;
+    float xysub_f;
     int ntx, nty, ntz;           // tile grid (sph_tile.cuh): 2 x 2 cell columns x TILE_Z cells per tile
     uint32_t n_fluid, n_bound;   // particle totals (n_fluid counts owned + ghost slots of the sorted arrays)
     uint32_t i_begin, n_owned;   // owned slots [i_begin, i_begin + n_owned): everything on one GPU; the slab between the
@@ -88,6 +95,15 @@ __device__ __forceinline__ void zrun(float z, int cz, int& lo, int& hi) {
     }
     lo = max(zbin(__fsub_rd(z, C.h_reach)), (cz - 1) * C.zsub);
     hi = min(zbin(__fadd_ru(z, C.h_reach)), (cz + 2) * C.zsub - 1);
+}
+// The same two functions for x / y in row order (explicit sub-division factor; zbin / zrun above are left as they were validated).
+__device__ __forceinline__ int abin(float v, int sub, float subf) {
+    const float q = __fdiv_rn(v, C.h), fl = floorf(q);
+    return (int)fl * sub + min(sub - 1, (int)((q - fl) * subf));
+}
+__device__ __forceinline__ void arun(float v, int c, int sub, float subf, int& lo, int& hi) {
+    lo = max(abin(__fsub_rd(v, C.h_reach), sub, subf), (c - 1) * sub);
+    hi = min(abin(__fadd_ru(v, C.h_reach), sub, subf), (c + 2) * sub - 1);
 }
 
 // contacts.rs:285,322,366: (dx*dx + dy*dy) + dz*dz <= h*h with no contraction (rustc never fuses).
@@ -362,6 +378,17 @@ __global__ void k_cell_hist(const float4* __restrict__ pos, uint32_t n, uint32_t
     }
     float4 p = pos[i];
     uint32_t id = (uint32_t)cell_id(cell_coord(p.x), cell_coord(p.y), zbin(p.z));
+    cid[i] = id;
+    rank[i] = atomicAdd(&count[id], 1u);
+}
+
+// row order (Consts::xysub > 1): x and y binned finer than h
+__global__ void k_cell_hist_xy(const float4* __restrict__ pos, uint32_t n, uint32_t* __restrict__ cid, uint32_t* __restrict__ rank,
+                               uint32_t* __restrict__ count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos[i];
+    uint32_t id = (uint32_t)cell_id(abin(p.x, C.xysub, C.xysub_f), abin(p.y, C.xysub, C.xysub_f), zbin(p.z));
     cid[i] = id;
     rank[i] = atomicAdd(&count[id], 1u);
 }
@@ -681,6 +708,106 @@ k_neighbors(const float4* __restrict__ pos, const float4* __restrict__ vel, cons
         if (mf) atomicMax(&maxcnt[0], mf);
         if (mb) atomicMax(&maxcnt[1], mb);
     }
+}
+
+// Row order (Consts::xysub > 1): the same search over the bin rows within reach in x and y (5 x 5 rows of width h / 2 at xysub = 2
+// instead of 3 x 3 of width h; arun() clips exactly like zrun(), so the contact sets are the reference's).  A separate kernel so that
+// the default path above stays byte for byte what was validated.
+template <bool MULTI>
+__global__ void __launch_bounds__(128)
+k_neighbors_xy(const float4* __restrict__ pos, const float4* __restrict__ vel, const uint32_t* __restrict__ cstart,
+               const float4* __restrict__ bpos, const float4* __restrict__ bvel, const uint32_t* __restrict__ bstart,
+               uint32_t* __restrict__ nbr_f, uint32_t* __restrict__ nbr_b, uint32_t* __restrict__ cnt_f, uint32_t* __restrict__ cnt_b,
+               uint32_t* __restrict__ maxcnt /* [0]=fluid,[1]=boundary */) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nf = 0, nb = 0;
+    const bool owned = i < C.n_owned;
+    i += C.i_begin;
+    if (owned) {
+        float4 pi = pos[i];
+        uint32_t fi = MULTI ? fid_of(vel[i]) : 0u;
+        const int cx = cell_coord(pi.x), cy = cell_coord(pi.y), cz = cell_coord(pi.z);
+        int xlo, xhi, ylo, yhi, zlo, zhi;
+        arun(pi.x, cx, C.xysub, C.xysub_f, xlo, xhi);
+        arun(pi.y, cy, C.xysub, C.xysub_f, ylo, yhi);
+        zrun(pi.z, cz, zlo, zhi);
+        uint32_t* wp = nbr_f + (size_t)i * 4;
+        const size_t gstep = (size_t)C.stride * 4 - 4;
+        for (int bx = xlo; bx <= xhi; ++bx)
+            for (int by = ylo; by <= yhi; ++by) {
+                const int lo = cell_id(bx, by, zlo), hi = lo + (zhi - zlo) + 1;
+                scan_run<false>(
+                    pi, pos, cstart[lo], cstart[hi],
+                    [&](uint32_t j) {
+                        if (!MULTI) return true;
+                        uint32_t fj = fid_of(__ldg(&vel[j]));
+                        return fi == fj || groups_test(C.fluids[fi].memberships, C.fluids[fi].filter, C.fluids[fj].memberships, C.fluids[fj].filter);
+                    },
+                    [&](uint32_t j) {
+                        if (nf < C.cap_f) *wp = j;
+                        ++nf;
+                        ++wp;
+                        if ((nf & 3u) == 0u) wp += gstep;
+                    });
+                if (C.n_bound)
+                    scan_run(
+                        pi, bpos, bstart[lo], bstart[hi],
+                        [&](uint32_t j) {
+                            uint32_t bj = fid_of(__ldg(&bvel[j]));
+                            return groups_test(C.fluids[fi].memberships, C.fluids[fi].filter, C.bounds[bj].memberships, C.bounds[bj].filter);
+                        },
+                        [&](uint32_t j) {
+                            if (nb < C.cap_b) nbr_b[(size_t)nb * C.stride + i] = j;
+                            ++nb;
+                        });
+            }
+        for (uint32_t t = nf; t < ((nf + 3u) & ~3u) && t < C.cap_f; ++t) *wp++ = i;  // pad the last group
+        cnt_f[i] = nf;
+        cnt_b[i] = nb;
+    }
+    uint32_t mf = nf, mb = nb;
+    for (int o = 16; o > 0; o >>= 1) {
+        mf = max(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+        mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mf) atomicMax(&maxcnt[0], mf);
+        if (mb) atomicMax(&maxcnt[1], mb);
+    }
+}
+// boundary volumes in row order: every bin of the 3 x 3 x 3 reference cells around the particle
+__global__ void __launch_bounds__(128)
+k_boundary_volumes_xy(const float4* __restrict__ bpos, const float4* __restrict__ bvel, const uint32_t* __restrict__ bstart, float* __restrict__ bvol,
+                      unsigned long long* __restrict__ ncontacts, int* __restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0;
+    if (i < C.n_bound) {
+        float4 pi = bpos[i];
+        uint32_t bi = fid_of(bvel[i]);
+        const int cx = cell_coord(pi.x), cy = cell_coord(pi.y), cz = cell_coord(pi.z);
+        float den = 0.f;
+        for (int bx = (cx - 1) * C.xysub; bx < (cx + 2) * C.xysub; ++bx)
+            for (int by = (cy - 1) * C.xysub; by < (cy + 2) * C.xysub; ++by) {
+                const int base = cell_id(bx, by, (cz - 1) * C.zsub);
+                const uint32_t s = bstart[base], e = bstart[base + 3 * C.zsub];
+                for (uint32_t j = s; j < e; ++j) {
+                    float4 pj = __ldg(&bpos[j]);
+                    float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                    float d2 = dist2_exact(dx, dy, dz);
+                    if (d2 <= C.h2) {
+                        uint32_t bj = fid_of(__ldg(&bvel[j]));
+                        if (bi == bj || groups_test(C.bounds[bi].memberships, C.bounds[bi].filter, C.bounds[bj].memberships, C.bounds[bj].filter)) {
+                            den += C.kgen ? kernel_w_kind(C.kw, __fsqrt_rn(d2)) : kernel_w(sqrtf(d2));
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        if (den == 0.f) atomicOr(err, 1);
+        bvol[i] = 1.0f / den;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(ncontacts, (unsigned long long)cnt);
 }
 
 // a4: compute_boundary_volumes dfsph_solver.rs:72-96 — vol_b = 1 / sum_{b'} W_bb' over boundary-boundary
